@@ -1,0 +1,201 @@
+"""ctypes binding of libccvpe_b200.so (the C ABI declared in include/ccvpe_b200.h).
+
+There is NO fallback: if the shared library is missing or a call fails, a `CcvpeError` is raised.  torch is used only
+to own device memory and the stream; every pointer handed to the library is `tensor.data_ptr()`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import torch
+
+from . import build as _build
+
+F32, BF16 = 0, 1
+BACKEND_AUTO, BACKEND_SIMT, BACKEND_TCGEN05 = 0, 1, 2
+
+EXPORTED_SYMBOLS = (
+    "ccvpe_abi_version", "ccvpe_last_error", "ccvpe_launch_count", "ccvpe_reset_launch_count",
+    "ccvpe_grd_descriptor", "ccvpe_igemm", "ccvpe_match_scratch_elems", "ccvpe_match_level",
+    "ccvpe_softmax_scratch_elems", "ccvpe_softmax_heatmap", "ccvpe_ori_normalize",
+    "ccvpe_pose_scratch_bytes", "ccvpe_pose_decode",
+)
+
+
+class CcvpeError(RuntimeError):
+    pass
+
+
+class IgemmDesc(C.Structure):
+    """Mirror of `ccvpe_igemm_desc` (include/ccvpe_b200.h)."""
+    _fields_ = [
+        ("a0", C.c_void_p), ("a1", C.c_void_p),
+        ("c0", C.c_int32), ("c1", C.c_int32), ("ld0", C.c_int32), ("ld1", C.c_int32),
+        ("B", C.c_int32), ("Hin", C.c_int32), ("Win", C.c_int32), ("Hout", C.c_int32), ("Wout", C.c_int32),
+        ("stride", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32), ("pad", C.c_int32),
+        ("N", C.c_int32), ("dtype", C.c_int32),
+        ("w_kn", C.c_void_p), ("w_nk", C.c_void_p),
+        ("bias", C.c_void_p), ("row_scale", C.c_void_p), ("row_r1", C.c_void_p), ("r1_w", C.c_void_p),
+        ("relu", C.c_int32), ("out_mode", C.c_int32), ("out_dtype", C.c_int32), ("ldo", C.c_int32),
+        ("out", C.c_void_p),
+        ("backend", C.c_int32),
+    ]
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load() -> C.CDLL:
+    """Loads the in-tree shared library (never builds implicitly: the .so ships with the repo snapshot)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise CcvpeError("%s not found -- run `python -m ccvpe_b200.build` (or __graft_entry__.build()); "
+                         "there is no CPU / PyTorch fallback for the post-encoder path" % path)
+    lib = C.CDLL(path)
+    lib.ccvpe_abi_version.restype = C.c_int
+    lib.ccvpe_last_error.restype = C.c_char_p
+    lib.ccvpe_launch_count.restype = C.c_int64
+    lib.ccvpe_reset_launch_count.restype = None
+    lib.ccvpe_grd_descriptor.restype = C.c_int
+    lib.ccvpe_grd_descriptor.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ccvpe_igemm.restype = C.c_int
+    lib.ccvpe_igemm.argtypes = [C.POINTER(IgemmDesc), C.c_void_p]
+    lib.ccvpe_match_scratch_elems.restype = C.c_int64
+    lib.ccvpe_match_scratch_elems.argtypes = [C.c_int, C.c_int, C.c_int]
+    lib.ccvpe_match_level.restype = C.c_int
+    lib.ccvpe_match_level.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_int, C.c_uint32,
+                                      C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_int, C.c_void_p]
+    lib.ccvpe_softmax_scratch_elems.restype = C.c_int64
+    lib.ccvpe_softmax_scratch_elems.argtypes = [C.c_int, C.c_int64]
+    lib.ccvpe_softmax_heatmap.restype = C.c_int
+    lib.ccvpe_softmax_heatmap.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]
+    lib.ccvpe_ori_normalize.restype = C.c_int
+    lib.ccvpe_ori_normalize.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_void_p]
+    lib.ccvpe_pose_scratch_bytes.restype = C.c_int64
+    lib.ccvpe_pose_scratch_bytes.argtypes = [C.c_int, C.c_int64]
+    lib.ccvpe_pose_decode.restype = C.c_int
+    lib.ccvpe_pose_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p]
+    if lib.ccvpe_abi_version() != 1:
+        raise CcvpeError("libccvpe_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        raise CcvpeError("%s failed (%d): %s" % (what, rc, load().ccvpe_last_error().decode()))
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    if dt == torch.float32:
+        return F32
+    if dt == torch.bfloat16:
+        return BF16
+    raise CcvpeError("unsupported dtype %s (float32 / bfloat16 only)" % dt)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise CcvpeError("ccvpe_b200 kernels need CUDA tensors (got a %s tensor); there is no CPU fallback"
+                             % t.device.type)
+
+
+def launch_count() -> int:
+    return int(load().ccvpe_launch_count())
+
+
+def reset_launch_count():
+    load().ccvpe_reset_launch_count()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# thin typed wrappers (allocate nothing; shapes are the caller's business)
+# ------------------------------------------------------------------------------------------------------------------
+def grd_descriptor(feat: torch.Tensor, w1, b1, w2, b2, out: torch.Tensor, scratch: torch.Tensor):
+    """feat: logical [B, K, H, W] (any strides); out fp32 [B, W*c]."""
+    _require_cuda(feat, w1, b1, w2, b2, out, scratch)
+    B, K, H, W = feat.shape
+    sb, sk, sh, sw = feat.stride()
+    c = w1.shape[0]
+    _check(load().ccvpe_grd_descriptor(_ptr(feat), dtype_code(feat.dtype), B, K, H, W, sb, sk, sh, sw,
+                                       _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), c, _ptr(out), _ptr(scratch), _stream()),
+           "ccvpe_grd_descriptor")
+
+
+def igemm(desc: IgemmDesc):
+    _check(load().ccvpe_igemm(C.byref(desc), _stream()), "ccvpe_igemm")
+
+
+def match_scratch_elems(B: int, Cch: int, n_rolls: int) -> int:
+    return int(load().ccvpe_match_scratch_elems(B, Cch, n_rolls))
+
+
+def match_level(x: torch.Tensor, g: torch.Tensor, offset: int, shifts: Sequence[int], max_mask: int,
+                scores=None, scores_cl=None, max_out=None, inv_norm=None, xhat=None, scratch=None,
+                backend: int = BACKEND_AUTO):
+    """x channels-last [B, H, W, C]; g fp32 [B, L]."""
+    _require_cuda(x, g, scores, scores_cl, max_out, inv_norm, xhat, scratch)
+    B, H, W, Cch = x.shape
+    n = len(shifts)
+    arr = (C.c_int32 * n)(*[int(s) for s in shifts])
+    ld_cl = 0 if scores_cl is None else scores_cl.shape[-1]
+    _check(load().ccvpe_match_level(_ptr(x), dtype_code(x.dtype), B, H * W, Cch, _ptr(g), g.shape[1], int(offset), arr,
+                                    n, C.c_uint32(max_mask & 0xFFFFFFFF), _ptr(scores), _ptr(scores_cl), ld_cl,
+                                    _ptr(max_out), _ptr(inv_norm), _ptr(xhat), _ptr(scratch), backend, _stream()),
+           "ccvpe_match_level")
+
+
+def softmax_heatmap(logits: torch.Tensor, heatmap: torch.Tensor, scratch: torch.Tensor):
+    _require_cuda(logits, heatmap, scratch)
+    B, n = logits.shape
+    _check(load().ccvpe_softmax_heatmap(_ptr(logits), _ptr(heatmap), B, n, _ptr(scratch), _stream()),
+           "ccvpe_softmax_heatmap")
+
+
+def softmax_scratch_elems(B: int, n: int) -> int:
+    return int(load().ccvpe_softmax_scratch_elems(B, n))
+
+
+def ori_normalize(x_cl: torch.Tensor, out: torch.Tensor):
+    """x_cl channels-last [B, H, W, ld>=2]; out fp32 [B, 2, H, W]."""
+    _require_cuda(x_cl, out)
+    B, H, W, ld = x_cl.shape
+    _check(load().ccvpe_ori_normalize(_ptr(x_cl), dtype_code(x_cl.dtype), ld, _ptr(out), B, H * W, _stream()),
+           "ccvpe_ori_normalize")
+
+
+def pose_scratch_bytes(B: int, n: int) -> int:
+    return int(load().ccvpe_pose_scratch_bytes(B, n))
+
+
+def pose_decode(heatmap: torch.Tensor, ori: torch.Tensor, idx, rc, cs, angle, valid, scratch):
+    _require_cuda(heatmap, ori, idx, rc, cs, angle, valid, scratch)
+    B = heatmap.shape[0]
+    H, W = heatmap.shape[-2:]
+    _check(load().ccvpe_pose_decode(_ptr(heatmap), _ptr(ori), B, H, W, _ptr(idx), _ptr(rc), _ptr(cs), _ptr(angle),
+                                    _ptr(valid), _ptr(scratch), _stream()), "ccvpe_pose_decode")

@@ -1,0 +1,87 @@
+// Shared helpers for libccvpe_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/ccvpe_b200.h"
+
+namespace ccvpe {
+
+// ---- error reporting -------------------------------------------------------------------------------------------
+char* last_error_buffer();          // thread-local, 512 bytes
+int64_t& launch_counter();          // thread-local
+
+inline int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(last_error_buffer(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CCVPE_REQUIRE(cond, ...)                                           \
+  do {                                                                     \
+    if (!(cond)) return ::ccvpe::fail(CCVPE_ERR_BAD_ARGUMENT, __VA_ARGS__); \
+  } while (0)
+
+inline int check_launch(const char* what) {
+  launch_counter() += 1;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(CCVPE_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  return CCVPE_OK;
+}
+
+#define CCVPE_LAUNCH_CHECK(what)                \
+  do {                                          \
+    int _rc = ::ccvpe::check_launch(what);      \
+    if (_rc != CCVPE_OK) return _rc;            \
+  } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int sm_count();  // cached cudaDevAttrMultiProcessorCount of the current device (148 on B200)
+
+// ---- element access ----------------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ float to_float(T v);
+template <> __device__ __forceinline__ float to_float<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_float<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T> __device__ __forceinline__ T from_float(float v);
+template <> __device__ __forceinline__ float from_float<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_float<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// load 4 consecutive elements as floats (pointer must be 4-element aligned)
+__device__ __forceinline__ float4 load4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 load4(const __nv_bfloat16* p) {
+  uint2 raw = *reinterpret_cast<const uint2*>(p);
+  __nv_bfloat162 lo = *reinterpret_cast<__nv_bfloat162*>(&raw.x);
+  __nv_bfloat162 hi = *reinterpret_cast<__nv_bfloat162*>(&raw.y);
+  float2 a = __bfloat1622float2(lo), b = __bfloat1622float2(hi);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void store4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void store4(__nv_bfloat16* p, float4 v) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+  uint2 raw;
+  raw.x = *reinterpret_cast<uint32_t*>(&lo);
+  raw.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p) = raw;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+}  // namespace ccvpe

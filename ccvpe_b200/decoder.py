@@ -1,0 +1,270 @@
+"""Host-side orchestration of the CUDA hot path: everything `CVM_*.forward` does after the two encoders.
+
+One `PostEncoderPipeline` per model instance.  It owns (a) a derived, non-persistent cache of re-laid-out weights
+(the module's parameters keep the reference's shapes and names so checkpoints load strictly; the cache is rebuilt
+whenever a parameter's version counter or storage changes) and (b) the sequence of C-ABI calls.  There is no
+PyTorch or CPU fallback in here: every stage is a kernel of libccvpe_b200.so.
+
+Data layout in HBM: activations are channels-last [B, H, W, C] in the pipeline dtype (fp32 parity path, bf16
+throughput path); nothing is ever concatenated -- `cat([max, normalize(x)])` becomes a row-scale + rank-1 epilogue of
+the transposed-conv GEMM and `cat([x, skip])` a K-split over two sources of the conv GEMM.  The nine tensors handed
+back to the caller are fp32 in the reference's NCHW shapes (reference models.py:343).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import cabi
+from .specs import ENCODER_CHANNELS, SKIP_BLOCKS, SKIP_CHANNELS, VariantSpec, loc_roll_indices
+
+SCORES_CL_PAD = 32  # channel stride of the channels-last copy of the level-1 score volume (ori decoder input)
+
+
+def _cl(t: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """Logical NCHW tensor -> channels-last [B, H, W, C] contiguous in `dtype` (free if it already is)."""
+    v = t.permute(0, 2, 3, 1)
+    if v.dtype != dtype:
+        v = v.to(dtype)
+    return v.contiguous()
+
+
+class PostEncoderPipeline:
+    def __init__(self, module: torch.nn.Module, spec: VariantSpec, ori_noise: Optional[float] = None):
+        self._module = [module]          # list: do not register the owner as a sub-module
+        self.spec = spec
+        self.ori_noise = ori_noise
+        self.backend = cabi.BACKEND_AUTO
+        self._cache: Dict[torch.dtype, dict] = {}
+        self._sig = None
+
+    # -- derived weight cache ---------------------------------------------------------------------------------
+    def _params(self) -> Dict[str, torch.Tensor]:
+        return {k: v for k, v in self._module[0].named_parameters()
+                if not k.startswith(("grd_efficientnet.", "sat_efficientnet."))}
+
+    def _signature(self, params):
+        return tuple((k, p.data_ptr(), p._version, p.device) for k, p in params.items())
+
+    @torch.no_grad()
+    def _weights(self, dtype: torch.dtype) -> dict:
+        params = self._params()
+        sig = self._signature(params)
+        if sig != self._sig:
+            self._cache.clear()
+            self._sig = sig
+        if dtype in self._cache:
+            return self._cache[dtype]
+        spec = self.spec
+        f32 = lambda t: t.detach().to(torch.float32).contiguous()
+        w: dict = {}
+        # a1 ground heads
+        w["heads"] = []
+        for l in range(1, 7):
+            w1 = params["grd_feature_to_descriptor%d.0.weight" % l]
+            w["heads"].append((f32(w1.reshape(w1.shape[0], -1)),
+                               f32(params["grd_feature_to_descriptor%d.0.bias" % l]),
+                               f32(params["grd_feature_to_descriptor%d.2.weight" % l].reshape(-1)),
+                               f32(params["grd_feature_to_descriptor%d.2.bias" % l])))
+        # a3 aerial cell descriptors: Linear(5120 -> D) with the 5120 axis ordered (c, dh, dw) == conv k2 s2
+        lw = params["sat_feature_to_descriptors.1.weight"].detach()
+        D = lw.shape[0]
+        w["cell"] = dict(w_kn=lw.view(D, ENCODER_CHANNELS, 2, 2).permute(2, 3, 1, 0).reshape(4, ENCODER_CHANNELS, D)
+                         .to(dtype).contiguous(), bias=f32(params["sat_feature_to_descriptors.1.bias"]))
+
+        def deconv(name: str, lead: int, lead_pad: int):
+            """ConvTranspose2d weight [Cin, Cout, 2, 2] -> GEMM B [1][K][4*Cout], N ordered (i, j, co).
+            lead > 0: the first `lead` input channels are a separate source padded to `lead_pad` channels;
+            lead == -1: the first input channel (the max score) becomes the rank-1 epilogue vector."""
+            W = params[name + ".weight"].detach()
+            cout = W.shape[1]
+            out = dict(bias=f32(params[name + ".bias"].detach().repeat(4)), cout=cout)
+            if lead == -1:
+                out["r1_w"] = f32(W[0].permute(1, 2, 0).reshape(4 * cout))
+                W = W[1:]
+            elif lead > 0:
+                pad = torch.zeros((lead_pad - lead,) + tuple(W.shape[1:]), dtype=W.dtype, device=W.device)
+                W = torch.cat([W[:lead], pad, W[lead:]], dim=0)
+            out["w_kn"] = W.permute(0, 2, 3, 1).reshape(1, W.shape[0], 4 * cout).to(dtype).contiguous()
+            return out
+
+        def conv(name: str):
+            W = params[name + ".weight"].detach()        # [Cout, Cin, 3, 3]
+            return dict(w_kn=W.permute(2, 3, 1, 0).reshape(9, W.shape[1], W.shape[0]).to(dtype).contiguous(),
+                        bias=f32(params[name + ".bias"]), cout=W.shape[0])
+
+        w["loc"] = [dict(deconv=deconv("deconv%d" % n, -1, 0), conv_a=conv("conv%d.0" % n), conv_b=conv("conv%d.2" % n))
+                    for n in range(6, 0, -1)]
+        w["ori"] = [dict(deconv=deconv("deconv%d_ori" % n, spec.n_rolls if n == 6 else 0, SCORES_CL_PAD),
+                         conv_a=conv("conv%d_ori.0" % n), conv_b=conv("conv%d_ori.2" % n)) for n in range(6, 0, -1)]
+        self._cache[dtype] = w
+        return w
+
+    # -- kernel helpers ---------------------------------------------------------------------------------------
+    def _igemm(self, a0, c0, a1, c1, B, Hin, Win, Hout, Wout, stride, k, pad, N, dtype, wt, out, out_mode, ldo,
+               relu=False, row_scale=None, row_r1=None, r1_w=None):
+        d = cabi.IgemmDesc()
+        d.a0, d.a1 = a0.data_ptr(), (a1.data_ptr() if a1 is not None else None)
+        d.c0, d.c1 = c0, c1
+        d.ld0, d.ld1 = a0.shape[-1], (a1.shape[-1] if a1 is not None else 0)
+        d.B, d.Hin, d.Win, d.Hout, d.Wout = B, Hin, Win, Hout, Wout
+        d.stride, d.kh, d.kw, d.pad = stride, k, k, pad
+        d.N, d.dtype = N, cabi.dtype_code(dtype)
+        d.w_kn = wt["w_kn"].data_ptr()
+        d.w_nk = wt["w_nk"].data_ptr() if "w_nk" in wt else None
+        d.bias = wt["bias"].data_ptr()
+        d.row_scale = row_scale.data_ptr() if row_scale is not None else None
+        d.row_r1 = row_r1.data_ptr() if row_r1 is not None else None
+        d.r1_w = r1_w.data_ptr() if r1_w is not None else None
+        d.relu, d.out_mode, d.out_dtype, d.ldo = int(relu), out_mode, cabi.dtype_code(out.dtype), ldo
+        d.out = out.data_ptr()
+        d.backend = self.backend
+        cabi.igemm(d)
+
+    def _deconv(self, wt, a0, c0, a1, c1, dtype, row_scale=None, row_r1=None):
+        """ConvTranspose2d(k2, s2) as GEMM + pixel shuffle (reference models.py:109-124)."""
+        B, H, W, _ = a0.shape
+        cout = wt["cout"]
+        out = torch.empty((B, 2 * H, 2 * W, cout), dtype=dtype, device=a0.device)
+        self._igemm(a0, c0, a1, c1, B, H, W, H, W, 1, 1, 0, 4 * cout, dtype, wt, out, 1, cout,
+                    row_scale=row_scale, row_r1=row_r1, r1_w=wt.get("r1_w") if row_r1 is not None else None)
+        return out
+
+    def _conv3(self, wt, a0, a1, dtype, relu, planar_f32=False, out_f32=False):
+        """3x3 pad-1 conv over the K-concatenation of a0 and a1 (reference models.py:42-47)."""
+        B, H, W, c0 = a0.shape
+        c1 = a1.shape[-1] if a1 is not None else 0
+        cout = wt["cout"]
+        if planar_f32:
+            out = torch.empty((B, cout, H, W), dtype=torch.float32, device=a0.device)
+            mode, ldo = 2, 0
+        else:
+            out = torch.empty((B, H, W, cout), dtype=torch.float32 if out_f32 else dtype, device=a0.device)
+            mode, ldo = 0, cout
+        self._igemm(a0, c0, a1, c1, B, H, W, H, W, 1, 3, 1, cout, dtype, wt, out, mode, ldo, relu=relu)
+        return out
+
+    # -- the path ---------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def run(self, grd_feat: torch.Tensor, sat_feat: torch.Tensor, multiscale: Sequence[torch.Tensor],
+            dtype: torch.dtype) -> Tuple[torch.Tensor, ...]:
+        if not (grd_feat.is_cuda and sat_feat.is_cuda):
+            raise cabi.CcvpeError("the post-encoder path runs on CUDA only (sm_100a); there is no CPU fallback")
+        spec = self.spec
+        w = self._weights(dtype)
+        dev = sat_feat.device
+        B = sat_feat.shape[0]
+        f32 = torch.float32
+
+        # a1 -- six ground descriptors (fp32, tiny)
+        if grd_feat.dtype not in (torch.float32, torch.bfloat16):
+            grd_feat = grd_feat.float()
+        Bg, Kg, Hg, Wg = grd_feat.shape
+        if Hg != spec.grd_feat_h:
+            raise cabi.CcvpeError("ground feature height %d does not match the %s heads (%d)" % (Hg, spec.name,
+                                                                                               spec.grd_feat_h))
+        scratch_g = torch.empty(Bg * Kg * Wg, dtype=f32, device=dev)
+        g: List[torch.Tensor] = []
+        for l in range(6):
+            w1, b1, w2, b2 = w["heads"][l]
+            out = torch.empty((Bg, Wg * w1.shape[0]), dtype=f32, device=dev)
+            cabi.grd_descriptor(grd_feat, w1, b1, w2, b2, out, scratch_g)
+            g.append(out)
+
+        # a3 -- aerial cell descriptors: [B,16,16,1280] -> [B,8,8,D]
+        fs = _cl(sat_feat, dtype)
+        Hs, Ws = fs.shape[1], fs.shape[2]
+        D = spec.sat_dim
+        x = torch.empty((B, Hs // 2, Ws // 2, D), dtype=dtype, device=dev)
+        self._igemm(fs, ENCODER_CHANNELS, None, 0, B, Hs, Ws, Hs // 2, Ws // 2, 2, 2, 0, D, dtype, w["cell"], x, 0, D)
+        skips = [_cl(multiscale[i], dtype) for i in SKIP_BLOCKS]
+
+        loc_rolls = loc_roll_indices(spec, self.ori_noise)
+        scores_out: List[torch.Tensor] = []
+        scores_cl = xhat = None
+        logits = None
+        for l in range(6):
+            _, H, W, C = x.shape
+            L = g[l].shape[1]
+            if spec.window_len(C, L) != L or L > C:
+                raise cabi.CcvpeError("level %d: ground descriptor length %d incompatible with %d aerial channels"
+                                      % (l + 1, L, C))
+            stride = spec.roll_strides[l]
+            if l == 0 and self.ori_noise is not None:
+                # full sweep for the orientation decoder, prior-limited subset for the max (models.py:489-511)
+                if spec.n_rolls * stride != C:
+                    raise cabi.CcvpeError("prior-limited matching needs a full-circle level-1 map")
+                rolls = list(range(spec.n_rolls))
+                mask = 0
+                for i in loc_rolls:
+                    mask |= 1 << (i % spec.n_rolls)
+            else:
+                rolls = loc_rolls
+                mask = (1 << len(rolls)) - 1
+            R = len(rolls)
+            scores = torch.empty((B, R, H, W), dtype=f32, device=dev)
+            mx = torch.empty((B, H, W), dtype=f32, device=dev)
+            inv = torch.empty((B, H, W), dtype=f32, device=dev)
+            if l == 0:
+                scores_cl = torch.empty((B, H, W, SCORES_CL_PAD), dtype=dtype, device=dev)
+                xhat = torch.empty_like(x)
+            scratch = torch.empty(cabi.match_scratch_elems(B, C, R), dtype=f32, device=dev)
+            cabi.match_level(x, g[l], spec.window_offset(C, L), [i * stride for i in rolls], mask, scores=scores,
+                             scores_cl=scores_cl if l == 0 else None, max_out=mx, inv_norm=inv,
+                             xhat=xhat if l == 0 else None, scratch=scratch,
+                             backend=cabi.BACKEND_SIMT if self.backend == cabi.BACKEND_SIMT else cabi.BACKEND_AUTO)
+            scores_out.append(scores)
+            lw = w["loc"][l]
+            up = self._deconv(lw["deconv"], x, C, None, 0, dtype, row_scale=inv, row_r1=mx)
+            if l < 5:
+                h = self._conv3(lw["conv_a"], up, skips[l], dtype, relu=True)
+                x = self._conv3(lw["conv_b"], h, None, dtype, relu=False)
+            else:
+                h = self._conv3(lw["conv_a"], up, None, dtype, relu=True)
+                logits = self._conv3(lw["conv_b"], h, None, dtype, relu=False, planar_f32=True)  # [B,1,512,512]
+
+        # a10 -- heatmap
+        Hh, Wh = logits.shape[-2:]
+        logits_flat = logits.view(B, Hh * Wh)
+        heatmap = torch.empty_like(logits)
+        sm_scratch = torch.empty(cabi.softmax_scratch_elems(B, Hh * Wh), dtype=f32, device=dev)
+        cabi.softmax_heatmap(logits_flat, heatmap.view(B, Hh * Wh), sm_scratch)
+
+        # a11 -- orientation decoder (no matching inside; input = [scores_1, normalize(x_1)], models.py:323)
+        o = None
+        for l in range(6):
+            ow = w["ori"][l]
+            if l == 0:
+                o = self._deconv(ow["deconv"], scores_cl, SCORES_CL_PAD, xhat, D, dtype)
+            else:
+                o = self._deconv(ow["deconv"], o, o.shape[-1], None, 0, dtype)
+            if l < 5:
+                o = self._conv3(ow["conv_a"], o, skips[l], dtype, relu=True)
+                o = self._conv3(ow["conv_b"], o, None, dtype, relu=False)
+            else:
+                o = self._conv3(ow["conv_a"], o, None, dtype, relu=True)
+                o = self._conv3(ow["conv_b"], o, None, dtype, relu=False, out_f32=True)   # [B,512,512,2] fp32
+        ori = torch.empty((B, 2, Hh, Wh), dtype=f32, device=dev)
+        cabi.ori_normalize(o, ori)                                                        # a12
+        return (logits_flat, heatmap, ori, *scores_out)
+
+
+@torch.no_grad()
+def decode_pose(heatmap: torch.Tensor, ori: torch.Tensor) -> Dict[str, torch.Tensor]:
+    """a13 -- device-side replacement of the scripts' NumPy decode (reference train_VIGOR.py:290-326).
+
+    heatmap [B,1,H,W] fp32, ori [B,2,H,W] fp32 (CUDA).  Returns CUDA tensors: idx int64[B], rc int32[B,2] (row, col),
+    cs float32[B,2], angle float64[B] (degrees, NaN where invalid), valid uint8[B]."""
+    if not heatmap.is_cuda:
+        raise cabi.CcvpeError("decode_pose needs CUDA tensors; there is no CPU fallback")
+    heatmap = heatmap.contiguous().float()
+    ori = ori.contiguous().float()
+    B, _, H, W = heatmap.shape
+    dev = heatmap.device
+    out = dict(idx=torch.empty(B, dtype=torch.int64, device=dev), rc=torch.empty((B, 2), dtype=torch.int32, device=dev),
+               cs=torch.empty((B, 2), dtype=torch.float32, device=dev),
+               angle=torch.empty(B, dtype=torch.float64, device=dev), valid=torch.empty(B, dtype=torch.uint8, device=dev))
+    scratch = torch.empty(cabi.pose_scratch_bytes(B, H * W), dtype=torch.uint8, device=dev)
+    cabi.pose_decode(heatmap, ori, out["idx"], out["rc"], out["cs"], out["angle"], out["valid"], scratch)
+    return out

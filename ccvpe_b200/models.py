@@ -1,0 +1,197 @@
+"""Drop-in replacements of the reference's four models (reference models.py:49, :346, :655, :954).
+
+Same constructor signatures, same `forward(grd, sat)` 9-tuple, same `state_dict()` keys and shapes (a reference
+checkpoint loads with strict=True).  The two EfficientNet-B0 encoders stay PyTorch (`efficientnet.py`); everything
+after them runs as sm_100a CUDA kernels through the C ABI (`decoder.PostEncoderPipeline`).  The `nn.Conv2d` /
+`nn.ConvTranspose2d` / `nn.Linear` sub-modules below are parameter containers only -- their `forward` is never
+called, and there is no PyTorch fallback for the decoder.
+
+Extras over the reference (all optional, defaults reproduce the reference's fp32 behaviour):
+  * `set_precision("bf16")`  -- encoders in bf16 channels-last, decoder kernels on tcgen05 tensor cores;
+  * `decode_pose(heatmap, ori)` -- the scripts' NumPy argmax/orientation decode as a CUDA kernel;
+  * `localize(grd, sat)`     -- forward + decode in one call, returns only the small pose tensors.
+"""
+from __future__ import annotations
+
+import copy
+from typing import Optional
+
+import torch
+from torch import nn
+
+from . import cabi
+from .decoder import PostEncoderPipeline, decode_pose
+from .efficientnet import EfficientNetB0
+from .specs import KITTI, OXFORD, SKIP_CHANNELS, VIGOR, VariantSpec
+
+
+class _Permute(nn.Module):
+    """Parameter-free placeholder so that the ground heads keep the reference's Sequential indices (0 and 2)."""
+
+    def __init__(self, *dims):
+        super().__init__()
+        self.dims = dims
+
+    def forward(self, x):
+        return x.permute(*self.dims)
+
+
+def _double_conv(cin: int, cout: int) -> nn.Sequential:
+    return nn.Sequential(nn.Conv2d(cin, cout, 3, padding=1), nn.ReLU(inplace=True), nn.Conv2d(cout, cout, 3, padding=1))
+
+
+def _final_conv(cout: int) -> nn.Sequential:
+    return nn.Sequential(nn.Conv2d(16, 16, 3, padding=1), nn.ReLU(inplace=True), nn.Conv2d(16, cout, 3, padding=1))
+
+
+class _CVMBase(nn.Module):
+    """Builds the parameter tree shared by all four classes from a `VariantSpec`."""
+
+    def __init__(self, spec: VariantSpec, device, circular_padding: bool, ori_noise: Optional[float] = None):
+        super().__init__()
+        self.device = device                      # stored and unused, exactly like the reference (models.py:52)
+        self.circular_padding = circular_padding
+        self.spec = spec
+        self.grd_efficientnet = EfficientNetB0(circular=bool(circular_padding))
+        for l, c in enumerate(spec.head_channels, start=1):
+            setattr(self, "grd_feature_to_descriptor%d" % l,
+                    nn.Sequential(nn.Conv2d(1280, c, 1), _Permute(0, 2, 3, 1), nn.Conv2d(spec.grd_feat_h, 1, 1),
+                                  nn.Flatten(start_dim=1)))
+        self.sat_efficientnet = EfficientNetB0(circular=False)
+        self.sat_feature_to_descriptors = nn.Sequential(nn.Flatten(start_dim=1), nn.Linear(1280 * 2 * 2, spec.sat_dim))
+        self.sat_normalization = nn.Identity()    # parameter-free in the reference too (models.py:106)
+        # localisation decoder
+        cin = spec.sat_dim
+        for i, n in enumerate(range(6, 0, -1)):
+            dout = spec.loc_deconv_out[i]
+            setattr(self, "deconv%d" % n, nn.ConvTranspose2d(cin + 1, dout, 2, 2))
+            if n > 1:
+                setattr(self, "conv%d" % n, _double_conv(dout + SKIP_CHANNELS[i], spec.loc_conv_out[i]))
+                cin = spec.loc_conv_out[i]
+            else:
+                self.conv1 = _final_conv(1)
+        # orientation decoder
+        cin = spec.sat_dim + spec.n_rolls
+        for i, n in enumerate(range(6, 0, -1)):
+            dout = spec.ori_deconv_out[i]
+            setattr(self, "deconv%d_ori" % n, nn.ConvTranspose2d(cin, dout, 2, 2))
+            if n > 1:
+                setattr(self, "conv%d_ori" % n, _double_conv(dout + SKIP_CHANNELS[i], spec.ori_conv_out[i]))
+                cin = spec.ori_conv_out[i]
+            else:
+                self.conv1_ori = _final_conv(2)
+        self._pipeline = [PostEncoderPipeline(self, spec, ori_noise)]   # in a list: not a sub-module, not in state_dict
+        self._precision = "fp32"
+        self._fast_encoders = [None]                                    # (signature, grd_enc_bf16, sat_enc_bf16)
+
+    # -- configuration ----------------------------------------------------------------------------------------
+    @property
+    def pipeline(self) -> PostEncoderPipeline:
+        return self._pipeline[0]
+
+    def set_precision(self, precision: str):
+        """"fp32": exact reference arithmetic (fp32 encoders, fp32-accumulate CUDA-core decoder kernels).
+        "bf16": bf16 channels-last encoders + bf16 decoder kernels with fp32 accumulation (tcgen05 where built)."""
+        if precision not in ("fp32", "bf16"):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        self._precision = precision
+        return self
+
+    def set_backend(self, backend: int):
+        self.pipeline.backend = backend
+        return self
+
+    def __deepcopy__(self, memo):
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if k in ("_pipeline", "_fast_encoders"):
+                continue
+            setattr(new, k, copy.deepcopy(v, memo))
+        new._pipeline = [PostEncoderPipeline(new, self.spec, self.pipeline.ori_noise)]
+        new._pipeline[0].backend = self.pipeline.backend
+        new._fast_encoders = [None]
+        return new
+
+    # -- encoders (PyTorch) -----------------------------------------------------------------------------------
+    def _bf16_encoders(self):
+        sig = tuple((p.data_ptr(), p._version) for enc in (self.grd_efficientnet, self.sat_efficientnet)
+                    for p in list(enc.parameters()) + list(enc.buffers()))
+        cached = self._fast_encoders[0]
+        if cached is None or cached[0] != sig:
+            encs = []
+            for enc in (self.grd_efficientnet, self.sat_efficientnet):
+                e = copy.deepcopy(enc).eval().to(dtype=torch.bfloat16).to(memory_format=torch.channels_last)
+                e.set_fast_activation(True)
+                encs.append(e)
+            cached = (sig, encs[0], encs[1])
+            self._fast_encoders[0] = cached
+        return cached[1], cached[2]
+
+    def _encode(self, grd, sat):
+        if self._precision == "bf16" and not self.training:
+            ge, se = self._bf16_encoders()
+            grd = grd.to(dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            sat = sat.to(dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            fg = ge.extract_features(grd)
+            fs, multi = se.extract_features_multiscale(sat)
+            return fg, fs, multi, torch.bfloat16
+        # fp32 means fp32: cuDNN must not silently drop the encoders to TF32 (torch's default for convolutions)
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            fg = self.grd_efficientnet.extract_features(grd)                      # reference models.py:151
+            fs, multi = self.sat_efficientnet.extract_features_multiscale(sat)    # reference models.py:166
+        return fg, fs, multi, (torch.bfloat16 if self._precision == "bf16" else torch.float32)
+
+    # -- the reference's entry point --------------------------------------------------------------------------
+    def forward(self, grd, sat):
+        """Returns (logits_flattened, heatmap, x_ori, matching_score_stacked, ..._stacked2, ..., ..._stacked6)
+        with the reference's shapes (models.py:343)."""
+        if torch.is_grad_enabled() and self.training:
+            raise NotImplementedError(
+                "ccvpe_b200: the CUDA decoder path is inference-only in this version (backward kernels for the "
+                "training config are the next scope row); call under torch.no_grad() / model.eval()")
+        if not (grd.is_cuda and sat.is_cuda):
+            raise cabi.CcvpeError("ccvpe_b200 models run on CUDA (sm_100a) only; there is no CPU fallback -- "
+                                  "move the model and inputs to a B200")
+        with torch.no_grad():
+            fg, fs, multi, dtype = self._encode(grd, sat)
+            return self.pipeline.run(fg, fs, multi, dtype)
+
+    # -- extras -----------------------------------------------------------------------------------------------
+    @staticmethod
+    def decode_pose(heatmap, ori):
+        return decode_pose(heatmap, ori)
+
+    def localize(self, grd, sat):
+        out = self.forward(grd, sat)
+        return decode_pose(out[1], out[2])
+
+
+class CVM_VIGOR(_CVMBase):
+    """reference models.py:49 -- `CVM_VIGOR(device, circular_padding)`."""
+
+    def __init__(self, device, circular_padding):
+        super().__init__(VIGOR, device, circular_padding)
+
+
+class CVM_VIGOR_ori_prior(_CVMBase):
+    """reference models.py:346 -- localisation sweeps only orientations within +-ori_noise (multiples of 18 deg)."""
+
+    def __init__(self, device, ori_noise, circular_padding=True):
+        super().__init__(VIGOR, device, circular_padding, ori_noise=float(ori_noise))
+        self.ori_noise = ori_noise
+
+
+class CVM_KITTI(_CVMBase):
+    """reference models.py:655 -- `CVM_KITTI(device)`."""
+
+    def __init__(self, device):
+        super().__init__(KITTI, device, False)
+
+
+class CVM_OxfordRobotCar(_CVMBase):
+    """reference models.py:954 -- `CVM_OxfordRobotCar(device)`."""
+
+    def __init__(self, device):
+        super().__init__(OXFORD, device, False)

@@ -1,0 +1,150 @@
+/*
+ * ccvpe_b200.h -- C ABI of libccvpe_b200.so: the post-encoder hot path of tudelft-iv/CCVPE as sm_100a CUDA kernels.
+ *
+ * The reference has no FFI layer (it is pure Python/PyTorch); its only boundary for this path is
+ * `CVM_*.forward(grd, sat)` in models.py.  The entry points below are the operators that boundary decomposes into
+ * (SURVEY.md section 8(a), rows a1..a13); `ccvpe_b200/models.py` re-assembles them behind the reference's own
+ * forward signatures.  Each function cites the reference lines it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`; nothing here allocates, frees or
+ *     synchronises: outputs and scratch are caller-allocated, work is enqueued on `stream` (a cudaStream_t).
+ *   - return value: 0 = ok; <0 = error (CCVPE_ERR_*); `ccvpe_last_error()` returns a thread-local message.
+ *   - activations are channels-last ("NHWC": [B, H, W, C], C contiguous) with element type `dtype`
+ *     (CCVPE_F32 or CCVPE_BF16); accumulation is always fp32.  Tensors returned to the caller of
+ *     `forward` (scores, logits, heatmap, orientation field) are fp32 in the reference's NCHW layout.
+ *   - all channel counts must be multiples of 8 (true for every layer of the four reference models).
+ */
+#ifndef CCVPE_B200_H_
+#define CCVPE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CCVPE_ABI_VERSION 1
+
+enum { CCVPE_F32 = 0, CCVPE_BF16 = 1 };
+
+enum {
+  CCVPE_OK = 0,
+  CCVPE_ERR_BAD_ARGUMENT = -1,  /* null pointer, negative size, misaligned pointer ...            */
+  CCVPE_ERR_UNSUPPORTED = -2,   /* shape / dtype / backend combination not implemented            */
+  CCVPE_ERR_CUDA = -3,          /* a CUDA runtime / driver call or kernel launch failed           */
+  CCVPE_ERR_NO_DEVICE = -4      /* no sm_100 device visible                                        */
+};
+
+/* backends for the dense contractions */
+enum {
+  CCVPE_BACKEND_AUTO = 0,    /* tcgen05 when dtype == BF16 and the shape is supported, else SIMT  */
+  CCVPE_BACKEND_SIMT = 1,    /* fp32-accumulate CUDA-core implicit GEMM (any dtype) -- the fp32 parity path */
+  CCVPE_BACKEND_TCGEN05 = 2  /* TMA-fed tcgen05.mma tiles, accumulators in TMEM (bf16 operands)   */
+};
+
+int ccvpe_abi_version(void);
+const char* ccvpe_last_error(void);
+/* number of kernels this library has launched on behalf of the calling thread since the last reset */
+int64_t ccvpe_launch_count(void);
+void ccvpe_reset_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * a1  Ground descriptor heads -- reference models.py:22-31, 57-97, 152-157 (and :355-395, :662-699, :961-998).
+ *   g[b, w*c + ch] = sum_h v[h] * (sum_k W[ch,k] * F[b,k,h,w] + bias1[ch]) + bias2
+ * feat: ground feature volume, logical [B, K, H, W] addressed through element strides (sb, sk, sh, sw) so both
+ *       NCHW and channels-last encoder outputs are accepted.  w1 [c, K] fp32, b1 [c] fp32, w2 [H] fp32, b2 [1] fp32.
+ * out : fp32 [B, W*c].  scratch: fp32, at least B*K*W elements.
+ * ------------------------------------------------------------------------------------------------------------- */
+int ccvpe_grd_descriptor(const void* feat, int dtype, int B, int K, int H, int W,
+                         int64_t sb, int64_t sk, int64_t sh, int64_t sw,
+                         const float* w1, const float* b1, const float* w2, const float* b2, int c,
+                         float* out, float* scratch, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Generic implicit GEMM used for a3 (aerial cell descriptors), a8 (ConvTranspose2d k2 s2) and a9 (3x3 convs):
+ *
+ *   acc[m, n] = sum_{tap=(ty,tx)} sum_{src in {0,1}} sum_{k < c_src}
+ *                   A_src[b, ho*stride + ty - pad, wo*stride + tx - pad, k] * Wt[tap][koff_src + k][n]
+ *   y[m, n]   = act( acc[m, n] * row_scale[m] + row_r1[m] * r1_w[n] + bias[n] )          m = (b, ho, wo)
+ *
+ * Two channels-last sources are K-concatenated on the fly: this is how torch.cat([x, skip]) (models.py:208, 230, ...)
+ * and torch.cat([max, normalize(x)]) (models.py:205, 228, ...) are executed without materialising the concat:
+ *   row_scale = 1/max(||x_m||, 1e-12)  (F.normalize, models.py:33-40), row_r1 = max-over-rolls score, r1_w = W[0, :].
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct ccvpe_igemm_desc {
+  /* sources (a1 may be NULL with c1 == 0); both have spatial size [B, Hin, Win]; ld* = channel stride in elements
+   * of one pixel (>= c*, lets a source be a channel-slice of a wider tensor) */
+  const void* a0; const void* a1;
+  int32_t c0, c1, ld0, ld1;
+  int32_t B, Hin, Win, Hout, Wout;
+  int32_t stride, kh, kw, pad;
+  int32_t N;                     /* GEMM N: Cout, or 4*Cout ordered (i, j, co) for the k2 s2 transposed conv        */
+  int32_t dtype;                 /* CCVPE_F32 / CCVPE_BF16: element type of sources and weights                     */
+  /* weights, one of (depending on backend):
+   *   w_kn : [taps][c0 + c1][N]                     (N contiguous)       -- SIMT backend
+   *   w_nk : [N_pad16][taps][c0_pad64 + c1_pad64]   (K contiguous, bf16) -- tcgen05 backend                        */
+  const void* w_kn; const void* w_nk;
+  const float* bias;             /* [N] fp32 or NULL                                                                */
+  const float* row_scale;        /* [M] fp32 or NULL                                                                */
+  const float* row_r1;           /* [M] fp32 or NULL                                                                */
+  const float* r1_w;             /* [N] fp32 (required iff row_r1)                                                  */
+  int32_t relu;
+  /* output */
+  int32_t out_mode;              /* 0: channels-last [M, ldo]; 1: pixel-shuffle of a k2 s2 transposed conv into
+                                    channels-last [B, 2*Hout, 2*Wout, ldo]; 2: fp32 planar NCHW [B, N, Hout, Wout]  */
+  int32_t out_dtype;             /* CCVPE_F32 / CCVPE_BF16 (mode 2 requires F32)                                    */
+  int32_t ldo;                   /* channel stride of the output pixel (modes 0/1)                                  */
+  void* out;
+  int32_t backend;               /* CCVPE_BACKEND_*                                                                 */
+} ccvpe_igemm_desc;
+
+/* a3: models.py:102-104,173-184 | a8: models.py:109-124,207,229,... | a9: models.py:42-47,110-127,209,231,...     */
+int ccvpe_igemm(const ccvpe_igemm_desc* desc, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * a4 a5 a6  Rolled cosine matching of one decoder level -- reference models.py:186-202 (x6 levels), prior-limited
+ * variant :489-511, KITTI :788-920, Oxford centred window :1094.
+ *
+ *   window_i[k]   = x[(k + offset + shift_i) mod C]          k = 0..L-1,  shift_i = roll_index_i * roll_stride
+ *   scores[b,i,p] = sum_k g[b,k] * window_i[k,p] / ( sqrt(sum_k window_i[k,p]^2) * sqrt(sum_k g[b,k]^2) )
+ *   max[b,p]      = max over the rolls i with bit i set in max_mask
+ *   inv_norm[b,p] = 1 / max( sqrt(sum_c x[b,p,c]^2), 1e-12 )                  (the F.normalize of models.py:205)
+ *
+ * x: channels-last [B, HW, C] (dtype).  g: fp32 [B, L].  shifts: HOST array of n_rolls ints (any sign).
+ * Outputs (any may be NULL): scores fp32 [B, n_rolls, HW] (the reference's NCHW score volume),
+ *   scores_cl (dtype) [B, HW, ld_scores_cl] channels-last copy (pad channels zero; feeds the orientation decoder,
+ *   models.py:323), max fp32 [B, HW], inv_norm fp32 [B, HW], xhat (dtype) [B, HW, C] = normalised map.
+ * scratch: fp32, at least ccvpe_match_scratch_elems(B, C, n_rolls) elements.
+ * ------------------------------------------------------------------------------------------------------------- */
+int64_t ccvpe_match_scratch_elems(int B, int C, int n_rolls);
+int ccvpe_match_level(const void* x, int dtype, int B, int HW, int C,
+                      const float* g, int L, int offset, const int32_t* shifts_host, int n_rolls, uint32_t max_mask,
+                      float* scores, void* scores_cl, int ld_scores_cl, float* max_out, float* inv_norm, void* xhat,
+                      float* scratch, int backend, void* stream);
+
+/* a10  softmax over the flattened heatmap logits -- reference models.py:319-320.
+ * logits fp32 [B, n]; heatmap fp32 [B, n]; scratch fp32 >= ccvpe_softmax_scratch_elems(B, n). */
+int64_t ccvpe_softmax_scratch_elems(int B, int64_t n);
+int ccvpe_softmax_heatmap(const float* logits, float* heatmap, int B, int64_t n, float* scratch, void* stream);
+
+/* a12  orientation vector-field normalisation -- reference models.py:341 (F.normalize p=2 dim=1, eps 1e-12).
+ * in: channels-last [B, HW, ld] (dtype), first 2 channels = (cos, sin); out: fp32 planar [B, 2, HW]. */
+int ccvpe_ori_normalize(const void* in, int dtype, int ld, float* out, int B, int64_t HW, void* stream);
+
+/* a13  argmax pose decode -- reference train_VIGOR.py:290-326 (+ 8 copies in the other scripts).
+ * heatmap fp32 [B, H*W]; ori fp32 planar [B, 2, H*W].
+ * idx[b]   = first index of the maximum of heatmap[b] (numpy argmax semantics; a NaN counts as the maximum)
+ * rc[b]    = (idx / W, idx % W);  cs[b] = (ori[b,0,idx], ori[b,1,idx])
+ * valid[b] = |cos| <= 1 && |sin| <= 1;  angle_deg[b] = valid ? (sin < 0 ? fmod(degrees(-acos(cos)), 360) (python %)
+ *            : degrees(acos(cos))) : NaN,   evaluated in float64.
+ * scratch: >= ccvpe_pose_scratch_bytes(B, H*W) bytes. */
+int64_t ccvpe_pose_scratch_bytes(int B, int64_t n);
+int ccvpe_pose_decode(const float* heatmap, const float* ori, int B, int H, int W,
+                      int64_t* idx, int32_t* rc, float* cs, double* angle_deg, uint8_t* valid,
+                      void* scratch, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CCVPE_B200_H_ */

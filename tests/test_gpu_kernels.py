@@ -1,0 +1,306 @@
+"""GPU parity tests, one per C-ABI operator, against the CPU oracle on the same seeded inputs.
+
+Tolerances (stated per test): fp32 path 1e-4 of max|ref| per tensor (BASELINE.json asks for 1e-3); bf16 path 2e-2.
+Index / integer outputs are compared bit-exact."""
+import math
+
+import numpy as np
+import pytest
+import torch
+from torch.nn import functional as F
+
+from ccvpe_b200 import cabi
+from ccvpe_b200.decoder import decode_pose
+from helpers import rel_err
+from oracle import ccvpe_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-4
+BF16_TOL = 2e-2
+
+
+def _gen(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def _cl(t, dtype, dev):
+    return t.permute(0, 2, 3, 1).contiguous().to(dev, dtype)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# a1 ground descriptors
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,H,W,c,layout,dtype", [
+    (2, 10, 20, 64, "nchw", torch.float32), (1, 10, 20, 2, "nchw", torch.float32),
+    (2, 8, 32, 16, "nhwc", torch.float32), (1, 4, 7, 1, "nchw", torch.float32),
+    (2, 10, 6, 32, "nhwc", torch.bfloat16),
+])
+def test_grd_descriptor(cuda_device, B, H, W, c, layout, dtype):
+    g = _gen(1)
+    feat = torch.randn(B, 1280, H, W, generator=g)
+    w1, b1 = torch.randn(c, 1280, 1, 1, generator=g) * 0.05, torch.randn(c, generator=g)
+    w2, b2 = torch.randn(1, H, 1, 1, generator=g), torch.randn(1, generator=g)
+    feat_ref = feat.to(dtype).float()
+    ref = orc.grd_descriptor(feat_ref, w1, b1, w2, b2)
+    f = feat.to(cuda_device, dtype)
+    if layout == "nhwc":
+        f = f.contiguous(memory_format=torch.channels_last)
+    out = torch.empty(B, W * c, device=cuda_device)
+    scratch = torch.empty(B * 1280 * W, device=cuda_device)
+    cabi.grd_descriptor(f, w1.reshape(c, 1280).to(cuda_device), b1.to(cuda_device), w2.reshape(H).to(cuda_device),
+                        b2.to(cuda_device), out, scratch)
+    assert rel_err(out, ref) < FP32_TOL
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# igemm helper
+# ---------------------------------------------------------------------------------------------------------------
+def _igemm(dev, a0, a1, Hout, Wout, stride, k, pad, N, w_kn, bias, out, out_mode, ldo, relu=False, row_scale=None,
+           row_r1=None, r1_w=None, backend=cabi.BACKEND_SIMT):
+    d = cabi.IgemmDesc()
+    B, Hin, Win, c0 = a0.shape
+    d.a0, d.a1 = a0.data_ptr(), (a1.data_ptr() if a1 is not None else None)
+    d.c0, d.c1 = c0, (a1.shape[-1] if a1 is not None else 0)
+    d.ld0, d.ld1 = c0, d.c1
+    d.B, d.Hin, d.Win, d.Hout, d.Wout = B, Hin, Win, Hout, Wout
+    d.stride, d.kh, d.kw, d.pad = stride, k, k, pad
+    d.N, d.dtype = N, cabi.dtype_code(a0.dtype)
+    d.w_kn, d.w_nk = w_kn.data_ptr(), None
+    d.bias = bias.data_ptr() if bias is not None else None
+    d.row_scale = row_scale.data_ptr() if row_scale is not None else None
+    d.row_r1 = row_r1.data_ptr() if row_r1 is not None else None
+    d.r1_w = r1_w.data_ptr() if r1_w is not None else None
+    d.relu, d.out_mode, d.out_dtype, d.ldo = int(relu), out_mode, cabi.dtype_code(out.dtype), ldo
+    d.out, d.backend = out.data_ptr(), backend
+    cabi.igemm(d)
+    torch.cuda.synchronize()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# a3 aerial cell descriptors  (Linear over 2x2 cells == conv k2 s2)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,D,dtype,tol", [(2, 1280, torch.float32, FP32_TOL), (1, 2048, torch.float32, FP32_TOL),
+                                           (3, 1280, torch.bfloat16, BF16_TOL)])
+def test_sat_cell_descriptors(cuda_device, B, D, dtype, tol):
+    g = _gen(2)
+    fs = torch.randn(B, 1280, 16, 16, generator=g)
+    W = torch.randn(D, 5120, generator=g) * 0.02
+    bias = torch.randn(D, generator=g)
+    ref = orc.sat_cell_descriptors(fs.to(dtype).float(), W.to(dtype).float(), bias)       # [B, D, 8, 8]
+    w_kn = W.view(D, 1280, 2, 2).permute(2, 3, 1, 0).reshape(4, 1280, D).contiguous().to(cuda_device, dtype)
+    out = torch.empty(B, 8, 8, D, device=cuda_device, dtype=dtype)
+    _igemm(cuda_device, _cl(fs, dtype, cuda_device), None, 8, 8, 2, 2, 0, D, w_kn, bias.to(cuda_device), out, 0, D)
+    assert rel_err(out.permute(0, 3, 1, 2).float(), ref) < tol
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# a4/a5/a6 matching: every odd case of SURVEY section 8 (window < C, wrap-around > 1x, centred, negative rolls)
+# ---------------------------------------------------------------------------------------------------------------
+MATCH_CASES = [
+    # name,          B, C,    L,    H,  rolls,                 stride, centred
+    ("vigor_l1",     2, 1280, 1280, 8,  list(range(20)),       64,  False),
+    ("vigor_l6",     1, 40,   40,   64, list(range(20)),       2,   False),
+    ("vigor_l4",     2, 160,  160,  16, list(range(20)),       8,   False),
+    ("fov180_l2",    2, 640,  320,  16, list(range(-4, 5)),    32,  False),
+    ("fov108_l6",    1, 40,   12,   32, list(range(-4, 5)),    2,   False),
+    ("prior180",     1, 320,  320,  8,  list(range(-10, 11)),  16,  False),
+    ("kitti_l1",     2, 2048, 512,  8,  list(range(16)),       128, False),
+    ("kitti_l2",     1, 512,  256,  16, list(range(16)),       64,  False),   # i*s wraps past C twice
+    ("kitti_l6",     1, 32,   32,   32, list(range(16)),       8,   False),
+    ("oxford_l1",    2, 1280, 224,  8,  list(range(20)),       64,  True),
+    ("oxford_l6",    1, 40,   7,    32, list(range(20)),       2,   True),
+    ("ragged_tile",  1, 80,   80,   10, list(range(20)),       4,   False),   # HW = 100: partial 128-pixel tile
+]
+
+
+@pytest.mark.parametrize("case", MATCH_CASES, ids=[c[0] for c in MATCH_CASES])
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, FP32_TOL), (torch.bfloat16, 2e-3)])
+def test_match_level(cuda_device, case, dtype, tol):
+    name, B, C, L, H, rolls, stride, centred = case
+    g = _gen(3)
+    x = torch.randn(B, C, H, H, generator=g)
+    gd = torch.randn(B, L, generator=g)
+    xr = x.to(dtype).float()                       # the oracle sees exactly the values the kernel sees
+    ref = orc.match_level(xr, gd, rolls, stride, centred)
+    offset = int(C / 2 - L / 2) if centred else 0
+    dev = cuda_device
+    R = len(rolls)
+    x_cl = _cl(x, dtype, dev)
+    scores = torch.empty(B, R, H, H, device=dev)
+    scores_cl = torch.full((B, H, H, 32), 7.0, device=dev, dtype=dtype)
+    mx = torch.empty(B, H, H, device=dev)
+    inv = torch.empty(B, H, H, device=dev)
+    xhat = torch.empty_like(x_cl)
+    scratch = torch.empty(cabi.match_scratch_elems(B, C, R), device=dev)
+    # max over an arbitrary subset of the rolls (the prior-limited level-1 case uses a mask)
+    mask = sum(1 << i for i in range(R) if i % 3 != 1)
+    cabi.match_level(x_cl, gd.to(dev), offset, [i * stride for i in rolls], mask, scores=scores, scores_cl=scores_cl,
+                     max_out=mx, inv_norm=inv, xhat=xhat, scratch=scratch, backend=cabi.BACKEND_SIMT)
+    torch.cuda.synchronize()
+    assert rel_err(scores, ref) < tol
+    sel = [i for i in range(R) if i % 3 != 1]
+    assert rel_err(mx, ref[:, sel].max(dim=1)[0]) < tol
+    assert rel_err(1.0 / inv, xr.norm(dim=1)) < tol
+    assert rel_err(xhat.permute(0, 3, 1, 2).float(), orc.l2_normalize(xr)) < (tol if dtype == torch.float32 else 1e-2)
+    cl = scores_cl.float()
+    assert rel_err(cl[..., :R].permute(0, 3, 1, 2), ref) < (tol if dtype == torch.float32 else 1e-2)
+    assert torch.all(cl[..., R:] == 0)
+
+
+def test_match_level_zero_window_is_nan(cuda_device):
+    """No epsilon in the cosine denominator (models.py:196): an all-zero window gives NaN, as in the reference."""
+    x = torch.zeros(1, 4, 4, 16, device=cuda_device)
+    gd = torch.ones(1, 16, device=cuda_device)
+    scores = torch.empty(1, 2, 4, 4, device=cuda_device)
+    mx = torch.empty(1, 4, 4, device=cuda_device)
+    inv = torch.empty(1, 4, 4, device=cuda_device)
+    scratch = torch.empty(cabi.match_scratch_elems(1, 16, 2), device=cuda_device)
+    cabi.match_level(x, gd, 0, [0, 8], 3, scores=scores, max_out=mx, inv_norm=inv, scratch=scratch,
+                     backend=cabi.BACKEND_SIMT)
+    assert torch.isnan(scores).all() and torch.isnan(mx).all()
+    assert torch.all(inv == 1e12)                  # F.normalize clamps at eps=1e-12 instead
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# a6/a7/a8 transposed conv with the normalise + max-channel concat folded into the epilogue
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,C,H,cout,dtype,tol", [(2, 1280, 8, 1024, torch.float32, FP32_TOL),
+                                                  (1, 40, 32, 16, torch.float32, FP32_TOL),
+                                                  (3, 80, 16, 40, torch.float32, FP32_TOL),
+                                                  (2, 160, 16, 80, torch.bfloat16, BF16_TOL)])
+def test_deconv_fused_normalize_concat(cuda_device, B, C, H, cout, dtype, tol):
+    g = _gen(4)
+    dev = cuda_device
+    x = torch.randn(B, C, H, H, generator=g) * 3.0
+    mx = torch.randn(B, 1, H, H, generator=g)
+    W = torch.randn(C + 1, cout, 2, 2, generator=g) * 0.1
+    bias = torch.randn(cout, generator=g)
+    xr, Wr = x.to(dtype).float(), W.to(dtype).float()
+    Wr[0] = W[0]                                           # the rank-1 vector stays fp32 in the kernel
+    ref = F.conv_transpose2d(torch.cat([mx, orc.l2_normalize(xr)], dim=1), Wr, bias, stride=2)
+    inv = (1.0 / xr.norm(dim=1).clamp_min(1e-12)).to(dev)
+    w_kn = W[1:].permute(0, 2, 3, 1).reshape(1, C, 4 * cout).contiguous().to(dev, dtype)
+    r1_w = W[0].permute(1, 2, 0).reshape(4 * cout).contiguous().to(dev)
+    out = torch.empty(B, 2 * H, 2 * H, cout, device=dev, dtype=dtype)
+    _igemm(dev, _cl(x, dtype, dev), None, H, H, 1, 1, 0, 4 * cout, w_kn, bias.repeat(4).to(dev), out, 1, cout,
+           row_scale=inv.contiguous(), row_r1=mx[:, 0].contiguous().to(dev), r1_w=r1_w)
+    assert rel_err(out.permute(0, 3, 1, 2).float(), ref) < tol
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# a7/a9 3x3 conv over two K-concatenated sources (+ReLU), planar fp32 output for the final 1/2-channel convs
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,c0,c1,cout,H,relu,mode,dtype,tol", [
+    (2, 1024, 320, 640, 16, True, 0, torch.float32, FP32_TOL),
+    (1, 40, 16, 40, 64, True, 0, torch.float32, FP32_TOL),
+    (1, 80, 24, 80, 32, False, 0, torch.float32, FP32_TOL),
+    (2, 16, 0, 1, 64, False, 2, torch.float32, FP32_TOL),
+    (2, 16, 0, 2, 32, False, 0, torch.float32, FP32_TOL),
+    (2, 160, 40, 160, 32, True, 0, torch.bfloat16, BF16_TOL),
+])
+def test_conv3x3_two_sources(cuda_device, B, c0, c1, cout, H, relu, mode, dtype, tol):
+    g = _gen(5)
+    dev = cuda_device
+    a0 = torch.randn(B, c0, H, H, generator=g)
+    a1 = torch.randn(B, c1, H, H, generator=g) if c1 else None
+    W = torch.randn(cout, c0 + c1, 3, 3, generator=g) * (1.0 / math.sqrt(9 * (c0 + c1)))
+    bias = torch.randn(cout, generator=g)
+    xin = torch.cat([a0, a1], dim=1) if c1 else a0
+    ref = F.conv2d(xin.to(dtype).float(), W.to(dtype).float(), bias, padding=1)
+    if relu:
+        ref = F.relu(ref)
+    w_kn = W.permute(2, 3, 1, 0).reshape(9, c0 + c1, cout).contiguous().to(dev, dtype)
+    if mode == 2:
+        out = torch.empty(B, cout, H, H, device=dev)
+        _igemm(dev, _cl(a0, dtype, dev), None, H, H, 1, 3, 1, cout, w_kn, bias.to(dev), out, 2, 0, relu=relu)
+        got = out
+    else:
+        odt = torch.float32 if cout <= 2 else dtype
+        out = torch.empty(B, H, H, cout, device=dev, dtype=odt)
+        _igemm(dev, _cl(a0, dtype, dev), _cl(a1, dtype, dev) if c1 else None, H, H, 1, 3, 1, cout, w_kn, bias.to(dev),
+               out, 0, cout, relu=relu)
+        got = out.permute(0, 3, 1, 2).float()
+    assert rel_err(got, ref) < tol
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# a10 softmax
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,n", [(1, 512 * 512), (3, 512 * 512), (64, 4096), (2, 1001), (5, 7)])
+def test_softmax_heatmap(cuda_device, B, n):
+    g = _gen(6)
+    logits = torch.randn(B, n, generator=g) * 3.0
+    logits[0, n // 2] = 40.0                                    # a strong peak must not overflow
+    ref = torch.softmax(logits, dim=-1)
+    lg = logits.to(cuda_device)
+    out = torch.empty_like(lg)
+    scratch = torch.empty(cabi.softmax_scratch_elems(B, n), device=cuda_device)
+    cabi.softmax_heatmap(lg, out, scratch)
+    assert rel_err(out, ref) < 1e-5
+    assert torch.allclose(out.sum(dim=1).cpu(), torch.ones(B), atol=1e-4)
+    assert torch.equal(out.argmax(dim=1).cpu(), ref.argmax(dim=1))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# a12 orientation normalisation
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_ori_normalize(cuda_device, dtype):
+    g = _gen(7)
+    o = torch.randn(2, 2, 64, 48, generator=g)
+    o[0, :, 0, 0] = 0.0                                         # zero vector -> stays zero (eps clamp)
+    ref = F.normalize(o.to(dtype).float(), p=2, dim=1)
+    out = torch.empty(2, 2, 64, 48, device=cuda_device)
+    cabi.ori_normalize(_cl(o, dtype, cuda_device), out)
+    assert rel_err(out, ref) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# a13 pose decode: bit-exact indices, numpy tie-breaking, guarded acos
+# ---------------------------------------------------------------------------------------------------------------
+def test_pose_decode_matches_numpy(cuda_device):
+    g = _gen(8)
+    B, H, W = 9, 512, 512
+    heat = torch.rand(B, 1, H, W, generator=g) * 1e-5
+    ori = F.normalize(torch.randn(B, 2, H, W, generator=g), dim=1)
+    flat = heat.view(B, -1)
+    flat[0, 1234] = flat[0, 99999] = 1.0                         # tie -> first occurrence
+    flat[1, :] = 0.5                                            # plateau -> 0
+    flat[2, H * W - 1] = 2.0                                    # last
+    flat[3, 0] = 2.0                                            # first
+    flat[4, 777] = float("nan")                                 # numpy: NaN is the argmax
+    flat[4, 50000] = float("nan")
+    flat[5, 4242] = 3.0
+    ori[5, :, 4242 // W, 4242 % W] = torch.tensor([1.5, 0.0])   # |cos| > 1 -> invalid
+    flat[6, 31337] = 3.0
+    ori[6, :, 31337 // W, 31337 % W] = torch.tensor([1.0, -0.0])
+    flat[7, 2 * W + 5] = 3.0
+    ori[7, :, 2, 5] = torch.tensor([-1.0, 0.0])
+    ref = orc.pose_decode(heat.numpy(), ori.numpy())
+    got = {k: v.cpu().numpy() for k, v in decode_pose(heat.to(cuda_device), ori.to(cuda_device)).items()}
+    assert got["idx"].tolist() == ref["idx"].tolist()
+    assert got["rc"].tolist() == ref["rc"].tolist()
+    assert np.array_equal(got["cs"], ref["cs"], equal_nan=True)
+    assert got["valid"].tolist() == ref["valid"].tolist()
+    np.testing.assert_allclose(got["angle"], ref["angle"], rtol=0, atol=1e-9, equal_nan=True)
+
+
+def test_pose_decode_small_and_odd_sizes(cuda_device):
+    g = _gen(9)
+    for (B, H, W) in [(1, 8, 8), (3, 17, 5), (64, 64, 64)]:
+        heat = torch.rand(B, 1, H, W, generator=g)
+        ori = F.normalize(torch.randn(B, 2, H, W, generator=g), dim=1)
+        ref = orc.pose_decode(heat.numpy(), ori.numpy())
+        got = {k: v.cpu().numpy() for k, v in decode_pose(heat.to(cuda_device), ori.to(cuda_device)).items()}
+        assert got["idx"].tolist() == ref["idx"].tolist()
+        np.testing.assert_allclose(got["angle"], ref["angle"], rtol=0, atol=1e-9)
+
+
+def test_errors_are_loud(cuda_device):
+    with pytest.raises(cabi.CcvpeError):
+        cabi.softmax_heatmap(torch.zeros(2, 8), torch.zeros(2, 8), torch.zeros(256))          # CPU tensors
+    x = torch.zeros(1, 4, 4, 12, device=cuda_device)                                          # C % 8 != 0
+    with pytest.raises(cabi.CcvpeError):
+        cabi.match_level(x, torch.zeros(1, 12, device=cuda_device), 0, [0], 1,
+                         scratch=torch.zeros(4096, device=cuda_device))
