@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""bench.py -- VIGOR pairs/sec of the CCVPE hot path on N B200s (BASELINE.json metric), one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--precision bf16|fp32] [--impl ours|reference]
+
+A "step" is one pass of `CVM_VIGOR.forward` + pose decode over one batch of synthetic VIGOR-shaped pairs
+(3x320x640 panorama + 3x512x512 aerial, random-init weights).  Workload = BASELINE.json configs[1]: batch 64 bf16 per
+GPU, batch-sharded (weak scaling: every rank owns its own 64 pairs; no data-path collective -- pairs are independent).
+
+  value     : pairs/s, inputs resident in HBM, K steps timed with CUDA events between barrier+synchronize, max over ranks
+  e2e       : same metric through the public API with HOST (pinned) inputs: H2D copy of both images and D2H read of the
+              decoded poses inside the timed region, every step
+  roofline  : the dominant kernel family of the post-encoder path, timed live with CUDA events on the launch stream
+  kernels   : per-family achieved GB/s or TFLOP/s vs the measured peaks (MEASURED_PEAKS.json)
+  cpu_baseline : the oracle port of the reference's CPU forward, timed on the host cores on a bounded sample (rank 0)
+
+`--impl reference` times that same CPU port (the reference itself is Python that cannot travel to the GPU box and its
+path does not compile to a library: see DESIGN.md) and prints the same line with "impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "VIGOR pairs/sec (CVM_VIGOR forward + pose decode, 320x640 panorama + 512x512 aerial)"
+GROUND_HW = (320, 640)
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], tensor_burst=p["bf16_tflops"], tensor_sustained=p["bf16_tflops_sustained"],
+                    source="measured")
+    return dict(hbm=6650.0, tensor_burst=1590.0, tensor_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs (B200_PROFILING.md)."""
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [v for v in sm if v >= 0.5 * max(sm)]
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU baseline: oracle port of the reference forward (encoders are PyTorch in both)
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_reference_throughput(sample_batch: int, reps: int, budget_s: float = 30.0):
+    from ccvpe_b200 import models
+    from ccvpe_b200.synthetic import fill_deterministic, synthetic_pair
+    from oracle import ccvpe_oracle as orc
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = models.CVM_VIGOR("cpu", True).eval()
+    fill_deterministic(model.state_dict(), seed=0)
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    grd, sat = synthetic_pair(sample_batch, GROUND_HW, seed=0)
+    times = []
+    t_begin = time.time()
+    with torch.no_grad():
+        for i in range(reps + 1):
+            t0 = time.time()
+            out = orc.forward_full("vigor", sd, model.grd_efficientnet, model.sat_efficientnet, grd, sat)
+            orc.pose_decode(out[1].numpy(), out[2].numpy())
+            dt = time.time() - t0
+            if i > 0:
+                times.append(dt)            # first pass is the warm-up
+            if time.time() - t_begin > budget_s and times:
+                break
+    best = min(times)
+    return dict(value=sample_batch / best, unit="pairs/s", cores=cores, kind="port",
+                sample="oracle port of CVM_VIGOR.forward + numpy pose decode, fp32, batch %d, best of %d after 1 warm-up "
+                       "(%.2f s/forward, torch threads=%d)" % (sample_batch, len(times), best, cores))
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    reps = max(1, min(args.steps, 10))
+    base = cpu_reference_throughput(sample_batch=1, reps=reps + args.warmup, budget_s=120.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": "pairs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / base["value"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "CVM_VIGOR forward + pose decode, VIGOR shape, FoV 360 (CPU: bounded sample of batch 1 "
+                               "per step)", "batch_per_gpu": args.batch, "parallelism": "cpu"},
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    from ccvpe_b200 import cabi, models
+    from ccvpe_b200.decoder import OpTimer
+    from ccvpe_b200.synthetic import fill_deterministic, synthetic_pair
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    B = args.batch
+    model = models.CVM_VIGOR("cuda", True).eval()
+    fill_deterministic(model.state_dict(), seed=0)
+    model = model.to(dev).set_precision(args.precision)
+    if args.backend == "simt":
+        model.set_backend(cabi.BACKEND_SIMT)
+    grd_h, sat_h = synthetic_pair(B, GROUND_HW, seed=100 + rank)
+    grd_h, sat_h = grd_h.pin_memory(), sat_h.pin_memory()
+    grd_d, sat_d = grd_h.to(dev), sat_h.to(dev)
+
+    def step_resident():
+        out = model(grd_d, sat_d)
+        return model.decode_pose(out[1], out[2])
+
+    def step_e2e():
+        g = grd_h.to(dev, non_blocking=True)
+        s = sat_h.to(dev, non_blocking=True)
+        out = model(g, s)
+        pose = model.decode_pose(out[1], out[2])
+        return {k: v.cpu() for k, v in pose.items()}          # D2H of the step's result (synchronises)
+
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            step_resident()
+        barrier()
+        # ---- timed region: device-resident inputs ------------------------------------------------------------
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        timer = OpTimer()
+        model.pipeline.timer = timer
+        cabi.reset_launch_count()
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(args.steps):
+            step_resident()
+        ev1.record()
+        barrier()
+        launches = cabi.launch_count()
+        ms_total = ev0.elapsed_time(ev1)
+        ops = timer.summary()
+        model.pipeline.timer = None
+        # ---- timed region: end to end from host buffers ------------------------------------------------------
+        step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step_e2e()
+        e1.record()
+        barrier()
+        ms_e2e = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+        clocks = sampler.stop() if rank == 0 else None
+
+    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e = t.tolist()
+
+    if rank == 0:
+        peaks = _peaks()
+        pairs = world * B * args.steps
+        value = pairs / (ms_total / 1e3)
+        e2e_value = pairs / (ms_e2e / 1e3)
+        kernels = {}
+        for tag, r in sorted(ops.items()):
+            sec = r["ms"] / 1e3
+            tensor_bound = tag.startswith("igemm")
+            if tensor_bound:
+                ach, peak, unit = r["flops"] / sec / 1e12, peaks["tensor_sustained"], "TFLOP/s"
+            else:
+                ach, peak, unit = r["bytes"] / sec / 1e9, peaks["hbm"], "GB/s"
+            kernels[tag] = {"bound": "tensor" if tensor_bound else "hbm", "achieved": round(ach, 2), "peak": peak,
+                            "unit": unit, "frac": round(ach / peak, 4), "launches_per_step": r["launches"] // args.steps,
+                            "ms_per_step": round(r["ms"] / args.steps, 4)}
+        igemm_ms = sum(r["ms"] for tag, r in ops.items() if tag.startswith("igemm"))
+        igemm_fl = sum(r["flops"] for tag, r in ops.items() if tag.startswith("igemm"))
+        igemm_n = sum(r["launches"] for tag, r in ops.items() if tag.startswith("igemm"))
+        post_ms = sum(r["ms"] for r in ops.values())
+        ach = igemm_fl / (igemm_ms / 1e3) / 1e12
+        roofline = {"kernel": "implicit-GEMM conv/deconv/cell-descriptor kernel (all igemm launches of the step)",
+                    "bound": "tensor", "achieved": round(ach, 2), "peak": peaks["tensor_sustained"], "unit": "TFLOP/s",
+                    "frac": round(ach / peaks["tensor_sustained"], 4), "traffic": None,
+                    "peak_source": peaks["source"] + " (sustained bf16: kernel timed inside a long step)",
+                    "launches": igemm_n // args.steps, "share_of_post_encoder_ms": round(igemm_ms / post_ms, 3),
+                    "post_encoder_ms_per_step": round(post_ms / args.steps, 3)}
+        cpu = cpu_reference_throughput(sample_batch=1, reps=5, budget_s=25.0) if (world == 1 and not args.no_cpu) else None
+        h2d = grd_h.numel() * grd_h.element_size() + sat_h.numel() * sat_h.element_size()
+        d2h = B * (8 + 8 + 8 + 8 + 1)
+        line = {
+            "metric": METRIC, "value": round(value, 3), "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
+            "data": "synthetic",
+            "config": {"workload": "CVM_VIGOR batched inference, synthetic VIGOR shape (3x320x640 + 3x512x512), FoV 360, "
+                                   "random-init weights (BASELINE.json configs[1])",
+                       "batch_per_gpu": B, "global_batch": world * B, "parallelism": "batch-sharded x%d" % world,
+                       "backend": args.backend,
+                       "l2": "per-step working set (inputs %.0f MB + >1 GB activations) exceeds the 126 MB L2" % (h2d / 1e6)},
+            "e2e": {"value": round(e2e_value, 3), "unit": "pairs/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": round(ms_e2e / args.steps, 3)},
+            "gpu_launches": int(launches),
+            "roofline": roofline, "kernels": kernels, "clocks": clocks,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=64, help="pairs per GPU per step")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--backend", default="auto", choices=["auto", "simt"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -30,6 +30,33 @@ def _cl(t: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     return v.contiguous()
 
 
+class OpTimer:
+    """Optional per-operator CUDA-event timer (bench.py): events are recorded on torch's current stream, which is the
+    stream every kernel of the pipeline is launched on.  `flops` / `nbytes` are the ALGORITHMIC work of the call."""
+
+    def __init__(self):
+        self.records = []
+
+    def run(self, tag: str, flops: float, nbytes: float, fn):
+        s = torch.cuda.Event(enable_timing=True)
+        e = torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        self.records.append((tag, s, e, float(flops), float(nbytes)))
+
+    def summary(self) -> Dict[str, dict]:
+        torch.cuda.synchronize()
+        out: Dict[str, dict] = {}
+        for tag, s, e, fl, nb in self.records:
+            r = out.setdefault(tag, dict(launches=0, ms=0.0, flops=0.0, bytes=0.0))
+            r["launches"] += 1
+            r["ms"] += s.elapsed_time(e)
+            r["flops"] += fl
+            r["bytes"] += nb
+        return out
+
+
 class PostEncoderPipeline:
     def __init__(self, module: torch.nn.Module, spec: VariantSpec, ori_noise: Optional[float] = None):
         self._module = [module]          # list: do not register the owner as a sub-module
@@ -38,6 +65,13 @@ class PostEncoderPipeline:
         self.backend = cabi.BACKEND_AUTO
         self._cache: Dict[torch.dtype, dict] = {}
         self._sig = None
+        self.timer: Optional[OpTimer] = None
+
+    def _op(self, tag: str, flops: float, nbytes: float, fn):
+        if self.timer is None:
+            fn()
+        else:
+            self.timer.run(tag, flops, nbytes, fn)
 
     # -- derived weight cache ---------------------------------------------------------------------------------
     def _params(self) -> Dict[str, torch.Tensor]:
@@ -102,7 +136,7 @@ class PostEncoderPipeline:
         return w
 
     # -- kernel helpers ---------------------------------------------------------------------------------------
-    def _igemm(self, a0, c0, a1, c1, B, Hin, Win, Hout, Wout, stride, k, pad, N, dtype, wt, out, out_mode, ldo,
+    def _igemm(self, tag, a0, c0, a1, c1, B, Hin, Win, Hout, Wout, stride, k, pad, N, dtype, wt, out, out_mode, ldo,
                relu=False, row_scale=None, row_r1=None, r1_w=None):
         d = cabi.IgemmDesc()
         d.a0, d.a1 = a0.data_ptr(), (a1.data_ptr() if a1 is not None else None)
@@ -120,14 +154,17 @@ class PostEncoderPipeline:
         d.relu, d.out_mode, d.out_dtype, d.ldo = int(relu), out_mode, cabi.dtype_code(out.dtype), ldo
         d.out = out.data_ptr()
         d.backend = self.backend
-        cabi.igemm(d)
+        M, K = B * Hout * Wout, k * k * (c0 + c1)
+        esz = a0.element_size()
+        nbytes = (B * Hin * Win * (c0 + c1) + K * N) * esz + M * N * out.element_size()
+        self._op(tag, 2.0 * M * N * K, nbytes, lambda: cabi.igemm(d))
 
     def _deconv(self, wt, a0, c0, a1, c1, dtype, row_scale=None, row_r1=None):
         """ConvTranspose2d(k2, s2) as GEMM + pixel shuffle (reference models.py:109-124)."""
         B, H, W, _ = a0.shape
         cout = wt["cout"]
         out = torch.empty((B, 2 * H, 2 * W, cout), dtype=dtype, device=a0.device)
-        self._igemm(a0, c0, a1, c1, B, H, W, H, W, 1, 1, 0, 4 * cout, dtype, wt, out, 1, cout,
+        self._igemm("igemm:deconv", a0, c0, a1, c1, B, H, W, H, W, 1, 1, 0, 4 * cout, dtype, wt, out, 1, cout,
                     row_scale=row_scale, row_r1=row_r1, r1_w=wt.get("r1_w") if row_r1 is not None else None)
         return out
 
@@ -142,7 +179,7 @@ class PostEncoderPipeline:
         else:
             out = torch.empty((B, H, W, cout), dtype=torch.float32 if out_f32 else dtype, device=a0.device)
             mode, ldo = 0, cout
-        self._igemm(a0, c0, a1, c1, B, H, W, H, W, 1, 3, 1, cout, dtype, wt, out, mode, ldo, relu=relu)
+        self._igemm("igemm:conv3x3", a0, c0, a1, c1, B, H, W, H, W, 1, 3, 1, cout, dtype, wt, out, mode, ldo, relu=relu)
         return out
 
     # -- the path ---------------------------------------------------------------------------------------------
@@ -169,7 +206,9 @@ class PostEncoderPipeline:
         for l in range(6):
             w1, b1, w2, b2 = w["heads"][l]
             out = torch.empty((Bg, Wg * w1.shape[0]), dtype=f32, device=dev)
-            cabi.grd_descriptor(grd_feat, w1, b1, w2, b2, out, scratch_g)
+            self._op("grd_descriptor", 2.0 * Bg * Wg * Kg * (Hg + w1.shape[0]),
+                     grd_feat.numel() * grd_feat.element_size() + out.numel() * 4,
+                     lambda: cabi.grd_descriptor(grd_feat, w1, b1, w2, b2, out, scratch_g))
             g.append(out)
 
         # a3 -- aerial cell descriptors: [B,16,16,1280] -> [B,8,8,D]
@@ -177,7 +216,8 @@ class PostEncoderPipeline:
         Hs, Ws = fs.shape[1], fs.shape[2]
         D = spec.sat_dim
         x = torch.empty((B, Hs // 2, Ws // 2, D), dtype=dtype, device=dev)
-        self._igemm(fs, ENCODER_CHANNELS, None, 0, B, Hs, Ws, Hs // 2, Ws // 2, 2, 2, 0, D, dtype, w["cell"], x, 0, D)
+        self._igemm("igemm:cell", fs, ENCODER_CHANNELS, None, 0, B, Hs, Ws, Hs // 2, Ws // 2, 2, 2, 0, D, dtype,
+                    w["cell"], x, 0, D)
         skips = [_cl(multiscale[i], dtype) for i in SKIP_BLOCKS]
 
         loc_rolls = loc_roll_indices(spec, self.ori_noise)
@@ -210,10 +250,14 @@ class PostEncoderPipeline:
                 scores_cl = torch.empty((B, H, W, SCORES_CL_PAD), dtype=dtype, device=dev)
                 xhat = torch.empty_like(x)
             scratch = torch.empty(cabi.match_scratch_elems(B, C, R), dtype=f32, device=dev)
-            cabi.match_level(x, g[l], spec.window_offset(C, L), [i * stride for i in rolls], mask, scores=scores,
-                             scores_cl=scores_cl if l == 0 else None, max_out=mx, inv_norm=inv,
-                             xhat=xhat if l == 0 else None, scratch=scratch,
-                             backend=cabi.BACKEND_SIMT if self.backend == cabi.BACKEND_SIMT else cabi.BACKEND_AUTO)
+            x_in, g_in = x, g[l]
+            # algorithmic traffic: read x once, write the score volume + max + 1/norm
+            nbytes = x.numel() * x.element_size() + (R + 2) * B * H * W * 4
+            self._op("match", 2.0 * R * L * B * H * W, nbytes, lambda: cabi.match_level(
+                x_in, g_in, spec.window_offset(C, L), [i * stride for i in rolls], mask, scores=scores,
+                scores_cl=scores_cl if l == 0 else None, max_out=mx, inv_norm=inv,
+                xhat=xhat if l == 0 else None, scratch=scratch,
+                backend=cabi.BACKEND_SIMT if self.backend == cabi.BACKEND_SIMT else cabi.BACKEND_AUTO))
             scores_out.append(scores)
             lw = w["loc"][l]
             up = self._deconv(lw["deconv"], x, C, None, 0, dtype, row_scale=inv, row_r1=mx)
@@ -229,7 +273,8 @@ class PostEncoderPipeline:
         logits_flat = logits.view(B, Hh * Wh)
         heatmap = torch.empty_like(logits)
         sm_scratch = torch.empty(cabi.softmax_scratch_elems(B, Hh * Wh), dtype=f32, device=dev)
-        cabi.softmax_heatmap(logits_flat, heatmap.view(B, Hh * Wh), sm_scratch)
+        self._op("softmax", 5.0 * B * Hh * Wh, 2.0 * B * Hh * Wh * 4,
+                 lambda: cabi.softmax_heatmap(logits_flat, heatmap.view(B, Hh * Wh), sm_scratch))
 
         # a11 -- orientation decoder (no matching inside; input = [scores_1, normalize(x_1)], models.py:323)
         o = None
@@ -246,7 +291,9 @@ class PostEncoderPipeline:
                 o = self._conv3(ow["conv_a"], o, None, dtype, relu=True)
                 o = self._conv3(ow["conv_b"], o, None, dtype, relu=False, out_f32=True)   # [B,512,512,2] fp32
         ori = torch.empty((B, 2, Hh, Wh), dtype=f32, device=dev)
-        cabi.ori_normalize(o, ori)                                                        # a12
+        o_in = o
+        self._op("ori_normalize", 6.0 * B * Hh * Wh, 2.0 * B * Hh * Wh * (o.element_size() + 4),
+                 lambda: cabi.ori_normalize(o_in, ori))                                   # a12
         return (logits_flat, heatmap, ori, *scores_out)
 
 

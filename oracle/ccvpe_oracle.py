@@ -182,6 +182,8 @@ def forward_post_encoder(variant: str, sd: Dict[str, Tensor], grd_feature_volume
     for lvl in range(2, 7):
         o = upsample_block(o, skips[lvl - 2], sd, "deconv%d_ori" % (8 - lvl), "conv%d_ori" % (8 - lvl))
     o = upsample_block(o, None, sd, "deconv1_ori", "conv1_ori")
+    if intermediates is not None:
+        intermediates["ori_raw"] = o
     o = F.normalize(o, p=2, dim=1)
     return (logits_flat, heatmap, o, *scores)
 
@@ -214,8 +216,8 @@ def pose_decode(heatmap: np.ndarray, ori: np.ndarray):
 # full forward incl. encoders -- used only as the timed CPU baseline (bench.py cpu_baseline / --impl reference)
 # ---------------------------------------------------------------------------------------------
 def forward_full(variant: str, sd: Dict[str, Tensor], grd_encoder, sat_encoder, grd: Tensor, sat: Tensor,
-                 ori_noise: Optional[float] = None):
+                 ori_noise: Optional[float] = None, intermediates: Optional[dict] = None):
     """Encoders are the caller's torch modules (the encoders stay PyTorch in reference and product alike)."""
     fg = grd_encoder.extract_features(grd)                              # models.py:151
     fs, multi = sat_encoder.extract_features_multiscale(sat)            # models.py:166
-    return forward_post_encoder(variant, sd, fg, fs, multi, ori_noise)
+    return forward_post_encoder(variant, sd, fg, fs, multi, ori_noise, intermediates)

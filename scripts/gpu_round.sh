@@ -1,0 +1,10 @@
+#!/bin/bash
+# One GPU visit: parity tests, smoke, a short bench, and the ncu launch list of the bench command.
+# usage (through gpurun): bash scripts/gpu_round.sh [tag]
+TAG=${1:-r01}
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${TAG}_smi.txt 2>&1
+timeout 1500 python -m pytest tests -q -m gpu 2>&1 | tail -60 > gpurun_out/${TAG}_pytest_gpu.log
+tail -5 gpurun_out/${TAG}_pytest_gpu.log
+timeout 300 python __graft_entry__.py --smoke > gpurun_out/${TAG}_smoke.log 2>&1; tail -2 gpurun_out/${TAG}_smoke.log
+timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; tail -c 3000 gpurun_out/${TAG}_bench.json; tail -5 gpurun_out/${TAG}_bench.err

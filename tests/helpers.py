@@ -37,12 +37,23 @@ def config_inputs(name):
     return synthetic_pair(batch, GROUND_SHAPES[shape_key], seed=iseed)
 
 
-def oracle_forward(model, variant, noise, grd, sat):
+def oracle_forward(model, variant, noise, grd, sat, intermediates=None):
     from oracle import ccvpe_oracle as orc
 
     sd = {k: v.detach() for k, v in model.state_dict().items()}
     with torch.no_grad():
-        return orc.forward_full(variant, sd, model.grd_efficientnet, model.sat_efficientnet, grd, sat, noise)
+        return orc.forward_full(variant, sd, model.grd_efficientnet, model.sat_efficientnet, grd, sat, noise,
+                                intermediates)
+
+
+def ori_field_err(ori: torch.Tensor, ori_ref: torch.Tensor, ori_raw_ref: torch.Tensor) -> float:
+    """Error of the unit orientation field measured on the field BEFORE normalisation: F.normalize divides by the
+    per-pixel magnitude, so an absolute error d on the raw 2-vector v shows up as ~d/|v| on v/|v|.  Returns
+    max_p |ori - ori_ref|_p * |v_p| / max|v|, i.e. the relative error of the raw field that explains the difference
+    (equals the plain relative error wherever |v_p| is of the order of max|v|)."""
+    mag = ori_raw_ref.detach().double().norm(dim=1, keepdim=True)
+    d = (ori.detach().double().cpu() - ori_ref.detach().double()).abs()
+    return (d * mag / ori_raw_ref.detach().double().abs().max()).max().item()
 
 
 def rel_err(a: torch.Tensor, ref: torch.Tensor) -> float:
@@ -53,7 +64,7 @@ def rel_err(a: torch.Tensor, ref: torch.Tensor) -> float:
     return (a - ref).abs().max().item() / (denom if denom > 0 else 1.0)
 
 
-def check_against_golden(outputs, golden, tol):
+def check_against_golden(outputs, golden, tol, loose=None):
     """outputs: 9-tuple of tensors; golden: np.load of a tests/golden file."""
     worst = {}
     for name, t in zip(OUT_NAMES, outputs):
@@ -65,7 +76,8 @@ def check_against_golden(outputs, golden, tol):
         scale = np.abs(ref).max()
         err = np.abs(got.astype(np.float64) - ref.astype(np.float64)).max() / (scale if scale > 0 else 1.0)
         worst[name] = err
-        assert err <= tol, "%s: sampled rel err %.3e > %.1e" % (name, err, tol)
+        tol_n = (loose or {}).get(name, tol)
+        assert err <= tol_n, "%s: sampled rel err %.3e > %.1e" % (name, err, tol)
         s_ref, as_ref = float(golden[name + ".sum"]), float(golden[name + ".abssum"])
         assert abs(flat.astype(np.float64).sum() - s_ref) <= tol * max(as_ref, 1e-30), name + " checksum"
     return worst
