@@ -1,8 +1,544 @@
-// placeholder until the tcgen05 backend lands
+// tcgen05 backend of the generic implicit GEMM: the bf16 throughput path of a3 (cell descriptors), a8 (transposed
+// convs) and a9 (3x3 convs).  sm_100a only.
+//
+//   * A (activations, channels-last bf16) is never im2col'ed: for every (tap, 64-channel block) ONE TMA box load of
+//     [128 pixels x 64 channels] at spatially shifted coordinates lands a K-major, 128B-swizzled UMMA operand tile in
+//     shared memory; the conv halo (pad 1) is TMA out-of-bounds zero fill, channel tails are zero filled too, and the
+//     skip concat is a second tensor map walked by the same K loop.
+//   * B (weights, [N][taps][K] bf16, K contiguous) tiles arrive through a 2-D tensor map the same way.
+//   * one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=block_n<=256, K=16) into TMEM; accumulators
+//     are double buffered (2 x 256 columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   * warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4..7 = epilogue (tcgen05.ld -> bias / row-scale /
+//     rank-1 / ReLU -> bf16 or fp32 stores incl. the transposed-conv pixel shuffle).  Persistent: grid = min(tiles, SMs).
+//   * every mbarrier wait is bounded (clock64 watchdog -> __trap) so a protocol bug fails the launch instead of
+//     hanging the GPU.
+#include <cuda.h>
+
+#include <mutex>
+#include <unordered_map>
+
 #include "common.cuh"
+
 namespace ccvpe {
-bool igemm_tcgen05_supported(const ccvpe_igemm_desc&) { return false; }
-int igemm_tcgen05(const ccvpe_igemm_desc&, cudaStream_t) {
-  return fail(CCVPE_ERR_UNSUPPORTED, "ccvpe_igemm: tcgen05 backend not built into this library version");
+
+constexpr int TC_BM = 128;          // pixels per tile (UMMA M)
+constexpr int TC_BK = 64;           // bf16 channels per K block (= one 128-byte swizzle row)
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;
+constexpr int TC_MAX_N = 256;
+constexpr int TC_THREADS = 256;
+constexpr int TC_MAX_STAGES = 8;
+constexpr int TC_SMEM_BUDGET = 200 * 1024;
+
+struct TcParams {
+  CUtensorMap tm_a0, tm_a1, tm_b;
+  int nb0, nb1, taps, n_tiles_n, total_tiles, block_n, stages;
+  int tiles[4], box[4];
+  int tap_off[9][4];
+  int out_stride[4], extent[4];
+  int N, HWo, Wout, Hout;
+  const float* bias;
+  const float* row_scale;
+  const float* row_r1;
+  const float* r1_w;
+  int relu, out_mode, out_f32, ldo;
+  void* out;
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s: a pipeline protocol bug must not hang the device
+  }
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(tm), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (rows of 128 bytes, 8-row groups 1024 bytes apart).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);  // start address, 16-byte units
+  d |= (uint64_t)1 << 16;                    // leading byte offset (unused for swizzled K-major), 16 B
+  d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset: next 8-row group
+  d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+  return d;
+}
+
+// ---- kernel ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 1) igemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[TC_MAX_STAGES];
+  __shared__ __align__(8) uint64_t bar_empty[TC_MAX_STAGES];
+  __shared__ __align__(8) uint64_t bar_tmem_full[2];
+  __shared__ __align__(8) uint64_t bar_tmem_empty[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int stage_bytes = TC_A_BYTES + p.block_n * TC_BK * 2;
+  const int nkb = p.taps * (p.nb0 + p.nb1);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(&bar_tmem_full[a]), 1);
+      mbar_init(smem_u32(&bar_tmem_empty[a]), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tm_a0);
+    if (p.nb1) prefetch_tmap(&p.tm_a1);
+    prefetch_tmap(&p.tm_b);
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                 "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles_n;
+        int mt = tile / p.n_tiles_n;
+        int base[4];
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+          base[d] = (mt % p.tiles[d]) * p.box[d];
+          mt /= p.tiles[d];
+        }
+        const int n0 = nt * p.block_n;
+        int kidx = 0;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int c1 = base[0] + p.tap_off[tap][0], c2 = base[1] + p.tap_off[tap][1];
+          const int c3 = base[2] + p.tap_off[tap][2], c4 = base[3] + p.tap_off[tap][3];
+          for (int src = 0; src < 2; ++src) {
+            const int nb = src ? p.nb1 : p.nb0;
+            const CUtensorMap* tm = src ? &p.tm_a1 : &p.tm_a0;
+            for (int cb = 0; cb < nb; ++cb, ++kidx) {
+              mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+              const uint32_t full = smem_u32(&bar_full[stage]);
+              const uint32_t a_dst = smem_base + stage * stage_bytes;
+              mbar_arrive_expect_tx(full, (uint32_t)stage_bytes);
+              tma_load_5d(a_dst, tm, full, cb * TC_BK, c1, c2, c3, c4);
+              tma_load_2d(a_dst + TC_A_BYTES, &p.tm_b, full, kidx * TC_BK, n0);
+              if (++stage == p.stages) {
+                stage = 0;
+                phase ^= 1u;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=block_n
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) |
+                             ((uint32_t)(TC_BM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(smem_u32(&bar_tmem_empty[acc]), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * TC_MAX_N);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(smem_u32(&bar_full[stage]), phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + stage * stage_bytes;
+          const uint64_t adesc = make_smem_desc(a_addr);
+          const uint64_t bdesc = make_smem_desc(a_addr + TC_A_BYTES);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the 16-byte address field
+            umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+          }
+          umma_commit(smem_u32(&bar_empty[stage]));   // frees the smem slot once these MMAs have read it
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(smem_u32(&bar_tmem_full[acc]));    // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (4 warps, warp w owns TMEM lanes 32*(w%4) .. +31) =====================
+    const int ew = warp & 3;
+    const int row = ew * 32 + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int nt = tile % p.n_tiles_n;
+      int mt = tile / p.n_tiles_n;
+      // row -> output pixel
+      int r = row;
+      int m_glob = 0;
+      bool valid = true;
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        const int coord = (mt % p.tiles[d]) * p.box[d] + (r % p.box[d]);
+        mt /= p.tiles[d];
+        r /= p.box[d];
+        valid = valid && (coord < p.extent[d]);
+        m_glob += coord * p.out_stride[d];
+      }
+      const int n0 = nt * p.block_n;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      float rs = 1.f, r1 = 0.f;
+      if (valid) {
+        if (p.row_scale) rs = __ldg(p.row_scale + m_glob);
+        if (p.row_r1) r1 = __ldg(p.row_r1 + m_glob);
+      }
+      // output addressing
+      int b_img = 0, hw = 0;
+      if (p.out_mode != 0) {
+        b_img = m_glob / p.HWo;
+        hw = m_glob - b_img * p.HWo;
+      }
+      mbar_wait(smem_u32(&bar_tmem_full[acc]), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * TC_MAX_N);
+      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (!valid) continue;
+        const int nbase = n0 + c0;
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) {
+          const int n = nbase + g8 * 8;
+          if (n >= p.N) break;
+          float y[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float a = __uint_as_float(v[g8 * 8 + j]);
+            const int nn = n + j;
+            if (nn < p.N) {
+              if (p.row_scale) a *= rs;
+              if (p.row_r1) a = fmaf(r1, __ldg(p.r1_w + nn), a);
+              if (p.bias) a += __ldg(p.bias + nn);
+              if (p.relu) a = fmaxf(a, 0.f);
+            }
+            y[j] = a;
+          }
+          if (p.out_mode == 2) {
+            float* o = static_cast<float*>(p.out);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (n + j < p.N) o[((int64_t)b_img * p.N + n + j) * p.HWo + hw] = y[j];
+            continue;
+          }
+          int64_t off;
+          if (p.out_mode == 0) {
+            off = (int64_t)m_glob * p.ldo + n;
+          } else {
+            const int cout = p.N >> 2;
+            const int ij = n / cout;
+            const int co = n - ij * cout;
+            const int h = hw / p.Wout, w = hw - h * p.Wout;
+            off = (((int64_t)b_img * 2 * p.Hout + 2 * h + (ij >> 1)) * (2 * p.Wout) + 2 * w + (ij & 1)) * p.ldo + co;
+          }
+          const bool full8 = (n + 8 <= p.N);
+          if (p.out_f32) {
+            float* o = static_cast<float*>(p.out) + off;
+            if (full8 && (p.ldo & 3) == 0) {
+              *reinterpret_cast<float4*>(o) = make_float4(y[0], y[1], y[2], y[3]);
+              *reinterpret_cast<float4*>(o + 4) = make_float4(y[4], y[5], y[6], y[7]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (n + j < p.N) o[j] = y[j];
+            }
+          } else {
+            __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.out) + off;
+            if (full8 && (p.ldo & 7) == 0) {
+              __nv_bfloat162 q0 = __floats2bfloat162_rn(y[0], y[1]), q1 = __floats2bfloat162_rn(y[2], y[3]);
+              __nv_bfloat162 q2 = __floats2bfloat162_rn(y[4], y[5]), q3 = __floats2bfloat162_rn(y[6], y[7]);
+              uint4 pk;
+              pk.x = *reinterpret_cast<uint32_t*>(&q0);
+              pk.y = *reinterpret_cast<uint32_t*>(&q1);
+              pk.z = *reinterpret_cast<uint32_t*>(&q2);
+              pk.w = *reinterpret_cast<uint32_t*>(&q3);
+              *reinterpret_cast<uint4*>(o) = pk;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (n + j < p.N) o[j] = __float2bfloat16_rn(y[j]);
+            }
+          }
+        }
+      }
+      // release the accumulator stage back to the MMA issuer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty[acc]));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &sym, 12000, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  });
+  return fn;
+}
+
+static int encode_map(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(CCVPE_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+  }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(CCVPE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rank=%d dims=[%llu,%llu,%llu,..] box=[%u,%u,%u,..]",
+                (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
+                (unsigned long long)(rank > 2 ? dims[2] : 0), box[0], box[1], rank > 2 ? box[2] : 0);
+  return CCVPE_OK;
+}
+
+static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+struct TcGeometry {
+  bool cell;        // k2 s2 cell-descriptor gather
+  int tw, th, tb;   // conv tile: tw x th pixels x tb images = 128 rows
+};
+
+static bool tc_geometry(const ccvpe_igemm_desc& d, TcGeometry* g) {
+  if (d.stride == 2 && d.kh == 2 && d.kw == 2 && d.pad == 0) {
+    if (d.Hin != 16 || d.Win != 16 || d.Hout != 8 || d.Wout != 8 || d.c1 != 0) return false;
+    g->cell = true;
+    g->tw = g->th = g->tb = 0;
+    return true;
+  }
+  if (d.stride != 1 || d.kh != d.kw || !(d.kh == 1 || d.kh == 3) || d.pad != (d.kh - 1) / 2) return false;
+  if (d.Hin != d.Hout || d.Win != d.Wout) return false;
+  if (!is_pow2(d.Wout) || !is_pow2(d.Hout)) return false;
+  int tw = d.Wout < TC_BM ? d.Wout : TC_BM;
+  int th = TC_BM / tw;
+  if (th > d.Hout) th = d.Hout;
+  int tb = TC_BM / (tw * th);
+  if (tw * th * tb != TC_BM || tb > 256) return false;
+  g->cell = false;
+  g->tw = tw;
+  g->th = th;
+  g->tb = tb;
+  return true;
+}
+
+bool igemm_tcgen05_supported(const ccvpe_igemm_desc& d) {
+  TcGeometry g;
+  if (d.dtype != CCVPE_BF16 || !d.w_nk) return false;
+  if (!tc_geometry(d, &g)) return false;
+  if (d.out_mode == 1 && (d.kh != 1)) return false;
+  return true;
+}
+
+int igemm_tcgen05(const ccvpe_igemm_desc& d, cudaStream_t st) {
+  TcGeometry g;
+  if (d.dtype != CCVPE_BF16) return fail(CCVPE_ERR_UNSUPPORTED, "ccvpe_igemm(tcgen05): bf16 operands only");
+  if (!d.w_nk) return fail(CCVPE_ERR_BAD_ARGUMENT, "ccvpe_igemm(tcgen05): w_nk is null");
+  if (!tc_geometry(d, &g)) return fail(CCVPE_ERR_UNSUPPORTED, "ccvpe_igemm(tcgen05): unsupported geometry");
+  if (!aligned16(d.w_nk)) return fail(CCVPE_ERR_BAD_ARGUMENT, "ccvpe_igemm(tcgen05): w_nk must be 16-byte aligned");
+
+  static thread_local TcParams p;   // > 1 KB: keep it off the stack; it is copied at launch
+  memset(&p, 0, sizeof(p));
+  p.nb0 = (d.c0 + TC_BK - 1) / TC_BK;
+  p.nb1 = (d.c1 + TC_BK - 1) / TC_BK;
+  p.taps = d.kh * d.kw;
+  const int n_tiles_n = (d.N + TC_MAX_N - 1) / TC_MAX_N;
+  int block_n = ((d.N + n_tiles_n - 1) / n_tiles_n + 15) / 16 * 16;
+  p.n_tiles_n = n_tiles_n;
+  p.block_n = block_n;
+  const int stage_bytes = TC_A_BYTES + block_n * TC_BK * 2;
+  int stages = TC_SMEM_BUDGET / stage_bytes;
+  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+  p.stages = stages;
+  const int64_t ktot = (int64_t)p.taps * (p.nb0 + p.nb1) * TC_BK;
+
+  int rc;
+  const uint64_t esz = 2;
+  if (g.cell) {
+    // [c][dw=2][j=8][dh=2][ib=8*B]
+    uint64_t dims[5] = {(uint64_t)d.c0, 2, 8, 2, (uint64_t)8 * d.B};
+    uint64_t str[4] = {(uint64_t)d.ld0 * esz, 2ull * d.ld0 * esz, (uint64_t)d.Win * d.ld0 * esz,
+                       2ull * d.Win * d.ld0 * esz};
+    uint32_t box[5] = {TC_BK, 1, 8, 1, 16};
+    if ((rc = encode_map(&p.tm_a0, d.a0, 5, dims, str, box)) != CCVPE_OK) return rc;
+    p.tiles[0] = 1; p.tiles[1] = 1; p.tiles[2] = 1; p.tiles[3] = (8 * d.B + 15) / 16;
+    p.box[0] = 1; p.box[1] = 8; p.box[2] = 1; p.box[3] = 16;
+    for (int t = 0; t < 4; ++t) {
+      p.tap_off[t][0] = t & 1;   // dw
+      p.tap_off[t][1] = 0;
+      p.tap_off[t][2] = t >> 1;  // dh
+      p.tap_off[t][3] = 0;
+    }
+    p.out_stride[0] = 0; p.out_stride[1] = 1; p.out_stride[2] = 0; p.out_stride[3] = 8;
+    p.extent[0] = 1 << 30; p.extent[1] = 8; p.extent[2] = 1 << 30; p.extent[3] = 8 * d.B;
+  } else {
+    for (int s = 0; s < 2; ++s) {
+      const void* base = s ? d.a1 : d.a0;
+      const int c = s ? d.c1 : d.c0, ld = s ? d.ld1 : d.ld0;
+      if (!c) continue;
+      uint64_t dims[5] = {(uint64_t)c, (uint64_t)d.Win, (uint64_t)d.Hin, (uint64_t)d.B, 1};
+      uint64_t str[4] = {(uint64_t)ld * esz, (uint64_t)d.Win * ld * esz, (uint64_t)d.Hin * d.Win * ld * esz,
+                         (uint64_t)d.B * d.Hin * d.Win * ld * esz};
+      uint32_t box[5] = {TC_BK, (uint32_t)g.tw, (uint32_t)g.th, (uint32_t)g.tb, 1};
+      if ((rc = encode_map(s ? &p.tm_a1 : &p.tm_a0, base, 5, dims, str, box)) != CCVPE_OK) return rc;
+    }
+    p.tiles[0] = d.Wout / g.tw; p.tiles[1] = d.Hout / g.th; p.tiles[2] = (d.B + g.tb - 1) / g.tb; p.tiles[3] = 1;
+    p.box[0] = g.tw; p.box[1] = g.th; p.box[2] = g.tb; p.box[3] = 1;
+    for (int t = 0; t < p.taps; ++t) {
+      p.tap_off[t][0] = (t % d.kw) - d.pad;
+      p.tap_off[t][1] = (t / d.kw) - d.pad;
+      p.tap_off[t][2] = 0;
+      p.tap_off[t][3] = 0;
+    }
+    p.out_stride[0] = 1; p.out_stride[1] = d.Wout; p.out_stride[2] = d.Hout * d.Wout; p.out_stride[3] = 0;
+    p.extent[0] = d.Wout; p.extent[1] = d.Hout; p.extent[2] = d.B; p.extent[3] = 1;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)ktot, (uint64_t)d.N};
+    uint64_t str[1] = {(uint64_t)ktot * esz};
+    uint32_t box[2] = {TC_BK, (uint32_t)block_n};
+    if ((rc = encode_map(&p.tm_b, d.w_nk, 2, dims, str, box)) != CCVPE_OK) return rc;
+  }
+  const int m_tiles = p.tiles[0] * p.tiles[1] * p.tiles[2] * p.tiles[3];
+  p.total_tiles = m_tiles * n_tiles_n;
+  p.N = d.N;
+  p.HWo = d.Hout * d.Wout;
+  p.Wout = d.Wout;
+  p.Hout = d.Hout;
+  p.bias = d.bias;
+  p.row_scale = d.row_scale;
+  p.row_r1 = d.row_r1;
+  p.r1_w = d.r1_w;
+  p.relu = d.relu;
+  p.out_mode = d.out_mode;
+  p.out_f32 = (d.out_dtype == CCVPE_F32);
+  p.ldo = d.ldo;
+  p.out = d.out;
+
+  const int smem = stages * stage_bytes + 1024;
+  static thread_local int smem_attr_set = 0;
+  if (smem_attr_set < smem) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
+    if (e != cudaSuccess) return fail(CCVPE_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    smem_attr_set = 227 * 1024;
+  }
+  int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
+  igemm_tcgen05_kernel<<<grid, TC_THREADS, smem, st>>>(p);
+  return check_launch("igemm_tcgen05_kernel");
+}
+
 }  // namespace ccvpe

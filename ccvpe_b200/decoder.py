@@ -104,8 +104,25 @@ class PostEncoderPipeline:
         # a3 aerial cell descriptors: Linear(5120 -> D) with the 5120 axis ordered (c, dh, dw) == conv k2 s2
         lw = params["sat_feature_to_descriptors.1.weight"].detach()
         D = lw.shape[0]
+        tc = dtype == torch.bfloat16     # also build the K-major layout of the tcgen05 backend
+
+        def nk(per_tap_rows: torch.Tensor, splits: Sequence[int]) -> torch.Tensor:
+            """[N, taps, K] -> [N, taps, sum(pad64(split))] bf16 with every source's K range zero padded to 64."""
+            N_, taps, _ = per_tap_rows.shape
+            pads = [(c + 63) // 64 * 64 for c in splits]
+            out = torch.zeros((N_, taps, sum(pads)), dtype=torch.bfloat16, device=per_tap_rows.device)
+            src = dst = 0
+            for c, cp in zip(splits, pads):
+                out[:, :, dst:dst + c] = per_tap_rows[:, :, src:src + c]
+                src += c
+                dst += cp
+            return out.contiguous()
+
         w["cell"] = dict(w_kn=lw.view(D, ENCODER_CHANNELS, 2, 2).permute(2, 3, 1, 0).reshape(4, ENCODER_CHANNELS, D)
                          .to(dtype).contiguous(), bias=f32(params["sat_feature_to_descriptors.1.bias"]))
+        if tc:
+            w["cell"]["w_nk"] = nk(lw.view(D, ENCODER_CHANNELS, 2, 2).permute(0, 2, 3, 1).reshape(D, 4, ENCODER_CHANNELS),
+                                   [ENCODER_CHANNELS])
 
         def deconv(name: str, lead: int, lead_pad: int):
             """ConvTranspose2d weight [Cin, Cout, 2, 2] -> GEMM B [1][K][4*Cout], N ordered (i, j, co).
@@ -121,17 +138,31 @@ class PostEncoderPipeline:
                 pad = torch.zeros((lead_pad - lead,) + tuple(W.shape[1:]), dtype=W.dtype, device=W.device)
                 W = torch.cat([W[:lead], pad, W[lead:]], dim=0)
             out["w_kn"] = W.permute(0, 2, 3, 1).reshape(1, W.shape[0], 4 * cout).to(dtype).contiguous()
+            if tc:
+                rows = W.permute(2, 3, 1, 0).reshape(4 * cout, 1, W.shape[0])
+                out["w_nk"] = nk(rows, [lead_pad, W.shape[0] - lead_pad] if lead > 0 else [W.shape[0]])
             return out
 
-        def conv(name: str):
+        def conv(name: str, c0: int):
             W = params[name + ".weight"].detach()        # [Cout, Cin, 3, 3]
-            return dict(w_kn=W.permute(2, 3, 1, 0).reshape(9, W.shape[1], W.shape[0]).to(dtype).contiguous(),
-                        bias=f32(params[name + ".bias"]), cout=W.shape[0])
+            out = dict(w_kn=W.permute(2, 3, 1, 0).reshape(9, W.shape[1], W.shape[0]).to(dtype).contiguous(),
+                       bias=f32(params[name + ".bias"]), cout=W.shape[0])
+            if tc:
+                rows = W.permute(0, 2, 3, 1).reshape(W.shape[0], 9, W.shape[1])
+                out["w_nk"] = nk(rows, [c0, W.shape[1] - c0] if c0 < W.shape[1] else [c0])
+            return out
 
-        w["loc"] = [dict(deconv=deconv("deconv%d" % n, -1, 0), conv_a=conv("conv%d.0" % n), conv_b=conv("conv%d.2" % n))
-                    for n in range(6, 0, -1)]
-        w["ori"] = [dict(deconv=deconv("deconv%d_ori" % n, spec.n_rolls if n == 6 else 0, SCORES_CL_PAD),
-                         conv_a=conv("conv%d_ori.0" % n), conv_b=conv("conv%d_ori.2" % n)) for n in range(6, 0, -1)]
+        w["loc"], w["ori"] = [], []
+        for i, n in enumerate(range(6, 0, -1)):
+            for branch, sfx, douts in (("loc", "", spec.loc_deconv_out), ("ori", "_ori", spec.ori_deconv_out)):
+                dname = "deconv%d%s" % (n, sfx)
+                if branch == "loc":
+                    dc = deconv(dname, -1, 0)
+                else:
+                    dc = deconv(dname, spec.n_rolls if n == 6 else 0, SCORES_CL_PAD)
+                ca = conv("conv%d%s.0" % (n, sfx), douts[i])          # sources: (deconv output, encoder skip)
+                cb = conv("conv%d%s.2" % (n, sfx), params["conv%d%s.2.weight" % (n, sfx)].shape[1])
+                w[branch].append(dict(deconv=dc, conv_a=ca, conv_b=cb))
         self._cache[dtype] = w
         return w
 

@@ -56,8 +56,21 @@ def test_grd_descriptor(cuda_device, B, H, W, c, layout, dtype):
 # ---------------------------------------------------------------------------------------------------------------
 # igemm helper
 # ---------------------------------------------------------------------------------------------------------------
+def _nk(rows, splits):
+    """[N, taps, K] -> tcgen05 weight layout [N, taps, sum(pad64(split))] bf16 (see include/ccvpe_b200.h)."""
+    N_, taps, _ = rows.shape
+    pads = [(c + 63) // 64 * 64 for c in splits]
+    out = torch.zeros((N_, taps, sum(pads)), dtype=torch.bfloat16)
+    src = dst = 0
+    for c, cp in zip(splits, pads):
+        out[:, :, dst:dst + c] = rows[:, :, src:src + c]
+        src += c
+        dst += cp
+    return out.contiguous()
+
+
 def _igemm(dev, a0, a1, Hout, Wout, stride, k, pad, N, w_kn, bias, out, out_mode, ldo, relu=False, row_scale=None,
-           row_r1=None, r1_w=None, backend=cabi.BACKEND_SIMT):
+           row_r1=None, r1_w=None, backend=cabi.BACKEND_SIMT, w_nk=None):
     d = cabi.IgemmDesc()
     B, Hin, Win, c0 = a0.shape
     d.a0, d.a1 = a0.data_ptr(), (a1.data_ptr() if a1 is not None else None)
@@ -66,7 +79,8 @@ def _igemm(dev, a0, a1, Hout, Wout, stride, k, pad, N, w_kn, bias, out, out_mode
     d.B, d.Hin, d.Win, d.Hout, d.Wout = B, Hin, Win, Hout, Wout
     d.stride, d.kh, d.kw, d.pad = stride, k, k, pad
     d.N, d.dtype = N, cabi.dtype_code(a0.dtype)
-    d.w_kn, d.w_nk = w_kn.data_ptr(), None
+    d.w_kn = w_kn.data_ptr() if w_kn is not None else None
+    d.w_nk = w_nk.data_ptr() if w_nk is not None else None
     d.bias = bias.data_ptr() if bias is not None else None
     d.row_scale = row_scale.data_ptr() if row_scale is not None else None
     d.row_r1 = row_r1.data_ptr() if row_r1 is not None else None
@@ -80,17 +94,21 @@ def _igemm(dev, a0, a1, Hout, Wout, stride, k, pad, N, w_kn, bias, out, out_mode
 # ---------------------------------------------------------------------------------------------------------------
 # a3 aerial cell descriptors  (Linear over 2x2 cells == conv k2 s2)
 # ---------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("B,D,dtype,tol", [(2, 1280, torch.float32, FP32_TOL), (1, 2048, torch.float32, FP32_TOL),
-                                           (3, 1280, torch.bfloat16, BF16_TOL)])
-def test_sat_cell_descriptors(cuda_device, B, D, dtype, tol):
+@pytest.mark.parametrize("B,D,dtype,tol,backend", [
+    (2, 1280, torch.float32, FP32_TOL, cabi.BACKEND_SIMT), (1, 2048, torch.float32, FP32_TOL, cabi.BACKEND_SIMT),
+    (3, 1280, torch.bfloat16, BF16_TOL, cabi.BACKEND_SIMT), (3, 1280, torch.bfloat16, BF16_TOL, cabi.BACKEND_TCGEN05),
+    (1, 2048, torch.bfloat16, BF16_TOL, cabi.BACKEND_TCGEN05), (64, 1280, torch.bfloat16, BF16_TOL, cabi.BACKEND_TCGEN05)])
+def test_sat_cell_descriptors(cuda_device, B, D, dtype, tol, backend):
     g = _gen(2)
     fs = torch.randn(B, 1280, 16, 16, generator=g)
     W = torch.randn(D, 5120, generator=g) * 0.02
     bias = torch.randn(D, generator=g)
     ref = orc.sat_cell_descriptors(fs.to(dtype).float(), W.to(dtype).float(), bias)       # [B, D, 8, 8]
     w_kn = W.view(D, 1280, 2, 2).permute(2, 3, 1, 0).reshape(4, 1280, D).contiguous().to(cuda_device, dtype)
+    w_nk = _nk(W.view(D, 1280, 2, 2).permute(0, 2, 3, 1).reshape(D, 4, 1280), [1280]).to(cuda_device)
     out = torch.empty(B, 8, 8, D, device=cuda_device, dtype=dtype)
-    _igemm(cuda_device, _cl(fs, dtype, cuda_device), None, 8, 8, 2, 2, 0, D, w_kn, bias.to(cuda_device), out, 0, D)
+    _igemm(cuda_device, _cl(fs, dtype, cuda_device), None, 8, 8, 2, 2, 0, D, w_kn, bias.to(cuda_device), out, 0, D,
+           backend=backend, w_nk=w_nk)
     assert rel_err(out.permute(0, 3, 1, 2).float(), ref) < tol
 
 
@@ -165,11 +183,17 @@ def test_match_level_zero_window_is_nan(cuda_device):
 # ---------------------------------------------------------------------------------------------------------------
 # a6/a7/a8 transposed conv with the normalise + max-channel concat folded into the epilogue
 # ---------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("B,C,H,cout,dtype,tol", [(2, 1280, 8, 1024, torch.float32, FP32_TOL),
-                                                  (1, 40, 32, 16, torch.float32, FP32_TOL),
-                                                  (3, 80, 16, 40, torch.float32, FP32_TOL),
-                                                  (2, 160, 16, 80, torch.bfloat16, BF16_TOL)])
-def test_deconv_fused_normalize_concat(cuda_device, B, C, H, cout, dtype, tol):
+@pytest.mark.parametrize("B,C,H,cout,dtype,tol,backend", [
+    (2, 1280, 8, 1024, torch.float32, FP32_TOL, cabi.BACKEND_SIMT),
+    (1, 40, 32, 16, torch.float32, FP32_TOL, cabi.BACKEND_SIMT),
+    (3, 80, 16, 40, torch.float32, FP32_TOL, cabi.BACKEND_SIMT),
+    (2, 160, 16, 80, torch.bfloat16, BF16_TOL, cabi.BACKEND_SIMT),
+    (2, 160, 16, 80, torch.bfloat16, BF16_TOL, cabi.BACKEND_TCGEN05),
+    (3, 1280, 8, 1024, torch.bfloat16, BF16_TOL, cabi.BACKEND_TCGEN05),     # 8x8 map, odd batch: half-empty last tile
+    (1, 40, 256, 16, torch.bfloat16, BF16_TOL, cabi.BACKEND_TCGEN05),       # 128x1 row tiles, K tail 40 -> 64
+    (2, 320, 32, 160, torch.bfloat16, BF16_TOL, cabi.BACKEND_TCGEN05),
+])
+def test_deconv_fused_normalize_concat(cuda_device, B, C, H, cout, dtype, tol, backend):
     g = _gen(4)
     dev = cuda_device
     x = torch.randn(B, C, H, H, generator=g) * 3.0
@@ -182,24 +206,33 @@ def test_deconv_fused_normalize_concat(cuda_device, B, C, H, cout, dtype, tol):
     inv = (1.0 / xr.norm(dim=1).clamp_min(1e-12)).to(dev)
     w_kn = W[1:].permute(0, 2, 3, 1).reshape(1, C, 4 * cout).contiguous().to(dev, dtype)
     r1_w = W[0].permute(1, 2, 0).reshape(4 * cout).contiguous().to(dev)
+    w_nk = _nk(W[1:].permute(2, 3, 1, 0).reshape(4 * cout, 1, C), [C]).to(dev)
     out = torch.empty(B, 2 * H, 2 * H, cout, device=dev, dtype=dtype)
     _igemm(dev, _cl(x, dtype, dev), None, H, H, 1, 1, 0, 4 * cout, w_kn, bias.repeat(4).to(dev), out, 1, cout,
-           row_scale=inv.contiguous(), row_r1=mx[:, 0].contiguous().to(dev), r1_w=r1_w)
+           row_scale=inv.contiguous(), row_r1=mx[:, 0].contiguous().to(dev), r1_w=r1_w, backend=backend, w_nk=w_nk)
     assert rel_err(out.permute(0, 3, 1, 2).float(), ref) < tol
 
 
 # ---------------------------------------------------------------------------------------------------------------
 # a7/a9 3x3 conv over two K-concatenated sources (+ReLU), planar fp32 output for the final 1/2-channel convs
 # ---------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("B,c0,c1,cout,H,relu,mode,dtype,tol", [
-    (2, 1024, 320, 640, 16, True, 0, torch.float32, FP32_TOL),
-    (1, 40, 16, 40, 64, True, 0, torch.float32, FP32_TOL),
-    (1, 80, 24, 80, 32, False, 0, torch.float32, FP32_TOL),
-    (2, 16, 0, 1, 64, False, 2, torch.float32, FP32_TOL),
-    (2, 16, 0, 2, 32, False, 0, torch.float32, FP32_TOL),
-    (2, 160, 40, 160, 32, True, 0, torch.bfloat16, BF16_TOL),
+@pytest.mark.parametrize("B,c0,c1,cout,H,relu,mode,dtype,tol,backend", [
+    (2, 1024, 320, 640, 16, True, 0, torch.float32, FP32_TOL, cabi.BACKEND_SIMT),
+    (1, 40, 16, 40, 64, True, 0, torch.float32, FP32_TOL, cabi.BACKEND_SIMT),
+    (1, 80, 24, 80, 32, False, 0, torch.float32, FP32_TOL, cabi.BACKEND_SIMT),
+    (2, 16, 0, 1, 64, False, 2, torch.float32, FP32_TOL, cabi.BACKEND_SIMT),
+    (2, 16, 0, 2, 32, False, 0, torch.float32, FP32_TOL, cabi.BACKEND_SIMT),
+    (2, 160, 40, 160, 32, True, 0, torch.bfloat16, BF16_TOL, cabi.BACKEND_SIMT),
+    (2, 160, 40, 160, 32, True, 0, torch.bfloat16, BF16_TOL, cabi.BACKEND_TCGEN05),
+    (2, 1024, 320, 640, 16, True, 0, torch.bfloat16, BF16_TOL, cabi.BACKEND_TCGEN05),   # 3 N tiles of 224
+    (1, 320, 112, 320, 32, True, 0, torch.bfloat16, BF16_TOL, cabi.BACKEND_TCGEN05),    # K tail 112 -> 128
+    (1, 40, 16, 40, 256, True, 0, torch.bfloat16, BF16_TOL, cabi.BACKEND_TCGEN05),      # row tiles, N 40 -> 48
+    (3, 80, 24, 80, 128, False, 0, torch.bfloat16, BF16_TOL, cabi.BACKEND_TCGEN05),
+    (2, 16, 0, 1, 128, False, 2, torch.bfloat16, BF16_TOL, cabi.BACKEND_TCGEN05),       # logits: N=1, planar fp32
+    (2, 16, 0, 2, 64, False, 0, torch.bfloat16, BF16_TOL, cabi.BACKEND_TCGEN05),        # ori: N=2, fp32 channels-last
+    (5, 640, 0, 640, 8, False, 0, torch.bfloat16, BF16_TOL, cabi.BACKEND_TCGEN05),      # 8x8 map, tb=2, odd batch
 ])
-def test_conv3x3_two_sources(cuda_device, B, c0, c1, cout, H, relu, mode, dtype, tol):
+def test_conv3x3_two_sources(cuda_device, B, c0, c1, cout, H, relu, mode, dtype, tol, backend):
     g = _gen(5)
     dev = cuda_device
     a0 = torch.randn(B, c0, H, H, generator=g)
@@ -211,15 +244,17 @@ def test_conv3x3_two_sources(cuda_device, B, c0, c1, cout, H, relu, mode, dtype,
     if relu:
         ref = F.relu(ref)
     w_kn = W.permute(2, 3, 1, 0).reshape(9, c0 + c1, cout).contiguous().to(dev, dtype)
+    w_nk = _nk(W.permute(0, 2, 3, 1).reshape(cout, 9, c0 + c1), [c0, c1] if c1 else [c0]).to(dev)
     if mode == 2:
         out = torch.empty(B, cout, H, H, device=dev)
-        _igemm(dev, _cl(a0, dtype, dev), None, H, H, 1, 3, 1, cout, w_kn, bias.to(dev), out, 2, 0, relu=relu)
+        _igemm(dev, _cl(a0, dtype, dev), None, H, H, 1, 3, 1, cout, w_kn, bias.to(dev), out, 2, 0, relu=relu,
+               backend=backend, w_nk=w_nk)
         got = out
     else:
         odt = torch.float32 if cout <= 2 else dtype
         out = torch.empty(B, H, H, cout, device=dev, dtype=odt)
         _igemm(dev, _cl(a0, dtype, dev), _cl(a1, dtype, dev) if c1 else None, H, H, 1, 3, 1, cout, w_kn, bias.to(dev),
-               out, 0, cout, relu=relu)
+               out, 0, cout, relu=relu, backend=backend, w_nk=w_nk)
         got = out.permute(0, 3, 1, 2).float()
     assert rel_err(got, ref) < tol
 
