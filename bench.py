@@ -217,8 +217,14 @@ def run_ours(args):
         barrier()
         launches = cabi.launch_count()
         ms_total = ev0.elapsed_time(ev1)
-        ops = timer.summary()
+        layers = timer.summary()
         model.pipeline.timer = None
+        ops = {}
+        for tag, r in layers.items():                       # "family|layer" -> family totals
+            fam = tag.split("|")[0]
+            o = ops.setdefault(fam, dict(launches=0, ms=0.0, flops=0.0, bytes=0.0))
+            for k in o:
+                o[k] += r[k]
         # ---- timed region: end to end from host buffers ------------------------------------------------------
         step_e2e()
         barrier()
@@ -285,6 +291,13 @@ def run_ours(args):
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
+        if args.layers:
+            with open(args.layers, "w") as f:
+                f.write("%-28s %9s %10s %10s %9s\n" % ("layer", "ms/step", "TFLOP/s", "GB/s", "launches"))
+                for tag, r in sorted(layers.items(), key=lambda kv: -kv[1]["ms"]):
+                    sec = r["ms"] / 1e3
+                    f.write("%-28s %9.4f %10.2f %10.1f %9d\n" % (tag, r["ms"] / args.steps, r["flops"] / sec / 1e12,
+                                                                r["bytes"] / sec / 1e9, r["launches"] // args.steps))
     if dist is not None:
         dist.destroy_process_group()
 
@@ -299,6 +312,7 @@ def main():
     ap.add_argument("--backend", default="auto", choices=["auto", "simt"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--layers", default=None, help="write a per-layer timing table to this file")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -190,16 +190,16 @@ class PostEncoderPipeline:
         nbytes = (B * Hin * Win * (c0 + c1) + K * N) * esz + M * N * out.element_size()
         self._op(tag, 2.0 * M * N * K, nbytes, lambda: cabi.igemm(d))
 
-    def _deconv(self, wt, a0, c0, a1, c1, dtype, row_scale=None, row_r1=None):
+    def _deconv(self, wt, a0, c0, a1, c1, dtype, row_scale=None, row_r1=None, name=""):
         """ConvTranspose2d(k2, s2) as GEMM + pixel shuffle (reference models.py:109-124)."""
         B, H, W, _ = a0.shape
         cout = wt["cout"]
         out = torch.empty((B, 2 * H, 2 * W, cout), dtype=dtype, device=a0.device)
-        self._igemm("igemm:deconv", a0, c0, a1, c1, B, H, W, H, W, 1, 1, 0, 4 * cout, dtype, wt, out, 1, cout,
+        self._igemm("igemm:deconv|" + name, a0, c0, a1, c1, B, H, W, H, W, 1, 1, 0, 4 * cout, dtype, wt, out, 1, cout,
                     row_scale=row_scale, row_r1=row_r1, r1_w=wt.get("r1_w") if row_r1 is not None else None)
         return out
 
-    def _conv3(self, wt, a0, a1, dtype, relu, planar_f32=False, out_f32=False):
+    def _conv3(self, wt, a0, a1, dtype, relu, planar_f32=False, out_f32=False, name=""):
         """3x3 pad-1 conv over the K-concatenation of a0 and a1 (reference models.py:42-47)."""
         B, H, W, c0 = a0.shape
         c1 = a1.shape[-1] if a1 is not None else 0
@@ -210,7 +210,7 @@ class PostEncoderPipeline:
         else:
             out = torch.empty((B, H, W, cout), dtype=torch.float32 if out_f32 else dtype, device=a0.device)
             mode, ldo = 0, cout
-        self._igemm("igemm:conv3x3", a0, c0, a1, c1, B, H, W, H, W, 1, 3, 1, cout, dtype, wt, out, mode, ldo, relu=relu)
+        self._igemm("igemm:conv3x3|" + name, a0, c0, a1, c1, B, H, W, H, W, 1, 3, 1, cout, dtype, wt, out, mode, ldo, relu=relu)
         return out
 
     # -- the path ---------------------------------------------------------------------------------------------
@@ -247,7 +247,7 @@ class PostEncoderPipeline:
         Hs, Ws = fs.shape[1], fs.shape[2]
         D = spec.sat_dim
         x = torch.empty((B, Hs // 2, Ws // 2, D), dtype=dtype, device=dev)
-        self._igemm("igemm:cell", fs, ENCODER_CHANNELS, None, 0, B, Hs, Ws, Hs // 2, Ws // 2, 2, 2, 0, D, dtype,
+        self._igemm("igemm:cell|", fs, ENCODER_CHANNELS, None, 0, B, Hs, Ws, Hs // 2, Ws // 2, 2, 2, 0, D, dtype,
                     w["cell"], x, 0, D)
         skips = [_cl(multiscale[i], dtype) for i in SKIP_BLOCKS]
 
@@ -284,20 +284,22 @@ class PostEncoderPipeline:
             x_in, g_in = x, g[l]
             # algorithmic traffic: read x once, write the score volume + max + 1/norm
             nbytes = x.numel() * x.element_size() + (R + 2) * B * H * W * 4
-            self._op("match", 2.0 * R * L * B * H * W, nbytes, lambda: cabi.match_level(
+            self._op("match|l%d" % (l + 1), 2.0 * R * L * B * H * W, nbytes, lambda: cabi.match_level(
                 x_in, g_in, spec.window_offset(C, L), [i * stride for i in rolls], mask, scores=scores,
                 scores_cl=scores_cl if l == 0 else None, max_out=mx, inv_norm=inv,
                 xhat=xhat if l == 0 else None, scratch=scratch,
                 backend=cabi.BACKEND_SIMT if self.backend == cabi.BACKEND_SIMT else cabi.BACKEND_AUTO))
             scores_out.append(scores)
             lw = w["loc"][l]
-            up = self._deconv(lw["deconv"], x, C, None, 0, dtype, row_scale=inv, row_r1=mx)
+            nm = "loc%d" % (6 - l)
+            up = self._deconv(lw["deconv"], x, C, None, 0, dtype, row_scale=inv, row_r1=mx, name=nm)
             if l < 5:
-                h = self._conv3(lw["conv_a"], up, skips[l], dtype, relu=True)
-                x = self._conv3(lw["conv_b"], h, None, dtype, relu=False)
+                h = self._conv3(lw["conv_a"], up, skips[l], dtype, relu=True, name=nm + "a")
+                x = self._conv3(lw["conv_b"], h, None, dtype, relu=False, name=nm + "b")
             else:
-                h = self._conv3(lw["conv_a"], up, None, dtype, relu=True)
-                logits = self._conv3(lw["conv_b"], h, None, dtype, relu=False, planar_f32=True)  # [B,1,512,512]
+                h = self._conv3(lw["conv_a"], up, None, dtype, relu=True, name=nm + "a")
+                logits = self._conv3(lw["conv_b"], h, None, dtype, relu=False, planar_f32=True,
+                                     name=nm + "b")                                              # [B,1,512,512]
 
         # a10 -- heatmap
         Hh, Wh = logits.shape[-2:]
@@ -311,16 +313,17 @@ class PostEncoderPipeline:
         o = None
         for l in range(6):
             ow = w["ori"][l]
+            nm = "ori%d" % (6 - l)
             if l == 0:
-                o = self._deconv(ow["deconv"], scores_cl, SCORES_CL_PAD, xhat, D, dtype)
+                o = self._deconv(ow["deconv"], scores_cl, SCORES_CL_PAD, xhat, D, dtype, name=nm)
             else:
-                o = self._deconv(ow["deconv"], o, o.shape[-1], None, 0, dtype)
+                o = self._deconv(ow["deconv"], o, o.shape[-1], None, 0, dtype, name=nm)
             if l < 5:
-                o = self._conv3(ow["conv_a"], o, skips[l], dtype, relu=True)
-                o = self._conv3(ow["conv_b"], o, None, dtype, relu=False)
+                o = self._conv3(ow["conv_a"], o, skips[l], dtype, relu=True, name=nm + "a")
+                o = self._conv3(ow["conv_b"], o, None, dtype, relu=False, name=nm + "b")
             else:
-                o = self._conv3(ow["conv_a"], o, None, dtype, relu=True)
-                o = self._conv3(ow["conv_b"], o, None, dtype, relu=False, out_f32=True)   # [B,512,512,2] fp32
+                o = self._conv3(ow["conv_a"], o, None, dtype, relu=True, name=nm + "a")
+                o = self._conv3(ow["conv_b"], o, None, dtype, relu=False, out_f32=True, name=nm + "b")  # fp32 [B,512,512,2]
         ori = torch.empty((B, 2, Hh, Wh), dtype=f32, device=dev)
         o_in = o
         self._op("ori_normalize", 6.0 * B * Hh * Wh, 2.0 * B * Hh * Wh * (o.element_size() + 4),
