@@ -30,8 +30,8 @@ constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_SMEM_BUDGET = 200 * 1024;
 
 struct TcParams {
-  CUtensorMap tm_a0, tm_a1, tm_b;
-  int nb0, nb1, taps, n_tiles_n, total_tiles, block_n, stages;
+  CUtensorMap tm_a0, tm_a1, tm_b0, tm_b1;
+  int nb0, nb1, c0, c1, kw0, kw1, kpad0, kpad1, taps, n_tiles_n, total_tiles, block_n, stages;
   int tiles[4], box[4];
   int tap_off[9][4];
   int out_stride[4], extent[4];
@@ -118,14 +118,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (rows of 128 bytes, 8-row groups 1024 bytes apart).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+// K-major swizzled shared-memory matrix descriptor.  A K block of kw bf16 channels is one swizzle row of 2*kw bytes
+// (kw = 64 -> SWIZZLE_128B, 32 -> SWIZZLE_64B, 16 -> SWIZZLE_32B); 8 rows form a group, groups are 16*kw bytes apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, int kw) {
+  const uint64_t layout = kw == 64 ? 2 : (kw == 32 ? 4 : 6);
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);  // start address, 16-byte units
   d |= (uint64_t)1 << 16;                    // leading byte offset (unused for swizzled K-major), 16 B
-  d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset: next 8-row group
+  d |= (uint64_t)((16 * kw) >> 4) << 32;     // stride byte offset: next 8-row group
   d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+  d |= layout << 61;
   return d;
 }
 
@@ -137,11 +139,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) igemm_tcgen05_kernel(const __gr
   __shared__ __align__(8) uint64_t bar_tmem_full[2];
   __shared__ __align__(8) uint64_t bar_tmem_empty[2];
   __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(16) float s_bias[2][TC_MAX_N];
+  __shared__ __align__(16) float s_r1w[2][TC_MAX_N];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const int stage_bytes = TC_A_BYTES + p.block_n * TC_BK * 2;
+  const int stage_bytes = TC_A_BYTES + p.block_n * TC_BK * 2;   // sized for the widest (64-channel) K block
   const int nkb = p.taps * (p.nb0 + p.nb1);
 
   if (threadIdx.x == 0) {
@@ -157,8 +161,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) igemm_tcgen05_kernel(const __gr
   }
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tm_a0);
-    if (p.nb1) prefetch_tmap(&p.tm_a1);
-    prefetch_tmap(&p.tm_b);
+    prefetch_tmap(&p.tm_b0);
+    if (p.nb1) {
+      prefetch_tmap(&p.tm_a1);
+      prefetch_tmap(&p.tm_b1);
+    }
   }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
@@ -186,20 +193,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) igemm_tcgen05_kernel(const __gr
           mt /= p.tiles[d];
         }
         const int n0 = nt * p.block_n;
-        int kidx = 0;
         for (int tap = 0; tap < p.taps; ++tap) {
           const int c1 = base[0] + p.tap_off[tap][0], c2 = base[1] + p.tap_off[tap][1];
           const int c3 = base[2] + p.tap_off[tap][2], c4 = base[3] + p.tap_off[tap][3];
           for (int src = 0; src < 2; ++src) {
             const int nb = src ? p.nb1 : p.nb0;
+            const int kw = src ? p.kw1 : p.kw0;
             const CUtensorMap* tm = src ? &p.tm_a1 : &p.tm_a0;
-            for (int cb = 0; cb < nb; ++cb, ++kidx) {
+            const CUtensorMap* tmb = src ? &p.tm_b1 : &p.tm_b0;
+            const int kbase = tap * (p.kpad0 + p.kpad1) + (src ? p.kpad0 : 0);   // column of this source in W[n][.]
+            const uint32_t tx = (uint32_t)((TC_BM + p.block_n) * kw * 2);
+            for (int cb = 0; cb < nb; ++cb) {
               mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
               const uint32_t full = smem_u32(&bar_full[stage]);
               const uint32_t a_dst = smem_base + stage * stage_bytes;
-              mbar_arrive_expect_tx(full, (uint32_t)stage_bytes);
-              tma_load_5d(a_dst, tm, full, cb * TC_BK, c1, c2, c3, c4);
-              tma_load_2d(a_dst + TC_A_BYTES, &p.tm_b, full, kidx * TC_BK, n0);
+              mbar_arrive_expect_tx(full, tx);
+              tma_load_5d(a_dst, tm, full, cb * kw, c1, c2, c3, c4);
+              tma_load_2d(a_dst + TC_A_BYTES, tmb, full, kbase + cb * kw, n0);
               if (++stage == p.stages) {
                 stage = 0;
                 phase ^= 1u;
@@ -225,15 +235,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) igemm_tcgen05_kernel(const __gr
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * TC_MAX_N);
         for (int kb = 0; kb < nkb; ++kb) {
+          // number of 16-channel MMAs that carry data in this K block (the rest is TMA zero fill)
+          const int within = kb % (p.nb0 + p.nb1);
+          const bool s1 = within >= p.nb0;
+          const int kw = s1 ? p.kw1 : p.kw0;
+          const int cvalid = s1 ? p.c1 - (within - p.nb0) * kw : p.c0 - within * kw;
+          const int nk16 = cvalid >= kw ? kw / 16 : (cvalid + 15) >> 4;
           mbar_wait(smem_u32(&bar_full[stage]), phase);
           tc_fence_after();
           const uint32_t a_addr = smem_base + stage * stage_bytes;
-          const uint64_t adesc = make_smem_desc(a_addr);
-          const uint64_t bdesc = make_smem_desc(a_addr + TC_A_BYTES);
+          const uint64_t adesc = make_smem_desc(a_addr, kw);
+          const uint64_t bdesc = make_smem_desc(a_addr + TC_A_BYTES, kw);
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k) {
             // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the 16-byte address field
-            umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+            if (k < nk16) umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
           }
           umma_commit(smem_u32(&bar_empty[stage]));   // frees the smem slot once these MMAs have read it
           if (++stage == p.stages) {
@@ -248,14 +264,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) igemm_tcgen05_kernel(const __gr
     // ===================== epilogue (4 warps, warp w owns TMEM lanes 32*(w%4) .. +31) =====================
     const int ew = warp & 3;
     const int row = ew * 32 + lane;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      const int nt = tile % p.n_tiles_n;
+    const int et = threadIdx.x - 128;                 // 0..127 within the epilogue group
+    const bool fixed_n = (p.n_tiles_n == 1);
+    const bool has_r1 = (p.row_r1 != nullptr), has_rs = (p.row_scale != nullptr);
+
+    // per-column epilogue vectors live in shared memory (one copy per accumulator stage)
+    auto stage_vectors = [&](int buf, int n0) {
+      for (int c = et; c < p.block_n; c += 128) {
+        const int n = n0 + c;
+        s_bias[buf][c] = (p.bias && n < p.N) ? __ldg(p.bias + n) : 0.f;
+        s_r1w[buf][c] = (has_r1 && n < p.N) ? __ldg(p.r1_w + n) : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    };
+    // row -> output pixel of a tile
+    auto locate = [&](int tile, int& m_glob, bool& valid) {
       int mt = tile / p.n_tiles_n;
-      // row -> output pixel
       int r = row;
-      int m_glob = 0;
-      bool valid = true;
+      m_glob = 0;
+      valid = true;
 #pragma unroll
       for (int d = 0; d < 4; ++d) {
         const int coord = (mt % p.tiles[d]) * p.box[d] + (r % p.box[d]);
@@ -264,63 +291,98 @@ __global__ void __launch_bounds__(TC_THREADS, 1) igemm_tcgen05_kernel(const __gr
         valid = valid && (coord < p.extent[d]);
         m_glob += coord * p.out_stride[d];
       }
+    };
+
+    if (fixed_n) stage_vectors(0, 0);
+    int m_glob, m_next = 0;
+    bool valid, valid_next = false;
+    float rs = 1.f, r1 = 0.f, rs_next = 1.f, r1_next = 0.f;
+    if ((int)blockIdx.x < p.total_tiles) {
+      locate(blockIdx.x, m_next, valid_next);
+      if (valid_next) {
+        if (has_rs) rs_next = __ldg(p.row_scale + m_next);
+        if (has_r1) r1_next = __ldg(p.row_r1 + m_next);
+      }
+    }
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      m_glob = m_next; valid = valid_next; rs = rs_next; r1 = r1_next;
+      {  // prefetch the per-row scalars of the next tile: their latency hides behind this tile's epilogue
+        const int nxt = tile + gridDim.x;
+        rs_next = 1.f; r1_next = 0.f; valid_next = false;
+        if (nxt < p.total_tiles) {
+          locate(nxt, m_next, valid_next);
+          if (valid_next) {
+            if (has_rs) rs_next = __ldg(p.row_scale + m_next);
+            if (has_r1) r1_next = __ldg(p.row_r1 + m_next);
+          }
+        }
+      }
+      const int nt = tile % p.n_tiles_n;
       const int n0 = nt * p.block_n;
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-      float rs = 1.f, r1 = 0.f;
-      if (valid) {
-        if (p.row_scale) rs = __ldg(p.row_scale + m_glob);
-        if (p.row_r1) r1 = __ldg(p.row_r1 + m_glob);
+      const int vb = fixed_n ? 0 : acc;
+      if (!fixed_n) stage_vectors(acc, n0);
+
+      // output addressing (hoisted out of the column loop)
+      int64_t base_px[4];
+      int64_t plane0 = 0;
+      if (p.out_mode == 0) {
+        base_px[0] = (int64_t)m_glob * p.ldo;
+      } else {
+        const int b_img = m_glob / p.HWo;
+        const int hw = m_glob - b_img * p.HWo;
+        if (p.out_mode == 2) {
+          plane0 = (int64_t)b_img * p.N * p.HWo + hw;
+        } else {
+          const int h = hw / p.Wout, w = hw - h * p.Wout;
+#pragma unroll
+          for (int ij = 0; ij < 4; ++ij)
+            base_px[ij] = (((int64_t)b_img * 2 * p.Hout + 2 * h + (ij >> 1)) * (2 * p.Wout) + 2 * w + (ij & 1)) * p.ldo;
+        }
       }
-      // output addressing
-      int b_img = 0, hw = 0;
-      if (p.out_mode != 0) {
-        b_img = m_glob / p.HWo;
-        hw = m_glob - b_img * p.HWo;
+      const int cout = p.out_mode == 1 ? (p.N >> 2) : p.N;
+      int ij = 0, co = n0;                       // running (quadrant, channel) of column n0 + c
+      if (p.out_mode == 1) {
+        ij = n0 / cout;
+        co = n0 - ij * cout;
       }
+
       mbar_wait(smem_u32(&bar_tmem_full[acc]), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * TC_MAX_N);
-      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(taddr + (uint32_t)c0, v);
-        tmem_ld_wait();
-        if (!valid) continue;
-        const int nbase = n0 + c0;
+
+      auto process = [&](const uint32_t (&v)[32], int c0) {
+        if (!valid) return;
 #pragma unroll
         for (int g8 = 0; g8 < 4; ++g8) {
-          const int n = nbase + g8 * 8;
-          if (n >= p.N) break;
-          float y[8];
+          const int cl = c0 + g8 * 8;             // column within the tile
+          const int n = n0 + cl;
+          if (n >= p.N || cl >= p.block_n) break;
+          const float4 b0 = *reinterpret_cast<const float4*>(&s_bias[vb][cl]);
+          const float4 b1 = *reinterpret_cast<const float4*>(&s_bias[vb][cl + 4]);
+          float y[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          if (has_r1) {
+            const float4 w0 = *reinterpret_cast<const float4*>(&s_r1w[vb][cl]);
+            const float4 w1 = *reinterpret_cast<const float4*>(&s_r1w[vb][cl + 4]);
+            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) y[j] = fmaf(r1, wv[j], y[j]);
+          }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            float a = __uint_as_float(v[g8 * 8 + j]);
-            const int nn = n + j;
-            if (nn < p.N) {
-              if (p.row_scale) a *= rs;
-              if (p.row_r1) a = fmaf(r1, __ldg(p.r1_w + nn), a);
-              if (p.bias) a += __ldg(p.bias + nn);
-              if (p.relu) a = fmaxf(a, 0.f);
-            }
-            y[j] = a;
+            y[j] = fmaf(__uint_as_float(v[g8 * 8 + j]), rs, y[j]);
+            if (p.relu) y[j] = fmaxf(y[j], 0.f);
           }
           if (p.out_mode == 2) {
-            float* o = static_cast<float*>(p.out);
+            float* o = static_cast<float*>(p.out) + plane0;
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              if (n + j < p.N) o[((int64_t)b_img * p.N + n + j) * p.HWo + hw] = y[j];
+              if (n + j < p.N) o[(int64_t)(n + j) * p.HWo] = y[j];
             continue;
           }
-          int64_t off;
-          if (p.out_mode == 0) {
-            off = (int64_t)m_glob * p.ldo + n;
-          } else {
-            const int cout = p.N >> 2;
-            const int ij = n / cout;
-            const int co = n - ij * cout;
-            const int h = hw / p.Wout, w = hw - h * p.Wout;
-            off = (((int64_t)b_img * 2 * p.Hout + 2 * h + (ij >> 1)) * (2 * p.Wout) + 2 * w + (ij & 1)) * p.ldo + co;
-          }
+          const int64_t off = (p.out_mode == 0 ? base_px[0] : base_px[ij]) + co;
           const bool full8 = (n + 8 <= p.N);
           if (p.out_f32) {
             float* o = static_cast<float*>(p.out) + off;
@@ -349,6 +411,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) igemm_tcgen05_kernel(const __gr
                 if (n + j < p.N) o[j] = __float2bfloat16_rn(y[j]);
             }
           }
+          co += 8;
+          if (p.out_mode == 1 && co >= cout) {
+            co -= cout;
+            ++ij;
+          }
+        }
+      };
+
+      // TMEM -> registers, double buffered: the load of chunk c+1 is in flight while chunk c is processed
+      uint32_t va[32], vb2[32];
+      tmem_ld32(taddr, va);
+      for (int c0 = 0; c0 < p.block_n; c0 += 64) {
+        tmem_ld_wait();
+        const bool more1 = (c0 + 32 < p.block_n);
+        if (more1) tmem_ld32(taddr + (uint32_t)(c0 + 32), vb2);
+        process(va, c0);
+        if (more1) {
+          tmem_ld_wait();
+          if (c0 + 64 < p.block_n) tmem_ld32(taddr + (uint32_t)(c0 + 64), va);
+          process(vb2, c0 + 32);
         }
       }
       // release the accumulator stage back to the MMA issuer
@@ -385,7 +467,7 @@ static EncodeTiledFn encode_fn() {
 }
 
 static int encode_map(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                      const uint32_t* box) {
+                      const uint32_t* box, int kw) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail(CCVPE_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t gdim[5];
@@ -398,7 +480,9 @@ static int encode_map(CUtensorMap* tm, const void* base, int rank, const uint64_
   }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  kw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kw == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B),
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(CCVPE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rank=%d dims=[%llu,%llu,%llu,..] box=[%u,%u,%u,..]",
@@ -408,6 +492,11 @@ static int encode_map(CUtensorMap* tm, const void* base, int rank, const uint64_
 }
 
 static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+// K-block width (bf16 channels) used for a source with c channels; one block is one swizzle row of 2*width bytes.
+// Narrow sources get narrow blocks so TMA neither over-fetches nor zero-fills most of the tile (include/ccvpe_b200.h
+// documents the same rule for the w_nk weight layout).
+static int tc_block_width(int c) { return c <= 16 ? 16 : (c < 96 ? 32 : 64); }
 
 struct TcGeometry {
   bool cell;        // k2 s2 cell-descriptor gather
@@ -453,8 +542,14 @@ int igemm_tcgen05(const ccvpe_igemm_desc& d, cudaStream_t st) {
 
   static thread_local TcParams p;   // > 1 KB: keep it off the stack; it is copied at launch
   memset(&p, 0, sizeof(p));
-  p.nb0 = (d.c0 + TC_BK - 1) / TC_BK;
-  p.nb1 = (d.c1 + TC_BK - 1) / TC_BK;
+  p.kw0 = tc_block_width(d.c0);
+  p.kw1 = d.c1 ? tc_block_width(d.c1) : 64;
+  p.nb0 = (d.c0 + p.kw0 - 1) / p.kw0;
+  p.nb1 = (d.c1 + p.kw1 - 1) / p.kw1;
+  p.kpad0 = p.nb0 * p.kw0;
+  p.kpad1 = p.nb1 * p.kw1;
+  p.c0 = d.c0;
+  p.c1 = d.c1;
   p.taps = d.kh * d.kw;
   const int n_tiles_n = (d.N + TC_MAX_N - 1) / TC_MAX_N;
   int block_n = ((d.N + n_tiles_n - 1) / n_tiles_n + 15) / 16 * 16;
@@ -464,7 +559,7 @@ int igemm_tcgen05(const ccvpe_igemm_desc& d, cudaStream_t st) {
   int stages = TC_SMEM_BUDGET / stage_bytes;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   p.stages = stages;
-  const int64_t ktot = (int64_t)p.taps * (p.nb0 + p.nb1) * TC_BK;
+  const int64_t ktot = (int64_t)p.taps * (p.kpad0 + p.kpad1);
 
   int rc;
   const uint64_t esz = 2;
@@ -473,8 +568,8 @@ int igemm_tcgen05(const ccvpe_igemm_desc& d, cudaStream_t st) {
     uint64_t dims[5] = {(uint64_t)d.c0, 2, 8, 2, (uint64_t)8 * d.B};
     uint64_t str[4] = {(uint64_t)d.ld0 * esz, 2ull * d.ld0 * esz, (uint64_t)d.Win * d.ld0 * esz,
                        2ull * d.Win * d.ld0 * esz};
-    uint32_t box[5] = {TC_BK, 1, 8, 1, 16};
-    if ((rc = encode_map(&p.tm_a0, d.a0, 5, dims, str, box)) != CCVPE_OK) return rc;
+    uint32_t box[5] = {(uint32_t)p.kw0, 1, 8, 1, 16};
+    if ((rc = encode_map(&p.tm_a0, d.a0, 5, dims, str, box, p.kw0)) != CCVPE_OK) return rc;
     p.tiles[0] = 1; p.tiles[1] = 1; p.tiles[2] = 1; p.tiles[3] = (8 * d.B + 15) / 16;
     p.box[0] = 1; p.box[1] = 8; p.box[2] = 1; p.box[3] = 16;
     for (int t = 0; t < 4; ++t) {
@@ -493,8 +588,9 @@ int igemm_tcgen05(const ccvpe_igemm_desc& d, cudaStream_t st) {
       uint64_t dims[5] = {(uint64_t)c, (uint64_t)d.Win, (uint64_t)d.Hin, (uint64_t)d.B, 1};
       uint64_t str[4] = {(uint64_t)ld * esz, (uint64_t)d.Win * ld * esz, (uint64_t)d.Hin * d.Win * ld * esz,
                          (uint64_t)d.B * d.Hin * d.Win * ld * esz};
-      uint32_t box[5] = {TC_BK, (uint32_t)g.tw, (uint32_t)g.th, (uint32_t)g.tb, 1};
-      if ((rc = encode_map(s ? &p.tm_a1 : &p.tm_a0, base, 5, dims, str, box)) != CCVPE_OK) return rc;
+      const int kw = s ? p.kw1 : p.kw0;
+      uint32_t box[5] = {(uint32_t)kw, (uint32_t)g.tw, (uint32_t)g.th, (uint32_t)g.tb, 1};
+      if ((rc = encode_map(s ? &p.tm_a1 : &p.tm_a0, base, 5, dims, str, box, kw)) != CCVPE_OK) return rc;
     }
     p.tiles[0] = d.Wout / g.tw; p.tiles[1] = d.Hout / g.th; p.tiles[2] = (d.B + g.tb - 1) / g.tb; p.tiles[3] = 1;
     p.box[0] = g.tw; p.box[1] = g.th; p.box[2] = g.tb; p.box[3] = 1;
@@ -507,11 +603,12 @@ int igemm_tcgen05(const ccvpe_igemm_desc& d, cudaStream_t st) {
     p.out_stride[0] = 1; p.out_stride[1] = d.Wout; p.out_stride[2] = d.Hout * d.Wout; p.out_stride[3] = 0;
     p.extent[0] = d.Wout; p.extent[1] = d.Hout; p.extent[2] = d.B; p.extent[3] = 1;
   }
-  {
+  for (int s = 0; s < (d.c1 ? 2 : 1); ++s) {
+    const int kw = s ? p.kw1 : p.kw0;
     uint64_t dims[2] = {(uint64_t)ktot, (uint64_t)d.N};
     uint64_t str[1] = {(uint64_t)ktot * esz};
-    uint32_t box[2] = {TC_BK, (uint32_t)block_n};
-    if ((rc = encode_map(&p.tm_b, d.w_nk, 2, dims, str, box)) != CCVPE_OK) return rc;
+    uint32_t box[2] = {(uint32_t)kw, (uint32_t)block_n};
+    if ((rc = encode_map(s ? &p.tm_b1 : &p.tm_b0, d.w_nk, 2, dims, str, box, kw)) != CCVPE_OK) return rc;
   }
   const int m_tiles = p.tiles[0] * p.tiles[1] * p.tiles[2] * p.tiles[3];
   p.total_tiles = m_tiles * n_tiles_n;
@@ -532,7 +629,7 @@ int igemm_tcgen05(const ccvpe_igemm_desc& d, cudaStream_t st) {
   const int smem = stages * stage_bytes + 1024;
   static thread_local int smem_attr_set = 0;
   if (smem_attr_set < smem) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
+    cudaError_t e = cudaFuncSetAttribute(igemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8192);
     if (e != cudaSuccess) return fail(CCVPE_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     smem_attr_set = 227 * 1024;
   }

@@ -107,9 +107,9 @@ class PostEncoderPipeline:
         tc = dtype == torch.bfloat16     # also build the K-major layout of the tcgen05 backend
 
         def nk(per_tap_rows: torch.Tensor, splits: Sequence[int]) -> torch.Tensor:
-            """[N, taps, K] -> [N, taps, sum(pad64(split))] bf16 with every source's K range zero padded to 64."""
+            """[N, taps, K] -> [N, taps, sum(pad64(split))] bf16 with every source K range zero padded to its K-block width (see ccvpe_b200.h)."""
             N_, taps, _ = per_tap_rows.shape
-            pads = [(c + 63) // 64 * 64 for c in splits]
+            pads = [-(-c // kw) * kw for c, kw in ((c, 16 if c <= 16 else (32 if c < 96 else 64)) for c in splits)]
             out = torch.zeros((N_, taps, sum(pads)), dtype=torch.bfloat16, device=per_tap_rows.device)
             src = dst = 0
             for c, cp in zip(splits, pads):

@@ -83,7 +83,8 @@ typedef struct ccvpe_igemm_desc {
   int32_t dtype;                 /* CCVPE_F32 / CCVPE_BF16: element type of sources and weights                     */
   /* weights, one of (depending on backend):
    *   w_kn : [taps][c0 + c1][N]                     (N contiguous)       -- SIMT backend
-   *   w_nk : [N_pad16][taps][c0_pad64 + c1_pad64]   (K contiguous, bf16) -- tcgen05 backend                        */
+   *   w_nk : [N][taps][pad(c0) + pad(c1)]           (K contiguous, bf16) -- tcgen05 backend; pad(c) rounds c up to
+   *          a multiple of the source's K-block width kw(c) = 16 if c <= 16, 32 if c < 96, else 64 (zero filled)   */
   const void* w_kn; const void* w_nk;
   const float* bias;             /* [N] fp32 or NULL                                                                */
   const float* row_scale;        /* [M] fp32 or NULL                                                                */
