@@ -1,0 +1,321 @@
+// Row-ring 3x3 convolution on tcgen05 -- the path for the wide, shallow decoder levels (W >= 128, C <= ~100), which
+// are HBM-bound and where the generic per-tap pipeline is limited by TMA's per-row issue rate (measured on B200:
+// ~3.5 cycles per box row, scripts/tma_probe.cu) and by one barrier round trip per tiny K block.
+//
+// A CTA walks a 128-pixel-wide strip of one image downwards.  Every INPUT row segment (130 pixels: the strip plus a
+// one-pixel halo, out-of-image pixels are TMA zero fill) is loaded ONCE into a ring of shared-memory row slots; the nine
+// taps of an output row are nine shifted views of three ring slots: tap (dy, dx) reads slot(y + dy - 1) starting dx
+// rows into the tile, which for the dense K-major swizzled layout is just a start-address offset of the UMMA
+// descriptor (the swizzle XOR is a function of the absolute shared-memory address, the same one TMA used to write).
+// All weights of the layer stay resident in shared memory, so the steady state is: 1 TMA row load, 1 barrier wait,
+// 9 x blocks MMAs, 1 commit per 128 output pixels, and HBM/L2 traffic of exactly one read of the input.
+//
+// Warp roles and the epilogue are the same as in igemm_tcgen05.cu (shared through tcgen05_common.cuh).
+#include "tcgen05_common.cuh"
+
+namespace ccvpe {
+
+constexpr int RING_THREADS = 384;
+constexpr int RING_MAX_DEPTH = 8;
+constexpr int RING_HALO_W = TC_BM + 2;
+constexpr int RING_SMEM_BUDGET = 208 * 1024;
+
+struct RingParams {
+  CUtensorMap tm_a0, tm_a1, tm_b0, tm_b1;
+  int nb0, nb1, c0, c1, kw0, kw1, kpad0, kpad1;
+  int block_n, depth;
+  int B, H, W, strips, R, chunks, total_units;
+  int a_blk0, a_blk1, row_bytes;      // ring slot geometry
+  int w_blk0, w_blk1, w_tap_bytes;    // resident weight geometry
+  int tx_row, tx_weights;
+  EpiParams e;
+};
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          dst),
+      "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(RING_THREADS, 1) conv_ring_tcgen05_kernel(const __grid_constant__ RingParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[RING_MAX_DEPTH];
+  __shared__ __align__(8) uint64_t bar_empty[RING_MAX_DEPTH];
+  __shared__ __align__(8) uint64_t bar_w;
+  __shared__ __align__(8) uint64_t bar_tmem_full[2];
+  __shared__ __align__(8) uint64_t bar_tmem_empty[2];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(16) float s_bias[TC_MAX_N];
+  __shared__ __align__(16) float s_r1w[TC_MAX_N];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t w_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t ring_base = w_base + 9u * (uint32_t)p.w_tap_bytes;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.depth; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    mbar_init(smem_u32(&bar_w), 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(&bar_tmem_full[a]), 1);
+      mbar_init(smem_u32(&bar_tmem_empty[a]), TC_EPI_THREADS / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tm_a0);
+    prefetch_tmap(&p.tm_b0);
+    if (p.nb1) {
+      prefetch_tmap(&p.tm_a1);
+      prefetch_tmap(&p.tm_b1);
+    }
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                 "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      // all weights of the layer, once
+      mbar_arrive_expect_tx(smem_u32(&bar_w), (uint32_t)p.tx_weights);
+      for (int tap = 0; tap < 9; ++tap) {
+        uint32_t dst = w_base + (uint32_t)(tap * p.w_tap_bytes);
+        const int kcol = tap * (p.kpad0 + p.kpad1);
+        for (int cb = 0; cb < p.nb0; ++cb, dst += p.w_blk0) tma_load_2d(dst, &p.tm_b0, smem_u32(&bar_w), kcol + cb * p.kw0, 0);
+        for (int cb = 0; cb < p.nb1; ++cb, dst += p.w_blk1)
+          tma_load_2d(dst, &p.tm_b1, smem_u32(&bar_w), kcol + p.kpad0 + cb * p.kw1, 0);
+      }
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int unit = blockIdx.x; unit < p.total_units; unit += gridDim.x) {
+        const int rc = unit % p.chunks;
+        const int xs = (unit / p.chunks) % p.strips;
+        const int b = unit / (p.chunks * p.strips);
+        const int y0 = rc * p.R, x0 = xs * TC_BM;
+        const int y_lo = y0 > 0 ? y0 - 1 : 0;
+        const int y_hi = (y0 + p.R < p.H) ? y0 + p.R : p.H - 1;
+        for (int y = y_lo; y <= y_hi; ++y) {
+          mbar_wait(smem_u32(&bar_empty[slot]), phase ^ 1u);
+          const uint32_t full = smem_u32(&bar_full[slot]);
+          mbar_arrive_expect_tx(full, (uint32_t)p.tx_row);
+          uint32_t dst = ring_base + (uint32_t)(slot * p.row_bytes);
+          const int yrow = b * p.H + y;
+          for (int cb = 0; cb < p.nb0; ++cb, dst += p.a_blk0) tma_load_3d(dst, &p.tm_a0, full, cb * p.kw0, x0 - 1, yrow);
+          for (int cb = 0; cb < p.nb1; ++cb, dst += p.a_blk1) tma_load_3d(dst, &p.tm_a1, full, cb * p.kw1, x0 - 1, yrow);
+          if (++slot == p.depth) {
+            slot = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) |
+                             ((uint32_t)(TC_BM >> 4) << 24);
+      const uint32_t hi0 = (uint32_t)(make_smem_desc(0, p.kw0) >> 32), hi1 = (uint32_t)(make_smem_desc(0, p.kw1) >> 32);
+      const int full0 = p.kw0 >> 4, full1 = p.kw1 >> 4;
+      const int tail0 = (p.c0 - (p.nb0 - 1) * p.kw0 + 15) >> 4, tail1 = p.nb1 ? (p.c1 - (p.nb1 - 1) * p.kw1 + 15) >> 4 : 0;
+      const uint32_t lo_flag = 1u << 16;
+      mbar_wait(smem_u32(&bar_w), 0);
+      tc_fence_after();
+      int ctr = 0;            // rows consumed from the ring so far (same sequence as the producer)
+      int it = 0;
+      for (int unit = blockIdx.x; unit < p.total_units; unit += gridDim.x) {
+        const int rc = unit % p.chunks;
+        const int y0 = rc * p.R;
+        const int y_lo = y0 > 0 ? y0 - 1 : 0;
+        const int y_hi = (y0 + p.R < p.H) ? y0 + p.R : p.H - 1;
+        int waited = ctr - 1;  // highest ring row counter whose data is known to have landed
+        for (int yo = y0; yo < y0 + p.R; ++yo, ++it) {
+          const int acc = it & 1;
+          const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+          mbar_wait(smem_u32(&bar_tmem_empty[acc]), acc_phase ^ 1u);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + (uint32_t)(acc * TC_MAX_N);
+          uint32_t accumulate = 0;
+#pragma unroll 1
+          for (int dy = 0; dy < 3; ++dy) {
+            const int yi = yo + dy - 1;
+            if (yi < 0 || yi >= p.H) continue;       // zero padding rows contribute nothing
+            const int rctr = ctr + (yi - y_lo);
+            const int slot = rctr % p.depth;
+            if (rctr > waited) {
+              mbar_wait(smem_u32(&bar_full[slot]), (uint32_t)(rctr / p.depth) & 1u);
+              tc_fence_after();
+              waited = rctr;
+            }
+            uint32_t a_tile = ring_base + (uint32_t)(slot * p.row_bytes);
+            uint32_t w_tile = w_base + (uint32_t)(dy * 3 * p.w_tap_bytes);
+#pragma unroll 1
+            for (int src = 0; src < 2; ++src) {
+              const int nb = src ? p.nb1 : p.nb0;
+              const uint32_t hi = src ? hi1 : hi0;
+              const int nfull = src ? full1 : full0, ntail = src ? tail1 : tail0;
+              const uint32_t a_blk = src ? p.a_blk1 : p.a_blk0, w_blk = src ? p.w_blk1 : p.w_blk0;
+              const uint32_t row_b = (uint32_t)(src ? p.kw1 : p.kw0) * 2u;
+#pragma unroll 1
+              for (int cb = 0; cb < nb; ++cb, a_tile += a_blk, w_tile += w_blk) {
+                const int nk16 = (cb == nb - 1) ? ntail : nfull;
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                  // tap (dy, dx): rows [dx, dx + 128) of the halo'd row tile; weights of tap dy*3 + dx
+                  const uint32_t a_lo = (((a_tile + dx * row_b) & 0x3FFFFu) >> 4) | lo_flag;
+                  const uint32_t b_lo = (((w_tile + dx * (uint32_t)p.w_tap_bytes) & 0x3FFFFu) >> 4) | lo_flag;
+                  const uint64_t adesc = ((uint64_t)hi << 32) | a_lo;
+                  const uint64_t bdesc = ((uint64_t)hi << 32) | b_lo;
+                  umma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);
+                  accumulate = 1;
+                  if (nk16 > 1) umma_bf16(tmem_d, adesc + 2, bdesc + 2, idesc, 1u);
+                  if (nk16 > 2) umma_bf16(tmem_d, adesc + 4, bdesc + 4, idesc, 1u);
+                  if (nk16 > 3) umma_bf16(tmem_d, adesc + 6, bdesc + 6, idesc, 1u);
+                }
+              }
+            }
+          }
+          umma_commit(smem_u32(&bar_tmem_full[acc]));
+          // input row yo-1 has no later reader; the last output row of the unit also retires rows yo and yo+1
+          if (yo - 1 >= y_lo) umma_commit(smem_u32(&bar_empty[(ctr + (yo - 1 - y_lo)) % p.depth]));
+          if (yo == y0 + p.R - 1) {
+            umma_commit(smem_u32(&bar_empty[(ctr + (yo - y_lo)) % p.depth]));
+            if (yo + 1 <= y_hi) umma_commit(smem_u32(&bar_empty[(ctr + (yo + 1 - y_lo)) % p.depth]));
+          }
+        }
+        ctr += y_hi - y_lo + 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int ew = warp & 3;
+    const int half = (warp - 4) >> 2;
+    const int row = ew * 32 + lane;
+    const int et = threadIdx.x - 128;
+    epi_stage_vectors(p.e, s_bias, s_r1w, 0, p.block_n, et);
+    int it = 0;
+    for (int unit = blockIdx.x; unit < p.total_units; unit += gridDim.x) {
+      const int rc = unit % p.chunks;
+      const int xs = (unit / p.chunks) % p.strips;
+      const int b = unit / (p.chunks * p.strips);
+      const int y0 = rc * p.R, x0 = xs * TC_BM;
+      for (int yo = y0; yo < y0 + p.R; ++yo, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+        const int m_glob = (b * p.H + yo) * p.W + x0 + row;
+        float rs = 1.f, r1 = 0.f;
+        if (p.e.row_scale) rs = __ldg(p.e.row_scale + m_glob);
+        if (p.e.row_r1) r1 = __ldg(p.e.row_r1 + m_glob);
+        mbar_wait(smem_u32(&bar_tmem_full[acc]), acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * TC_MAX_N);
+        epi_store_row(p.e, taddr, half, p.block_n, 0, true, m_glob, rs, r1, s_bias, s_r1w);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty[acc]));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------
+static int round1k(int v) { return (v + 1023) / 1024 * 1024; }
+
+static bool ring_plan(const ccvpe_igemm_desc& d, RingParams* p) {
+  if (d.dtype != CCVPE_BF16 || !d.w_nk) return false;
+  if (d.stride != 1 || d.kh != 3 || d.kw != 3 || d.pad != 1) return false;
+  if (d.Hin != d.Hout || d.Win != d.Wout || d.Wout % TC_BM != 0) return false;
+  if (d.out_mode == 1 || d.N > TC_MAX_N) return false;
+  p->kw0 = tc_block_width(d.c0);
+  p->kw1 = d.c1 ? tc_block_width(d.c1) : 64;
+  p->nb0 = (d.c0 + p->kw0 - 1) / p->kw0;
+  p->nb1 = d.c1 ? (d.c1 + p->kw1 - 1) / p->kw1 : 0;
+  p->kpad0 = p->nb0 * p->kw0;
+  p->kpad1 = p->nb1 * p->kw1;
+  p->c0 = d.c0;
+  p->c1 = d.c1;
+  p->block_n = (d.N + 15) / 16 * 16;
+  p->a_blk0 = round1k(RING_HALO_W * p->kw0 * 2);
+  p->a_blk1 = round1k(RING_HALO_W * p->kw1 * 2);
+  p->row_bytes = p->nb0 * p->a_blk0 + p->nb1 * p->a_blk1;
+  p->w_blk0 = round1k(p->block_n * p->kw0 * 2);
+  p->w_blk1 = round1k(p->block_n * p->kw1 * 2);
+  p->w_tap_bytes = p->nb0 * p->w_blk0 + p->nb1 * p->w_blk1;
+  p->tx_row = (p->nb0 * p->kw0 + p->nb1 * p->kw1) * RING_HALO_W * 2;
+  p->tx_weights = 9 * (p->nb0 * p->kw0 + p->nb1 * p->kw1) * p->block_n * 2;
+  const int avail = RING_SMEM_BUDGET - 9 * p->w_tap_bytes;
+  if (avail < 4 * p->row_bytes) return false;
+  int depth = avail / p->row_bytes;
+  p->depth = depth > RING_MAX_DEPTH ? RING_MAX_DEPTH : depth;
+  p->B = d.B;
+  p->H = d.Hout;
+  p->W = d.Wout;
+  p->strips = d.Wout / TC_BM;
+  int R = 32;
+  while (R > 4 && ((int64_t)d.B * p->strips * (d.Hout / R) < 3 * (int64_t)sm_count() || d.Hout % R != 0)) R >>= 1;
+  if (d.Hout % R != 0) return false;
+  p->R = R;
+  p->chunks = d.Hout / R;
+  p->total_units = d.B * p->strips * p->chunks;
+  return true;
+}
+
+bool conv_ring_supported(const ccvpe_igemm_desc& d) {
+  static thread_local RingParams probe;
+  return ring_plan(d, &probe);
+}
+
+int conv_ring_tcgen05(const ccvpe_igemm_desc& d, cudaStream_t st) {
+  static thread_local RingParams p;
+  memset(&p, 0, sizeof(p));
+  if (!ring_plan(d, &p)) return fail(CCVPE_ERR_UNSUPPORTED, "conv_ring_tcgen05: unsupported shape");
+  int rc;
+  const uint64_t esz = 2;
+  for (int s = 0; s < (d.c1 ? 2 : 1); ++s) {
+    const void* base = s ? d.a1 : d.a0;
+    const int c = s ? d.c1 : d.c0, ld = s ? d.ld1 : d.ld0, kw = s ? p.kw1 : p.kw0;
+    uint64_t dims[3] = {(uint64_t)c, (uint64_t)d.Win, (uint64_t)d.B * d.Hin};
+    uint64_t str[2] = {(uint64_t)ld * esz, (uint64_t)d.Win * ld * esz};
+    uint32_t box[3] = {(uint32_t)kw, (uint32_t)RING_HALO_W, 1};
+    if ((rc = encode_map(s ? &p.tm_a1 : &p.tm_a0, base, 3, dims, str, box, kw)) != CCVPE_OK) return rc;
+    const uint64_t ktot = 9ull * (p.kpad0 + p.kpad1);
+    uint64_t wdims[2] = {ktot, (uint64_t)d.N};
+    uint64_t wstr[1] = {ktot * esz};
+    uint32_t wbox[2] = {(uint32_t)kw, (uint32_t)p.block_n};
+    if ((rc = encode_map(s ? &p.tm_b1 : &p.tm_b0, d.w_nk, 2, wdims, wstr, wbox, kw)) != CCVPE_OK) return rc;
+  }
+  fill_epi(p.e, d);
+  int smem = 9 * p.w_tap_bytes + p.depth * p.row_bytes + 1024;
+  if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: each CTA allocates all 512 TMEM columns
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_ring_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         RING_SMEM_BUDGET + 2048);
+    if (e != cudaSuccess) return fail(CCVPE_ERR_CUDA, "cudaFuncSetAttribute(ring): %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int grid = p.total_units < sm_count() ? p.total_units : sm_count();
+  conv_ring_tcgen05_kernel<<<grid, RING_THREADS, smem, st>>>(p);
+  return check_launch("conv_ring_tcgen05_kernel");
+}
+
+}  // namespace ccvpe

@@ -4,6 +4,8 @@
 //
 // Tile: 128 output pixels x 64 output channels x 16 input channels per step, 256 threads, 8x4 outputs per thread.
 // The K loop walks taps x {source 0, source 1} x channel chunks, so torch.cat([x, skip]) is never materialised.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace ccvpe {
@@ -209,6 +211,8 @@ int igemm_simt(const ccvpe_igemm_desc& d, cudaStream_t st) {
 
 int igemm_tcgen05(const ccvpe_igemm_desc& d, cudaStream_t st);  // igemm_tcgen05.cu
 bool igemm_tcgen05_supported(const ccvpe_igemm_desc& d);
+int conv_ring_tcgen05(const ccvpe_igemm_desc& d, cudaStream_t st);  // conv_ring_tcgen05.cu
+bool conv_ring_supported(const ccvpe_igemm_desc& d);
 
 }  // namespace ccvpe
 
@@ -236,7 +240,12 @@ extern "C" int ccvpe_igemm(const ccvpe_igemm_desc* desc, void* stream) {
   if (backend == CCVPE_BACKEND_AUTO)
     backend = (d.dtype == CCVPE_BF16 && d.w_nk && igemm_tcgen05_supported(d)) ? CCVPE_BACKEND_TCGEN05
                                                                                : CCVPE_BACKEND_SIMT;
-  if (backend == CCVPE_BACKEND_TCGEN05) return igemm_tcgen05(d, st);
+  if (backend == CCVPE_BACKEND_TCGEN05) {
+    // wide shallow 3x3 levels take the row-ring kernel (CCVPE_DISABLE_RING=1 forces the generic pipeline: A/B tests)
+    static const bool ring_off = getenv("CCVPE_DISABLE_RING") != nullptr;
+    if (!ring_off && conv_ring_supported(d)) return conv_ring_tcgen05(d, st);
+    return igemm_tcgen05(d, st);
+  }
   if (backend == CCVPE_BACKEND_SIMT) return igemm_simt(d, st);
   return fail(CCVPE_ERR_BAD_ARGUMENT, "ccvpe_igemm: unknown backend %d", d.backend);
 }

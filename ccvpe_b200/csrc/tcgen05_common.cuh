@@ -1,0 +1,305 @@
+// Shared pieces of the tcgen05 kernels: PTX wrappers (mbarrier, TMA, tcgen05.mma / ld / commit), the shared-memory
+// matrix descriptor, the common epilogue (TMEM -> registers -> bias / row-scale / rank-1 / ReLU -> global stores)
+// and the host-side tensor-map encoder.  sm_100a only.
+#pragma once
+
+#include <cuda.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace ccvpe {
+
+constexpr int TC_BM = 128;          // pixels per tile (UMMA M)
+constexpr int TC_MAX_N = 256;       // widest accumulator tile (TMEM columns per stage)
+constexpr int TC_EPI_THREADS = 256; // 8 epilogue warps
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s: a pipeline protocol bug must not hang the device
+  }
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(tm), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major swizzled shared-memory matrix descriptor.  A K block of kw bf16 channels is one swizzle row of 2*kw bytes
+// (kw = 64 -> SWIZZLE_128B, 32 -> SWIZZLE_64B, 16 -> SWIZZLE_32B); 8 rows form a group, groups are 16*kw bytes apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, int kw) {
+  const uint64_t layout = kw == 64 ? 2 : (kw == 32 ? 4 : 6);
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);  // start address, 16-byte units
+  d |= (uint64_t)1 << 16;                    // leading byte offset (unused for swizzled K-major), 16 B
+  d |= (uint64_t)((16 * kw) >> 4) << 32;     // stride byte offset: next 8-row group
+  d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
+  d |= layout << 61;
+  return d;
+}
+
+
+// ---- epilogue ------------------------------------------------------------------------------------------------------
+struct EpiParams {
+  int N, HWo, Wout, Hout;
+  const float* bias;
+  const float* row_scale;
+  const float* row_r1;
+  const float* r1_w;
+  int relu, out_mode, out_f32, ldo;
+  void* out;
+};
+
+// Stages bias / rank-1 vectors of the N tile [n0, n0 + block_n) into shared memory (all TC_EPI_THREADS threads call).
+__device__ __forceinline__ void epi_stage_vectors(const EpiParams& e, float* s_bias, float* s_r1w, int n0, int block_n,
+                                                  int et) {
+  for (int c = et; c < block_n; c += TC_EPI_THREADS) {
+    const int n = n0 + c;
+    s_bias[c] = (e.bias && n < e.N) ? __ldg(e.bias + n) : 0.f;
+    s_r1w[c] = (e.row_r1 && n < e.N) ? __ldg(e.r1_w + n) : 0.f;
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+}
+
+// One thread = one accumulator row (output pixel m_glob); `half` selects the interleaved set of 32-column chunks this
+// warp handles.  taddr = TMEM address of (lane group, first column of the accumulator stage).
+__device__ __forceinline__ void epi_store_row(const EpiParams& e, uint32_t taddr, int half, int block_n, int n0,
+                                              bool valid, int m_glob, float rs, float r1, const float* s_bias,
+                                              const float* s_r1w) {
+  const bool has_r1 = (e.row_r1 != nullptr);
+  int64_t base_px[4];
+  int64_t plane0 = 0;
+  if (e.out_mode == 0) {
+    base_px[0] = (int64_t)m_glob * e.ldo;
+  } else {
+    const int b_img = m_glob / e.HWo;
+    const int hw = m_glob - b_img * e.HWo;
+    if (e.out_mode == 2) {
+      plane0 = (int64_t)b_img * e.N * e.HWo + hw;
+    } else {
+      const int h = hw / e.Wout, w = hw - h * e.Wout;
+#pragma unroll
+      for (int ij = 0; ij < 4; ++ij)
+        base_px[ij] = (((int64_t)b_img * 2 * e.Hout + 2 * h + (ij >> 1)) * (2 * e.Wout) + 2 * w + (ij & 1)) * e.ldo;
+    }
+  }
+  const int cout = e.out_mode == 1 ? (e.N >> 2) : e.N;
+
+  auto process = [&](const uint32_t (&v)[32], int c0) {
+    if (!valid) return;
+    int ij = 0, co = n0 + c0;                // (quadrant, channel) of the chunk's first column
+    if (e.out_mode == 1) {
+      ij = co / cout;
+      co -= ij * cout;
+    }
+#pragma unroll
+    for (int g8 = 0; g8 < 4; ++g8) {
+      const int cl = c0 + g8 * 8;             // column within the tile
+      const int n = n0 + cl;
+      if (n >= e.N || cl >= block_n) break;
+      const float4 b0 = *reinterpret_cast<const float4*>(&s_bias[cl]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&s_bias[cl + 4]);
+      float y[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      if (has_r1) {
+        const float4 w0 = *reinterpret_cast<const float4*>(&s_r1w[cl]);
+        const float4 w1 = *reinterpret_cast<const float4*>(&s_r1w[cl + 4]);
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] = fmaf(r1, wv[j], y[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        y[j] = fmaf(__uint_as_float(v[g8 * 8 + j]), rs, y[j]);
+        if (e.relu) y[j] = fmaxf(y[j], 0.f);
+      }
+      if (e.out_mode == 2) {
+        float* o = static_cast<float*>(e.out) + plane0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (n + j < e.N) o[(int64_t)(n + j) * e.HWo] = y[j];
+        continue;
+      }
+      const int64_t off = (e.out_mode == 0 ? base_px[0] : base_px[ij]) + co;
+      const bool full8 = (n + 8 <= e.N);
+      if (e.out_f32) {
+        float* o = static_cast<float*>(e.out) + off;
+        if (full8 && (e.ldo & 3) == 0) {
+          *reinterpret_cast<float4*>(o) = make_float4(y[0], y[1], y[2], y[3]);
+          *reinterpret_cast<float4*>(o + 4) = make_float4(y[4], y[5], y[6], y[7]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (n + j < e.N) o[j] = y[j];
+        }
+      } else {
+        __nv_bfloat16* o = static_cast<__nv_bfloat16*>(e.out) + off;
+        if (full8 && (e.ldo & 7) == 0) {
+          __nv_bfloat162 q0 = __floats2bfloat162_rn(y[0], y[1]), q1 = __floats2bfloat162_rn(y[2], y[3]);
+          __nv_bfloat162 q2 = __floats2bfloat162_rn(y[4], y[5]), q3 = __floats2bfloat162_rn(y[6], y[7]);
+          uint4 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&q0);
+          pk.y = *reinterpret_cast<uint32_t*>(&q1);
+          pk.z = *reinterpret_cast<uint32_t*>(&q2);
+          pk.w = *reinterpret_cast<uint32_t*>(&q3);
+          *reinterpret_cast<uint4*>(o) = pk;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (n + j < e.N) o[j] = __float2bfloat16_rn(y[j]);
+        }
+      }
+      co += 8;
+      if (e.out_mode == 1 && co >= cout) {
+        co -= cout;
+        ++ij;
+      }
+    }
+  };
+
+  // TMEM -> registers, double buffered: the load of the next chunk is in flight while this one is processed
+  uint32_t va[32], vb2[32];
+  const int cfirst = half * 32;
+  if (cfirst < block_n) tmem_ld32(taddr + (uint32_t)cfirst, va);
+  for (int c0 = cfirst; c0 < block_n; c0 += 128) {
+    tmem_ld_wait();
+    const bool more1 = (c0 + 64 < block_n);
+    if (more1) tmem_ld32(taddr + (uint32_t)(c0 + 64), vb2);
+    process(va, c0);
+    if (more1) {
+      tmem_ld_wait();
+      if (c0 + 128 < block_n) tmem_ld32(taddr + (uint32_t)(c0 + 128), va);
+      process(vb2, c0 + 64);
+    }
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &sym, 12000, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  });
+  return fn;
+}
+
+inline int encode_map(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box, int kw) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(CCVPE_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+  }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  kw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kw == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B),
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(CCVPE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rank=%d dims=[%llu,%llu,%llu,..] box=[%u,%u,%u,..]",
+                (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
+                (unsigned long long)(rank > 2 ? dims[2] : 0), box[0], box[1], rank > 2 ? box[2] : 0);
+  return CCVPE_OK;
+}
+
+
+// K-block width (bf16 channels) used for a source with c channels; one block is one swizzle row of 2*width bytes.
+// Narrow sources get narrow blocks so TMA neither over-fetches nor zero-fills most of the tile (include/ccvpe_b200.h
+// documents the same rule for the w_nk weight layout).
+inline int tc_block_width(int c) { return c <= 16 ? 16 : (c < 96 ? 32 : 64); }
+
+inline void fill_epi(EpiParams& e, const ccvpe_igemm_desc& d) {
+  e.N = d.N;
+  e.HWo = d.Hout * d.Wout;
+  e.Wout = d.Wout;
+  e.Hout = d.Hout;
+  e.bias = d.bias;
+  e.row_scale = d.row_scale;
+  e.row_r1 = d.row_r1;
+  e.r1_w = d.r1_w;
+  e.relu = d.relu;
+  e.out_mode = d.out_mode;
+  e.out_f32 = (d.out_dtype == CCVPE_F32);
+  e.ldo = d.ldo;
+  e.out = d.out;
+}
+
+}  // namespace ccvpe

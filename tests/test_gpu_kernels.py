@@ -231,6 +231,13 @@ def test_deconv_fused_normalize_concat(cuda_device, B, C, H, cout, dtype, tol, b
     (2, 16, 0, 1, 128, False, 2, torch.bfloat16, BF16_TOL, cabi.BACKEND_TCGEN05),       # logits: N=1, planar fp32
     (2, 16, 0, 2, 64, False, 0, torch.bfloat16, BF16_TOL, cabi.BACKEND_TCGEN05),        # ori: N=2, fp32 channels-last
     (5, 640, 0, 640, 8, False, 0, torch.bfloat16, BF16_TOL, cabi.BACKEND_TCGEN05),      # 8x8 map, tb=2, odd batch
+    # row-ring kernel (W >= 128, resident weights): level-1/2 shapes of both decoders, chunk / image borders
+    (2, 16, 0, 16, 512, True, 0, torch.bfloat16, BF16_TOL, cabi.BACKEND_TCGEN05),
+    (1, 32, 16, 32, 256, True, 0, torch.bfloat16, BF16_TOL, cabi.BACKEND_TCGEN05),
+    (2, 40, 0, 40, 256, False, 0, torch.bfloat16, BF16_TOL, cabi.BACKEND_TCGEN05),
+    (5, 16, 0, 16, 128, False, 0, torch.bfloat16, BF16_TOL, cabi.BACKEND_TCGEN05),
+    (1, 16, 0, 2, 512, False, 0, torch.bfloat16, BF16_TOL, cabi.BACKEND_TCGEN05),
+    (3, 64, 24, 64, 128, True, 0, torch.bfloat16, BF16_TOL, cabi.BACKEND_TCGEN05),
 ])
 def test_conv3x3_two_sources(cuda_device, B, c0, c1, cout, H, relu, mode, dtype, tol, backend):
     g = _gen(5)
