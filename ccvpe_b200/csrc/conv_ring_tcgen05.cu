@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(RING_THREADS, 1) conv_ring_tcgen05_kernel(cons
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(16) float s_bias[TC_MAX_N];
   __shared__ __align__(16) float s_r1w[TC_MAX_N];
+  __shared__ __align__(16) uint4 s_blk[4];   // per K block: descriptor offsets (16-byte units) for the MMA issuer
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -61,6 +62,18 @@ __global__ void __launch_bounds__(RING_THREADS, 1) conv_ring_tcgen05_kernel(cons
       mbar_init(smem_u32(&bar_empty[s]), 1);
     }
     mbar_init(smem_u32(&bar_w), 1);
+    {
+      uint32_t ao = 0, wo = 0;
+      for (int g = 0; g < p.nb0 + p.nb1; ++g) {
+        const bool s1 = g >= p.nb0;
+        const int kw = s1 ? p.kw1 : p.kw0, cb = s1 ? g - p.nb0 : g, c = s1 ? p.c1 : p.c0, nb = s1 ? p.nb1 : p.nb0;
+        const uint32_t nk16 = (cb == nb - 1) ? (uint32_t)((c - cb * kw + 15) >> 4) : (uint32_t)(kw >> 4);
+        s_blk[g] = make_uint4(ao >> 4, wo >> 4, (uint32_t)(make_smem_desc(0, kw) >> 32),
+                              ((uint32_t)(kw * 2) >> 4) | (nk16 << 16));
+        ao += s1 ? p.a_blk1 : p.a_blk0;
+        wo += s1 ? p.w_blk1 : p.w_blk0;
+      }
+    }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&bar_tmem_full[a]), 1);
       mbar_init(smem_u32(&bar_tmem_empty[a]), TC_EPI_THREADS / 32);
@@ -124,78 +137,86 @@ __global__ void __launch_bounds__(RING_THREADS, 1) conv_ring_tcgen05_kernel(cons
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
+    // One thread issues every MMA, so its instruction count per output row IS the kernel's clock for the narrow levels:
+    // everything is precomputed into registers (16-byte-unit descriptor offsets per K block), ring slots roll without
+    // div/mod, and the (block, dx, k) loops are fully unrolled.
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) |
                              ((uint32_t)(TC_BM >> 4) << 24);
-      const uint32_t hi0 = (uint32_t)(make_smem_desc(0, p.kw0) >> 32), hi1 = (uint32_t)(make_smem_desc(0, p.kw1) >> 32);
-      const int full0 = p.kw0 >> 4, full1 = p.kw1 >> 4;
-      const int tail0 = (p.c0 - (p.nb0 - 1) * p.kw0 + 15) >> 4, tail1 = p.nb1 ? (p.c1 - (p.nb1 - 1) * p.kw1 + 15) >> 4 : 0;
+      const int nblk = p.nb0 + p.nb1;
       const uint32_t lo_flag = 1u << 16;
+      const uint32_t ring16 = ((ring_base & 0x3FFFFu) >> 4) | lo_flag, row16 = (uint32_t)p.row_bytes >> 4;
+      const uint32_t w16 = ((w_base & 0x3FFFFu) >> 4) | lo_flag, tap16 = (uint32_t)p.w_tap_bytes >> 4;
+      const int depth = p.depth, H = p.H, R = p.R, chunks = p.chunks;
+      const uint32_t bar_full0 = smem_u32(&bar_full[0]), bar_empty0 = smem_u32(&bar_empty[0]);
+      const uint32_t bar_tf0 = smem_u32(&bar_tmem_full[0]), bar_te0 = smem_u32(&bar_tmem_empty[0]);
       mbar_wait(smem_u32(&bar_w), 0);
       tc_fence_after();
-      int ctr = 0;            // rows consumed from the ring so far (same sequence as the producer)
+      // ring position of the NEXT row to be consumed for the first time (same sequence as the producer)
+      int nslot = 0;
+      uint32_t nphase = 0;
       int it = 0;
       for (int unit = blockIdx.x; unit < p.total_units; unit += gridDim.x) {
-        const int rc = unit % p.chunks;
-        const int y0 = rc * p.R;
-        const int y_lo = y0 > 0 ? y0 - 1 : 0;
-        const int y_hi = (y0 + p.R < p.H) ? y0 + p.R : p.H - 1;
-        int waited = ctr - 1;  // highest ring row counter whose data is known to have landed
-        for (int yo = y0; yo < y0 + p.R; ++yo, ++it) {
-          const int acc = it & 1;
-          const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-          mbar_wait(smem_u32(&bar_tmem_empty[acc]), acc_phase ^ 1u);
+        const int y0 = (unit % chunks) * R;
+        // slots of input rows yo-1, yo, yo+1 (-1: outside the image, never loaded)
+        int s_prev = -1, s_cur = -1, s_next = -1;
+        auto acquire = [&]() {   // waits for the next ring row and returns its slot
+          const int sl = nslot;
+          mbar_wait(bar_full0 + 8u * (uint32_t)sl, nphase);
+          if (++nslot == depth) {
+            nslot = 0;
+            nphase ^= 1u;
+          }
+          return sl;
+        };
+        if (y0 > 0) s_prev = acquire();
+        s_cur = acquire();
+        for (int yo = y0; yo < y0 + R; ++yo, ++it) {
+          s_next = (yo + 1 < H) ? acquire() : -1;
           tc_fence_after();
-          const uint32_t tmem_d = tmem_base + (uint32_t)(acc * TC_MAX_N);
+          const uint32_t acc = (uint32_t)it & 1u;
+          mbar_wait(bar_te0 + 8u * acc, (((uint32_t)it >> 1) & 1u) ^ 1u);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + acc * (uint32_t)TC_MAX_N;
           uint32_t accumulate = 0;
 #pragma unroll 1
           for (int dy = 0; dy < 3; ++dy) {
-            const int yi = yo + dy - 1;
-            if (yi < 0 || yi >= p.H) continue;       // zero padding rows contribute nothing
-            const int rctr = ctr + (yi - y_lo);
-            const int slot = rctr % p.depth;
-            if (rctr > waited) {
-              mbar_wait(smem_u32(&bar_full[slot]), (uint32_t)(rctr / p.depth) & 1u);
-              tc_fence_after();
-              waited = rctr;
-            }
-            uint32_t a_tile = ring_base + (uint32_t)(slot * p.row_bytes);
-            uint32_t w_tile = w_base + (uint32_t)(dy * 3 * p.w_tap_bytes);
+            const int sl = dy == 0 ? s_prev : (dy == 1 ? s_cur : s_next);
+            if (sl < 0) continue;                    // zero padding row: contributes nothing
+            const uint32_t a_row = ring16 + (uint32_t)sl * row16;
+            const uint32_t w_tap = w16 + (uint32_t)(dy * 3) * tap16;
 #pragma unroll 1
-            for (int src = 0; src < 2; ++src) {
-              const int nb = src ? p.nb1 : p.nb0;
-              const uint32_t hi = src ? hi1 : hi0;
-              const int nfull = src ? full1 : full0, ntail = src ? tail1 : tail0;
-              const uint32_t a_blk = src ? p.a_blk1 : p.a_blk0, w_blk = src ? p.w_blk1 : p.w_blk0;
-              const uint32_t row_b = (uint32_t)(src ? p.kw1 : p.kw0) * 2u;
-#pragma unroll 1
-              for (int cb = 0; cb < nb; ++cb, a_tile += a_blk, w_tile += w_blk) {
-                const int nk16 = (cb == nb - 1) ? ntail : nfull;
+            for (int g = 0; g < nblk; ++g) {
+              const uint4 bk = s_blk[g];             // {a offset, w offset, descriptor hi word, row pitch | k16 count << 16}
+              const uint64_t hi = (uint64_t)bk.z << 32;
+              const uint32_t rowp = bk.w & 0xFFFFu, nk16 = bk.w >> 16;
 #pragma unroll
-                for (int dx = 0; dx < 3; ++dx) {
-                  // tap (dy, dx): rows [dx, dx + 128) of the halo'd row tile; weights of tap dy*3 + dx
-                  const uint32_t a_lo = (((a_tile + dx * row_b) & 0x3FFFFu) >> 4) | lo_flag;
-                  const uint32_t b_lo = (((w_tile + dx * (uint32_t)p.w_tap_bytes) & 0x3FFFFu) >> 4) | lo_flag;
-                  const uint64_t adesc = ((uint64_t)hi << 32) | a_lo;
-                  const uint64_t bdesc = ((uint64_t)hi << 32) | b_lo;
-                  umma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);
-                  accumulate = 1;
-                  if (nk16 > 1) umma_bf16(tmem_d, adesc + 2, bdesc + 2, idesc, 1u);
-                  if (nk16 > 2) umma_bf16(tmem_d, adesc + 4, bdesc + 4, idesc, 1u);
-                  if (nk16 > 3) umma_bf16(tmem_d, adesc + 6, bdesc + 6, idesc, 1u);
+              for (int dx = 0; dx < 3; ++dx) {
+                // tap (dy, dx): rows [dx, dx + 128) of the halo'd row tile; weights of tap dy*3 + dx
+                const uint64_t adesc = hi | (a_row + bk.x + (uint32_t)dx * rowp);
+                const uint64_t bdesc = hi | (w_tap + (uint32_t)dx * tap16 + bk.y);
+                umma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);
+                accumulate = 1;
+                if (nk16 > 1) {
+                  umma_bf16(tmem_d, adesc + 2, bdesc + 2, idesc, 1u);
+                  if (nk16 > 2) {
+                    umma_bf16(tmem_d, adesc + 4, bdesc + 4, idesc, 1u);
+                    if (nk16 > 3) umma_bf16(tmem_d, adesc + 6, bdesc + 6, idesc, 1u);
+                  }
                 }
               }
             }
           }
-          umma_commit(smem_u32(&bar_tmem_full[acc]));
+          umma_commit(bar_tf0 + 8u * acc);
           // input row yo-1 has no later reader; the last output row of the unit also retires rows yo and yo+1
-          if (yo - 1 >= y_lo) umma_commit(smem_u32(&bar_empty[(ctr + (yo - 1 - y_lo)) % p.depth]));
-          if (yo == y0 + p.R - 1) {
-            umma_commit(smem_u32(&bar_empty[(ctr + (yo - y_lo)) % p.depth]));
-            if (yo + 1 <= y_hi) umma_commit(smem_u32(&bar_empty[(ctr + (yo + 1 - y_lo)) % p.depth]));
+          if (s_prev >= 0) umma_commit(bar_empty0 + 8u * (uint32_t)s_prev);
+          if (yo == y0 + R - 1) {
+            umma_commit(bar_empty0 + 8u * (uint32_t)s_cur);
+            if (s_next >= 0) umma_commit(bar_empty0 + 8u * (uint32_t)s_next);
           }
+          s_prev = s_cur;
+          s_cur = s_next;
         }
-        ctr += y_hi - y_lo + 1;
       }
     }
   } else if (warp >= 4) {
@@ -249,6 +270,7 @@ static bool ring_plan(const ccvpe_igemm_desc& d, RingParams* p) {
   p->kw1 = d.c1 ? tc_block_width(d.c1) : 64;
   p->nb0 = (d.c0 + p->kw0 - 1) / p->kw0;
   p->nb1 = d.c1 ? (d.c1 + p->kw1 - 1) / p->kw1 : 0;
+  if (p->nb0 + p->nb1 > 4) return false;
   p->kpad0 = p->nb0 * p->kw0;
   p->kpad1 = p->nb1 * p->kw1;
   p->c0 = d.c0;
