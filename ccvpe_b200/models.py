@@ -22,6 +22,7 @@ from torch import nn
 from . import cabi
 from .decoder import PostEncoderPipeline, decode_pose
 from .efficientnet import EfficientNetB0
+from .fast_encoder import FastEncoder
 from .specs import KITTI, OXFORD, SKIP_CHANNELS, VIGOR, VariantSpec
 
 
@@ -116,24 +117,19 @@ class _CVMBase(nn.Module):
 
     # -- encoders (PyTorch) -----------------------------------------------------------------------------------
     def _bf16_encoders(self):
+        """Inference execution plans of the two encoders (see fast_encoder.py), rebuilt when encoder weights change."""
         sig = tuple((p.data_ptr(), p._version) for enc in (self.grd_efficientnet, self.sat_efficientnet)
                     for p in list(enc.parameters()) + list(enc.buffers()))
         cached = self._fast_encoders[0]
         if cached is None or cached[0] != sig:
-            encs = []
-            for enc in (self.grd_efficientnet, self.sat_efficientnet):
-                e = copy.deepcopy(enc).eval().to(dtype=torch.bfloat16).to(memory_format=torch.channels_last)
-                e.set_fast_activation(True)
-                encs.append(e)
-            cached = (sig, encs[0], encs[1])
+            cached = (sig, FastEncoder(self.grd_efficientnet, torch.bfloat16),
+                      FastEncoder(self.sat_efficientnet, torch.bfloat16))
             self._fast_encoders[0] = cached
         return cached[1], cached[2]
 
     def _encode(self, grd, sat):
         if self._precision == "bf16" and not self.training:
             ge, se = self._bf16_encoders()
-            grd = grd.to(dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
-            sat = sat.to(dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
             fg = ge.extract_features(grd)
             fs, multi = se.extract_features_multiscale(sat)
             return fg, fs, multi, torch.bfloat16
