@@ -166,6 +166,40 @@ def test_match_level(cuda_device, case, dtype, tol):
     assert torch.all(cl[..., R:] == 0)
 
 
+@pytest.mark.parametrize("B,C,H,R,stride", [(2, 1280, 8, 20, 64), (3, 640, 16, 20, 32), (2, 160, 64, 20, 8),
+                                              (1, 80, 128, 20, 4), (2, 40, 256, 20, 2), (1, 320, 10, 21, 16),
+                                              (2, 32, 64, 16, 8)])
+def test_match_level_tcgen05(cuda_device, B, C, H, R, stride):
+    """bf16 tensor-core correlation (full-circle case L == C) vs the oracle on the same bf16-rounded inputs.
+    The ground descriptor is rounded to bf16 inside the kernel: tolerance 1e-2 of max|ref| (scores are cosines)."""
+    g = _gen(11)
+    dev = cuda_device
+    x = torch.randn(B, C, H, H, generator=g)
+    gd = torch.randn(B, C, generator=g)
+    xr = x.to(torch.bfloat16).float()
+    rolls = list(range(R)) if R != 21 else list(range(-10, 11))
+    ref = orc.match_level(xr, gd, rolls, stride, False)
+    x_cl = _cl(x, torch.bfloat16, dev)
+    scores = torch.empty(B, R, H, H, device=dev)
+    scores_cl = torch.full((B, H, H, 32), 7.0, device=dev, dtype=torch.bfloat16)
+    mx = torch.empty(B, H, H, device=dev)
+    inv = torch.empty(B, H, H, device=dev)
+    xhat = torch.empty_like(x_cl)
+    scratch = torch.empty(cabi.match_scratch_elems(B, C, R), device=dev)
+    mask = sum(1 << i for i in range(R) if i % 4 != 2)
+    cabi.match_level(x_cl, gd.to(dev), 0, [i * stride for i in rolls], mask, scores=scores, scores_cl=scores_cl,
+                     max_out=mx, inv_norm=inv, xhat=xhat, scratch=scratch, backend=cabi.BACKEND_TCGEN05)
+    torch.cuda.synchronize()
+    assert rel_err(scores, ref) < 1e-2
+    sel = [i for i in range(R) if i % 4 != 2]
+    assert rel_err(mx, ref[:, sel].max(dim=1)[0]) < 1e-2
+    assert rel_err(1.0 / inv, xr.norm(dim=1)) < 1e-4
+    assert rel_err(xhat.permute(0, 3, 1, 2).float(), orc.l2_normalize(xr)) < 1e-2
+    cl = scores_cl.float()
+    assert rel_err(cl[..., :R].permute(0, 3, 1, 2), ref) < 2e-2
+    assert torch.all(cl[..., R:] == 0)
+
+
 def test_match_level_zero_window_is_nan(cuda_device):
     """No epsilon in the cosine denominator (models.py:196): an all-zero window gives NaN, as in the reference."""
     x = torch.zeros(1, 4, 4, 16, device=cuda_device)
