@@ -71,7 +71,7 @@ __global__ void build_rolled_descriptor_bf16_kernel(const float* __restrict__ g,
   }
 }
 
-__global__ void __launch_bounds__(MT_THREADS, 1) match_tcgen05_kernel(const __grid_constant__ MatchTcParams p) {
+__global__ void __launch_bounds__(MT_THREADS, 4) match_tcgen05_kernel(const __grid_constant__ MatchTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[MT_MAX_STAGES];
   __shared__ __align__(8) uint64_t bar_empty[MT_MAX_STAGES];
@@ -224,16 +224,19 @@ __global__ void __launch_bounds__(MT_THREADS, 1) match_tcgen05_kernel(const __gr
       if (valid) {
         const float nrm = sqrtf(sq);
         const float inv = 1.f / fmaxf(nrm, 1e-12f);
-        const float den = nrm * __ldg(p.gnorm + b);                  // no epsilon: 0/0 -> NaN like models.py:196
+        // one reciprocal of the cosine denominator, no epsilon: den == 0 gives inf and 0 * inf = NaN like the
+        // reference's 0 / 0 (models.py:196)
+        const float rden = 1.f / (nrm * __ldg(p.gnorm + b));
         const int64_t gp = (int64_t)b * p.HW + pix;
         float best = -INFINITY;
         bool any_nan = false;
         float sc[MT_N];
+        float* sp = p.scores ? p.scores + (int64_t)b * p.n_rolls * p.HW + pix : nullptr;
 #pragma unroll
         for (int i = 0; i < MT_N; ++i) {
-          sc[i] = __uint_as_float(v[i]) / den;
           if (i < p.n_rolls) {
-            if (p.scores) p.scores[((int64_t)b * p.n_rolls + i) * p.HW + pix] = sc[i];
+            sc[i] = __uint_as_float(v[i]) * rden;
+            if (sp) sp[(int64_t)i * p.HW] = sc[i];
             if ((p.max_mask >> i) & 1u) {
               any_nan |= (sc[i] != sc[i]);
               best = fmaxf(best, sc[i]);
@@ -317,7 +320,10 @@ int match_tcgen05(const void* x, int B, int HW, int C, const float* g, int L, in
   p.total_tiles = B * p.tiles_per_img;
   p.a_bytes = TC_BM * p.kw * 2;
   p.stage_bytes = p.a_bytes + ((MT_N * p.kw * 2 + 1023) / 1024) * 1024;
-  int stages = (160 * 1024) / p.stage_bytes;
+  // ~52 KB of pipeline per CTA so that four CTAs (16 norm/epilogue warps) share an SM: the epilogue is scalar-ALU and
+  // store bound and needs the extra warps to hide its own latency
+  int stages = (52 * 1024) / p.stage_bytes;
+  if (stages < 2) stages = 2;
   p.stages = stages > MT_MAX_STAGES ? MT_MAX_STAGES : stages;
   p.n_rolls = n_rolls;
   p.ld_scores_cl = scores_cl ? ld_scores_cl : 0;
@@ -345,7 +351,7 @@ int match_tcgen05(const void* x, int B, int HW, int C, const float* g, int L, in
     if (e != cudaSuccess) return fail(CCVPE_ERR_CUDA, "cudaFuncSetAttribute(match): %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
+  const int grid = p.total_tiles < 4 * sm_count() ? p.total_tiles : 4 * sm_count();
   match_tcgen05_kernel<<<grid, MT_THREADS, smem, st>>>(p);
   return check_launch("match_tcgen05_kernel");
 }
