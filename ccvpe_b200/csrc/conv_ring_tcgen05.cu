@@ -100,17 +100,19 @@ __global__ void __launch_bounds__(RING_THREADS, 1) conv_ring_tcgen05_kernel(cons
   const uint32_t tmem_base = tmem_base_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      // all weights of the layer, once
-      mbar_arrive_expect_tx(smem_u32(&bar_w), (uint32_t)p.tx_weights);
-      for (int tap = 0; tap < 9; ++tap) {
-        uint32_t dst = w_base + (uint32_t)(tap * p.w_tap_bytes);
-        const int kcol = tap * (p.kpad0 + p.kpad1);
-        for (int cb = 0; cb < p.nb0; ++cb, dst += p.w_blk0) tma_load_2d(dst, &p.tm_b0, smem_u32(&bar_w), kcol + cb * p.kw0, 0);
-        for (int cb = 0; cb < p.nb1; ++cb, dst += p.w_blk1)
-          tma_load_2d(dst, &p.tm_b1, smem_u32(&bar_w), kcol + p.kpad0 + cb * p.kw1, 0);
+    // ===================== TMA producer (whole warp converged, single-lane issue via elect_one) =====================
+    {
+      if (elect_one()) {   // all weights of the layer, once
+        mbar_arrive_expect_tx(smem_u32(&bar_w), (uint32_t)p.tx_weights);
+        for (int tap = 0; tap < 9; ++tap) {
+          uint32_t dst = w_base + (uint32_t)(tap * p.w_tap_bytes);
+          const int kcol = tap * (p.kpad0 + p.kpad1);
+          for (int cb = 0; cb < p.nb0; ++cb, dst += p.w_blk0) tma_load_2d(dst, &p.tm_b0, smem_u32(&bar_w), kcol + cb * p.kw0, 0);
+          for (int cb = 0; cb < p.nb1; ++cb, dst += p.w_blk1)
+            tma_load_2d(dst, &p.tm_b1, smem_u32(&bar_w), kcol + p.kpad0 + cb * p.kw1, 0);
+        }
       }
+      __syncwarp();
       int slot = 0;
       uint32_t phase = 0;
       for (int unit = blockIdx.x; unit < p.total_units; unit += gridDim.x) {
@@ -122,12 +124,15 @@ __global__ void __launch_bounds__(RING_THREADS, 1) conv_ring_tcgen05_kernel(cons
         const int y_hi = (y0 + p.R < p.H) ? y0 + p.R : p.H - 1;
         for (int y = y_lo; y <= y_hi; ++y) {
           mbar_wait(smem_u32(&bar_empty[slot]), phase ^ 1u);
-          const uint32_t full = smem_u32(&bar_full[slot]);
-          mbar_arrive_expect_tx(full, (uint32_t)p.tx_row);
-          uint32_t dst = ring_base + (uint32_t)(slot * p.row_bytes);
-          const int yrow = b * p.H + y;
-          for (int cb = 0; cb < p.nb0; ++cb, dst += p.a_blk0) tma_load_3d(dst, &p.tm_a0, full, cb * p.kw0, x0 - 1, yrow);
-          for (int cb = 0; cb < p.nb1; ++cb, dst += p.a_blk1) tma_load_3d(dst, &p.tm_a1, full, cb * p.kw1, x0 - 1, yrow);
+          if (elect_one()) {
+            const uint32_t full = smem_u32(&bar_full[slot]);
+            mbar_arrive_expect_tx(full, (uint32_t)p.tx_row);
+            uint32_t dst = ring_base + (uint32_t)(slot * p.row_bytes);
+            const int yrow = b * p.H + y;
+            for (int cb = 0; cb < p.nb0; ++cb, dst += p.a_blk0) tma_load_3d(dst, &p.tm_a0, full, cb * p.kw0, x0 - 1, yrow);
+            for (int cb = 0; cb < p.nb1; ++cb, dst += p.a_blk1) tma_load_3d(dst, &p.tm_a1, full, cb * p.kw1, x0 - 1, yrow);
+          }
+          __syncwarp();
           if (++slot == p.depth) {
             slot = 0;
             phase ^= 1u;
@@ -140,7 +145,7 @@ __global__ void __launch_bounds__(RING_THREADS, 1) conv_ring_tcgen05_kernel(cons
     // One thread issues every MMA, so its instruction count per output row IS the kernel's clock for the narrow levels:
     // everything is precomputed into registers (16-byte-unit descriptor offsets per K block), ring slots roll without
     // div/mod, and the (block, dx, k) loops are fully unrolled.
-    if (lane == 0) {
+    {  // the whole warp runs the loop converged; single-lane work is predicated with elect_one()
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) |
                              ((uint32_t)(TC_BM >> 4) << 24);
       const int nblk = p.nb0 + p.nb1;
@@ -190,30 +195,37 @@ __global__ void __launch_bounds__(RING_THREADS, 1) conv_ring_tcgen05_kernel(cons
               const uint4 bk = s_blk[g];             // {a offset, w offset, descriptor hi word, row pitch | k16 count << 16}
               const uint64_t hi = (uint64_t)bk.z << 32;
               const uint32_t rowp = bk.w & 0xFFFFu, nk16 = bk.w >> 16;
+              if (elect_one()) {
 #pragma unroll
-              for (int dx = 0; dx < 3; ++dx) {
-                // tap (dy, dx): rows [dx, dx + 128) of the halo'd row tile; weights of tap dy*3 + dx
-                const uint64_t adesc = hi | (a_row + bk.x + (uint32_t)dx * rowp);
-                const uint64_t bdesc = hi | (w_tap + (uint32_t)dx * tap16 + bk.y);
-                umma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);
-                accumulate = 1;
-                if (nk16 > 1) {
-                  umma_bf16(tmem_d, adesc + 2, bdesc + 2, idesc, 1u);
-                  if (nk16 > 2) {
-                    umma_bf16(tmem_d, adesc + 4, bdesc + 4, idesc, 1u);
-                    if (nk16 > 3) umma_bf16(tmem_d, adesc + 6, bdesc + 6, idesc, 1u);
+                for (int dx = 0; dx < 3; ++dx) {
+                  // tap (dy, dx): rows [dx, dx + 128) of the halo'd row tile; weights of tap dy*3 + dx
+                  const uint64_t adesc = hi | (a_row + bk.x + (uint32_t)dx * rowp);
+                  const uint64_t bdesc = hi | (w_tap + (uint32_t)dx * tap16 + bk.y);
+                  umma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);
+                  accumulate = 1;
+                  if (nk16 > 1) {
+                    umma_bf16(tmem_d, adesc + 2, bdesc + 2, idesc, 1u);
+                    if (nk16 > 2) {
+                      umma_bf16(tmem_d, adesc + 4, bdesc + 4, idesc, 1u);
+                      if (nk16 > 3) umma_bf16(tmem_d, adesc + 6, bdesc + 6, idesc, 1u);
+                    }
                   }
                 }
               }
+              accumulate = 1;
+              __syncwarp();
             }
           }
-          umma_commit(bar_tf0 + 8u * acc);
-          // input row yo-1 has no later reader; the last output row of the unit also retires rows yo and yo+1
-          if (s_prev >= 0) umma_commit(bar_empty0 + 8u * (uint32_t)s_prev);
-          if (yo == y0 + R - 1) {
-            umma_commit(bar_empty0 + 8u * (uint32_t)s_cur);
-            if (s_next >= 0) umma_commit(bar_empty0 + 8u * (uint32_t)s_next);
+          if (elect_one()) {
+            umma_commit(bar_tf0 + 8u * acc);
+            // input row yo-1 has no later reader; the last output row of the unit also retires rows yo and yo+1
+            if (s_prev >= 0) umma_commit(bar_empty0 + 8u * (uint32_t)s_prev);
+            if (yo == y0 + R - 1) {
+              umma_commit(bar_empty0 + 8u * (uint32_t)s_cur);
+              if (s_next >= 0) umma_commit(bar_empty0 + 8u * (uint32_t)s_next);
+            }
           }
+          __syncwarp();
           s_prev = s_cur;
           s_cur = s_next;
         }

@@ -77,8 +77,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) igemm_tcgen05_kernel(const __gr
   const uint32_t tmem_base = tmem_base_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp converged, single-lane issue via elect_one) =====================
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -103,11 +103,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) igemm_tcgen05_kernel(const __gr
             const uint32_t tx = (uint32_t)((TC_BM + p.block_n) * kw * 2);
             for (int cb = 0; cb < nb; ++cb) {
               mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
-              const uint32_t full = smem_u32(&bar_full[stage]);
-              const uint32_t a_dst = smem_base + stage * stage_bytes;
-              mbar_arrive_expect_tx(full, tx);
-              tma_load_5d(a_dst, tm, full, cb * kw, c1, c2, c3, c4);
-              tma_load_2d(a_dst + p.a_bytes, tmb, full, kbase + cb * kw, n0);
+              if (elect_one()) {
+                const uint32_t full = smem_u32(&bar_full[stage]);
+                const uint32_t a_dst = smem_base + stage * stage_bytes;
+                mbar_arrive_expect_tx(full, tx);
+                tma_load_5d(a_dst, tm, full, cb * kw, c1, c2, c3, c4);
+                tma_load_2d(a_dst + p.a_bytes, tmb, full, kbase + cb * kw, n0);
+              }
+              __syncwarp();
               if (++stage == p.stages) {
                 stage = 0;
                 phase ^= 1u;
@@ -120,8 +123,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) igemm_tcgen05_kernel(const __gr
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     // One thread issues everything, so the per-K-block instruction count is the pipeline's clock: all descriptor
-    // pieces are precomputed and the loop nest mirrors the producer's (no div/mod in the steady state).
-    if (lane == 0) {
+    // pieces are precomputed and the loop nest mirrors the producer's (no div/mod in the steady state).  The warp stays
+    // converged; the MMAs and commits are predicated with elect_one().
+    {
       // instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=block_n
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) |
                              ((uint32_t)(TC_BM >> 4) << 24);
@@ -154,13 +158,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) igemm_tcgen05_kernel(const __gr
               const uint32_t a_lo = lo_base + (uint32_t)stage * lo_stage;
               const uint64_t adesc = ((uint64_t)hi << 32) | a_lo;
               const uint64_t bdesc = ((uint64_t)hi << 32) | (a_lo + lo_b);
-              // k-th MMA: advance 16 bf16 = 32 bytes inside the swizzle row (+2 in the 16-byte address field)
-              umma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);
+              if (elect_one()) {
+                // k-th MMA: advance 16 bf16 = 32 bytes inside the swizzle row (+2 in the 16-byte address field)
+                umma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);
+                if (nk16 > 1) umma_bf16(tmem_d, adesc + 2, bdesc + 2, idesc, 1u);
+                if (nk16 > 2) umma_bf16(tmem_d, adesc + 4, bdesc + 4, idesc, 1u);
+                if (nk16 > 3) umma_bf16(tmem_d, adesc + 6, bdesc + 6, idesc, 1u);
+                umma_commit(smem_u32(&bar_empty[stage]));   // frees the smem slot once these MMAs have read it
+              }
               accumulate = 1;
-              if (nk16 > 1) umma_bf16(tmem_d, adesc + 2, bdesc + 2, idesc, 1u);
-              if (nk16 > 2) umma_bf16(tmem_d, adesc + 4, bdesc + 4, idesc, 1u);
-              if (nk16 > 3) umma_bf16(tmem_d, adesc + 6, bdesc + 6, idesc, 1u);
-              umma_commit(smem_u32(&bar_empty[stage]));   // frees the smem slot once these MMAs have read it
+              __syncwarp();
               if (++stage == p.stages) {
                 stage = 0;
                 phase ^= 1u;
@@ -168,7 +175,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) igemm_tcgen05_kernel(const __gr
             }
           }
         }
-        umma_commit(smem_u32(&bar_tmem_full[acc]));    // accumulator complete -> epilogue
+        if (elect_one()) umma_commit(smem_u32(&bar_tmem_full[acc]));    // accumulator complete -> epilogue
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {

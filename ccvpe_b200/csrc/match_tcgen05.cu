@@ -110,8 +110,8 @@ __global__ void __launch_bounds__(MT_THREADS, 4) match_tcgen05_kernel(const __gr
   const uint32_t tmem_base = tmem_base_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp converged, single-lane issue via elect_one) =====================
+    {
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx = (uint32_t)((TC_BM + MT_N) * p.kw * 2);
@@ -120,11 +120,14 @@ __global__ void __launch_bounds__(MT_THREADS, 4) match_tcgen05_kernel(const __gr
         const int prow = b * p.HW + (tile - b * p.tiles_per_img) * TC_BM;   // first pixel row of the tile
         for (int kb = 0; kb < p.nb; ++kb) {
           mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
-          const uint32_t full = smem_u32(&bar_full[stage]);
-          const uint32_t dst = smem_base + (uint32_t)(stage * p.stage_bytes);
-          mbar_arrive_expect_tx(full, tx);
-          tma_load_2d(dst, &p.tm_x, full, kb * p.kw, prow);
-          tma_load_2d(dst + (uint32_t)p.a_bytes, &p.tm_g, full, kb * p.kw, b * MT_N);
+          if (elect_one()) {
+            const uint32_t full = smem_u32(&bar_full[stage]);
+            const uint32_t dst = smem_base + (uint32_t)(stage * p.stage_bytes);
+            mbar_arrive_expect_tx(full, tx);
+            tma_load_2d(dst, &p.tm_x, full, kb * p.kw, prow);
+            tma_load_2d(dst + (uint32_t)p.a_bytes, &p.tm_g, full, kb * p.kw, b * MT_N);
+          }
+          __syncwarp();
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1u;
@@ -133,8 +136,8 @@ __global__ void __launch_bounds__(MT_THREADS, 4) match_tcgen05_kernel(const __gr
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (converged warp, elect_one issue) =====================
+    {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(MT_N >> 3) << 17) |
                              ((uint32_t)(TC_BM >> 4) << 24);
       const uint64_t hi = (uint64_t)(uint32_t)(make_smem_desc(0, p.kw) >> 32) << 32;
@@ -157,18 +160,22 @@ __global__ void __launch_bounds__(MT_THREADS, 4) match_tcgen05_kernel(const __gr
           tc_fence_after();
           const uint32_t a_lo = lo_base + (uint32_t)stage * lo_stage;
           const uint64_t adesc = hi | a_lo, bdesc = hi | (a_lo + lo_b);
-          umma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);
+          if (elect_one()) {
+            umma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);
+            if (nk16 > 1) umma_bf16(tmem_d, adesc + 2, bdesc + 2, idesc, 1u);
+            if (nk16 > 2) umma_bf16(tmem_d, adesc + 4, bdesc + 4, idesc, 1u);
+            if (nk16 > 3) umma_bf16(tmem_d, adesc + 6, bdesc + 6, idesc, 1u);
+            umma_commit(smem_u32(&bar_empty[stage]));
+          }
           accumulate = 1;
-          if (nk16 > 1) umma_bf16(tmem_d, adesc + 2, bdesc + 2, idesc, 1u);
-          if (nk16 > 2) umma_bf16(tmem_d, adesc + 4, bdesc + 4, idesc, 1u);
-          if (nk16 > 3) umma_bf16(tmem_d, adesc + 6, bdesc + 6, idesc, 1u);
-          umma_commit(smem_u32(&bar_empty[stage]));
+          __syncwarp();
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(smem_u32(&bar_tmem_full[acc]));
+        if (elect_one()) umma_commit(smem_u32(&bar_tmem_full[acc]));
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {

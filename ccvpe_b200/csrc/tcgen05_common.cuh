@@ -18,6 +18,19 @@ constexpr int TC_EPI_THREADS = 256; // 8 epilogue warps
 // ---- PTX wrappers ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// True in exactly one lane of a converged warp.  Issuing the warp-level tcgen05 / TMA instructions under this predicate
+// (instead of `lane == 0` inside a divergent branch) lets ptxas emit them straight on the uniform datapath; with a
+// divergent single lane it wraps every UTCHMMA / UTMALDG / UTCBAR in an ELECT + BRA.U.ANY retry loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
