@@ -18,7 +18,7 @@ BACKEND_AUTO, BACKEND_SIMT, BACKEND_TCGEN05 = 0, 1, 2
 
 EXPORTED_SYMBOLS = (
     "ccvpe_abi_version", "ccvpe_last_error", "ccvpe_launch_count", "ccvpe_reset_launch_count",
-    "ccvpe_grd_descriptor", "ccvpe_igemm", "ccvpe_match_scratch_elems", "ccvpe_match_level",
+    "ccvpe_grd_descriptor", "ccvpe_igemm", "ccvpe_igemm_plan", "ccvpe_match_scratch_elems", "ccvpe_match_level",
     "ccvpe_softmax_scratch_elems", "ccvpe_softmax_heatmap", "ccvpe_ori_normalize",
     "ccvpe_pose_scratch_bytes", "ccvpe_pose_decode",
 )
@@ -72,6 +72,8 @@ def load() -> C.CDLL:
                                          C.c_void_p, C.c_void_p, C.c_void_p]
     lib.ccvpe_igemm.restype = C.c_int
     lib.ccvpe_igemm.argtypes = [C.POINTER(IgemmDesc), C.c_void_p]
+    lib.ccvpe_igemm_plan.restype = C.c_int
+    lib.ccvpe_igemm_plan.argtypes = [C.POINTER(IgemmDesc)]
     lib.ccvpe_match_scratch_elems.restype = C.c_int64
     lib.ccvpe_match_scratch_elems.argtypes = [C.c_int, C.c_int, C.c_int]
     lib.ccvpe_match_level.restype = C.c_int
@@ -149,6 +151,16 @@ def grd_descriptor(feat: torch.Tensor, w1, b1, w2, b2, out: torch.Tensor, scratc
 
 def igemm(desc: IgemmDesc):
     _check(load().ccvpe_igemm(C.byref(desc), _stream()), "ccvpe_igemm")
+
+
+IGEMM_KERNELS = ("igemm_simt_kernel", "igemm_tcgen05_kernel", "conv_ring_tcgen05_kernel")
+
+
+def igemm_kernel_name(desc: IgemmDesc) -> str:
+    rc = load().ccvpe_igemm_plan(C.byref(desc))
+    if rc < 0:
+        _check(rc, "ccvpe_igemm_plan")
+    return IGEMM_KERNELS[rc]
 
 
 def match_scratch_elems(B: int, Cch: int, n_rolls: int) -> int:

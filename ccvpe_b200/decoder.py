@@ -188,6 +188,8 @@ class PostEncoderPipeline:
         M, K = B * Hout * Wout, k * k * (c0 + c1)
         esz = a0.element_size()
         nbytes = (B * Hin * Win * (c0 + c1) + K * N) * esz + M * N * out.element_size()
+        if self.timer is not None:            # attribute the launch to the kernel the library will pick
+            tag = cabi.igemm_kernel_name(d) + ":" + tag
         self._op(tag, 2.0 * M * N * K, nbytes, lambda: cabi.igemm(d))
 
     def _deconv(self, wt, a0, c0, a1, c1, dtype, row_scale=None, row_r1=None, name=""):
@@ -237,7 +239,7 @@ class PostEncoderPipeline:
         for l in range(6):
             w1, b1, w2, b2 = w["heads"][l]
             out = torch.empty((Bg, Wg * w1.shape[0]), dtype=f32, device=dev)
-            self._op("grd_descriptor", 2.0 * Bg * Wg * Kg * (Hg + w1.shape[0]),
+            self._op("grd_project_kernel:grd_descriptor|", 2.0 * Bg * Wg * Kg * (Hg + w1.shape[0]),
                      grd_feat.numel() * grd_feat.element_size() + out.numel() * 4,
                      lambda: cabi.grd_descriptor(grd_feat, w1, b1, w2, b2, out, scratch_g))
             g.append(out)
@@ -284,7 +286,9 @@ class PostEncoderPipeline:
             x_in, g_in = x, g[l]
             # algorithmic traffic: read x once, write the score volume + max + 1/norm
             nbytes = x.numel() * x.element_size() + (R + 2) * B * H * W * 4
-            self._op("match|l%d" % (l + 1), 2.0 * R * L * B * H * W, nbytes, lambda: cabi.match_level(
+            mk = "match_tcgen05_kernel" if (dtype == torch.bfloat16 and L == C and
+                                            self.backend != cabi.BACKEND_SIMT) else "match_level_simt_kernel"
+            self._op(mk + ":match|l%d" % (l + 1), 2.0 * R * L * B * H * W, nbytes, lambda: cabi.match_level(
                 x_in, g_in, spec.window_offset(C, L), [i * stride for i in rolls], mask, scores=scores,
                 scores_cl=scores_cl if l == 0 else None, max_out=mx, inv_norm=inv,
                 xhat=xhat if l == 0 else None, scratch=scratch,
@@ -306,7 +310,7 @@ class PostEncoderPipeline:
         logits_flat = logits.view(B, Hh * Wh)
         heatmap = torch.empty_like(logits)
         sm_scratch = torch.empty(cabi.softmax_scratch_elems(B, Hh * Wh), dtype=f32, device=dev)
-        self._op("softmax", 5.0 * B * Hh * Wh, 2.0 * B * Hh * Wh * 4,
+        self._op("softmax_finish_kernel:softmax|", 5.0 * B * Hh * Wh, 2.0 * B * Hh * Wh * 4,
                  lambda: cabi.softmax_heatmap(logits_flat, heatmap.view(B, Hh * Wh), sm_scratch))
 
         # a11 -- orientation decoder (no matching inside; input = [scores_1, normalize(x_1)], models.py:323)
@@ -326,7 +330,7 @@ class PostEncoderPipeline:
                 o = self._conv3(ow["conv_b"], o, None, dtype, relu=False, out_f32=True, name=nm + "b")  # fp32 [B,512,512,2]
         ori = torch.empty((B, 2, Hh, Wh), dtype=f32, device=dev)
         o_in = o
-        self._op("ori_normalize", 6.0 * B * Hh * Wh, 2.0 * B * Hh * Wh * (o.element_size() + 4),
+        self._op("ori_normalize_kernel:ori_normalize|", 6.0 * B * Hh * Wh, 2.0 * B * Hh * Wh * (o.element_size() + 4),
                  lambda: cabi.ori_normalize(o_in, ori))                                   # a12
         return (logits_flat, heatmap, ori, *scores_out)
 

@@ -102,6 +102,9 @@ typedef struct ccvpe_igemm_desc {
 
 /* a3: models.py:102-104,173-184 | a8: models.py:109-124,207,229,... | a9: models.py:42-47,110-127,209,231,...     */
 int ccvpe_igemm(const ccvpe_igemm_desc* desc, void* stream);
+/* which kernel ccvpe_igemm would launch for this descriptor: 0 = igemm_simt_kernel, 1 = igemm_tcgen05_kernel,
+ * 2 = conv_ring_tcgen05_kernel; < 0 = error.  (Used by the benchmark to attribute time to kernels.) */
+int ccvpe_igemm_plan(const ccvpe_igemm_desc* desc);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * a4 a5 a6  Rolled cosine matching of one decoder level -- reference models.py:186-202 (x6 levels), prior-limited
