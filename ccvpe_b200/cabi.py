@@ -20,7 +20,7 @@ EXPORTED_SYMBOLS = (
     "ccvpe_abi_version", "ccvpe_last_error", "ccvpe_launch_count", "ccvpe_reset_launch_count",
     "ccvpe_grd_descriptor", "ccvpe_igemm", "ccvpe_igemm_plan", "ccvpe_match_scratch_elems", "ccvpe_match_level",
     "ccvpe_softmax_scratch_elems", "ccvpe_softmax_heatmap", "ccvpe_ori_normalize",
-    "ccvpe_pose_scratch_bytes", "ccvpe_pose_decode",
+    "ccvpe_pose_scratch_bytes", "ccvpe_pose_decode", "ccvpe_bias_silu_nhwc",
 )
 
 
@@ -93,6 +93,9 @@ def load() -> C.CDLL:
     lib.ccvpe_pose_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p]
+    lib.ccvpe_bias_silu_nhwc.restype = C.c_int
+    lib.ccvpe_bias_silu_nhwc.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
+                                         C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     if lib.ccvpe_abi_version() != 1:
         raise CcvpeError("libccvpe_b200.so ABI version mismatch")
     _lib = lib
@@ -211,3 +214,13 @@ def pose_decode(heatmap: torch.Tensor, ori: torch.Tensor, idx, rc, cs, angle, va
     H, W = heatmap.shape[-2:]
     _check(load().ccvpe_pose_decode(_ptr(heatmap), _ptr(ori), B, H, W, _ptr(idx), _ptr(rc), _ptr(cs), _ptr(angle),
                                     _ptr(valid), _ptr(scratch), _stream()), "ccvpe_pose_decode")
+
+
+def bias_silu_nhwc(x: torch.Tensor, bias: Optional[torch.Tensor], y: torch.Tensor, chan_sum: Optional[torch.Tensor] = None):
+    """x contiguous NHWC bf16 [B,H,W,C]; y NHWC bf16 view with contiguous channels (any batch/row/pixel strides)."""
+    _require_cuda(x, bias, y, chan_sum)
+    B, H, W, Cc = x.shape
+    if not x.is_contiguous() or y.stride(3) != 1 or tuple(y.shape) != tuple(x.shape):
+        raise CcvpeError("bias_silu_nhwc: x must be contiguous NHWC and y an NHWC view of the same shape")
+    _check(load().ccvpe_bias_silu_nhwc(_ptr(x), _ptr(bias), _ptr(y), y.stride(0), y.stride(1), y.stride(2), B, H, W, Cc,
+                                       _ptr(chan_sum), _stream()), "ccvpe_bias_silu_nhwc")

@@ -1,0 +1,99 @@
+// First step of SURVEY section 8(f)-2 (the PyTorch encoders are the end-to-end bottleneck once the decoder is fast):
+// one fused, vectorised pass for the glue between the encoder's cuDNN/cuBLAS calls,
+//
+//   y[b, h, w, c] = SiLU( x[b, h, w, c] + bias[c] )          (+ optional per-(b, c) sum over h, w of y)
+//
+// x is a contiguous channels-last bf16 tensor; y may be a strided view (the interior of a pre-zeroed padded buffer, so
+// the TensorFlow-"same" / circular padding of the following depthwise conv costs no extra copy); the channel sums feed
+// the squeeze-excite gate, so the separate mean pass over the 6x-expanded activation disappears as well.
+// HBM-bound: one read + one write of the tensor, 16-byte accesses.
+#include "common.cuh"
+
+namespace ccvpe {
+
+__global__ void __launch_bounds__(256)
+bias_silu_nhwc_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ bias,
+                      __nv_bfloat16* __restrict__ y, int64_t y_sb, int64_t y_sh, int64_t y_sw, int H, int W, int C,
+                      int pix_per_block, float* __restrict__ chan_sum) {
+  extern __shared__ float s_sum[];                 // [C] per-block channel sums (only if chan_sum)
+  const int G = C >> 3;                            // 8-channel groups per pixel
+  const int lanes = blockDim.x / G;                // pixels processed concurrently by the block
+  const int cg = threadIdx.x % G, pl = threadIdx.x / G;
+  const int b = blockIdx.y;
+  const int HW = H * W;
+  const int p_lo = blockIdx.x * pix_per_block;
+  const int p_hi = min(HW, p_lo + pix_per_block);
+  if (chan_sum) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) s_sum[c] = 0.f;
+    __syncthreads();
+  }
+  float bv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (bias && pl < lanes) {
+    uint4 q = *reinterpret_cast<const uint4*>(bias + cg * 8);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 f = __bfloat1622float2(h[j]);
+      bv[2 * j] = f.x;
+      bv[2 * j + 1] = f.y;
+    }
+  }
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (pl < lanes) {
+    const __nv_bfloat16* xb = x + (int64_t)b * HW * C + cg * 8;
+    __nv_bfloat16* yb = y + (int64_t)b * y_sb + cg * 8;
+    for (int p = p_lo + pl; p < p_hi; p += lanes) {
+      uint4 q = *reinterpret_cast<const uint4*>(xb + (int64_t)p * C);
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 f = __bfloat1622float2(h[j]);
+        float a0 = f.x + bv[2 * j], a1 = f.y + bv[2 * j + 1];
+        a0 = a0 / (1.f + __expf(-a0));
+        a1 = a1 / (1.f + __expf(-a1));
+        h[j] = __floats2bfloat162_rn(a0, a1);
+        if (chan_sum) {                            // sum what is actually stored (bf16-rounded), like a mean of y
+          float2 r = __bfloat1622float2(h[j]);
+          acc[2 * j] += r.x;
+          acc[2 * j + 1] += r.y;
+        }
+      }
+      const int hh = p / W, ww = p - hh * W;
+      *reinterpret_cast<uint4*>(yb + hh * y_sh + ww * y_sw) = q;
+    }
+  }
+  if (chan_sum) {
+    if (pl < lanes) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&s_sum[cg * 8 + j], acc[j]);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(chan_sum + (int64_t)b * C + c, s_sum[c]);
+  }
+}
+
+}  // namespace ccvpe
+
+extern "C" int ccvpe_bias_silu_nhwc(const void* x, const void* bias, void* y, int64_t y_sb, int64_t y_sh, int64_t y_sw,
+                                    int B, int H, int W, int C, float* chan_sum, void* stream) {
+  using namespace ccvpe;
+  CCVPE_REQUIRE(x && y, "ccvpe_bias_silu_nhwc: null pointer");
+  CCVPE_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && C <= 2048, "ccvpe_bias_silu_nhwc: bad shape B=%d H=%d W=%d C=%d",
+                B, H, W, C);
+  CCVPE_REQUIRE(aligned16(x) && aligned16(y) && aligned16(bias), "ccvpe_bias_silu_nhwc: pointers must be 16-byte aligned");
+  CCVPE_REQUIRE(y_sw % 8 == 0 && y_sh % 8 == 0 && y_sb % 8 == 0, "ccvpe_bias_silu_nhwc: output strides must be multiples of 8");
+  const int G = C / 8;
+  CCVPE_REQUIRE(G <= 256, "ccvpe_bias_silu_nhwc: C too large");
+  const int lanes = 256 / G;
+  // enough blocks to fill the machine a few times over, each with a long pixel loop (few atomics per block)
+  const int64_t HW = (int64_t)H * W;
+  int blocks_x = (int)((8LL * sm_count() + B - 1) / B);
+  int64_t ppb = (HW + blocks_x - 1) / blocks_x;
+  ppb = (ppb + lanes - 1) / lanes * lanes;
+  if (ppb < lanes) ppb = lanes;
+  blocks_x = (int)((HW + ppb - 1) / ppb);
+  bias_silu_nhwc_kernel<<<dim3(blocks_x, B), 256, chan_sum ? C * sizeof(float) : 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, (const __nv_bfloat16*)bias, (__nv_bfloat16*)y, y_sb, y_sh, y_sw, H, W, C, (int)ppb, chan_sum);
+  CCVPE_LAUNCH_CHECK("bias_silu_nhwc_kernel");
+  return CCVPE_OK;
+}

@@ -24,6 +24,7 @@ from typing import Dict, List, Tuple
 import torch
 from torch.nn import functional as F
 
+from . import cabi
 from .efficientnet import EfficientNetB0, MBConv, SamePadConv2d
 
 
@@ -87,17 +88,42 @@ class FastEncoder:
             self._buffers[key] = buf
         return buf                                                                   # NHWC physical
 
-    def _silu_into_padded(self, y_nhwc: torch.Tensor, lo: int, hi: int, tag) -> torch.Tensor:
-        """SiLU(y) written into the interior of a padded NHWC buffer; returns it as an NCHW-logical channels-last view."""
-        B, H, W, C = y_nhwc.shape
-        buf = self._padded(B, C, H, W, lo, hi, tag)
-        torch.ops.aten.silu.out(y_nhwc, out=buf[:, lo:lo + H, lo:lo + W, :])
-        if self.circular:                                  # wrap-around columns (vertical borders stay zero)
-            if lo:
-                buf[:, lo:lo + H, :lo, :] = buf[:, lo:lo + H, W:W + lo, :]
-            if hi:
-                buf[:, lo:lo + H, lo + W:, :] = buf[:, lo:lo + H, lo:lo + hi, :]
-        return buf.permute(0, 3, 1, 2)
+    def _wrap_columns(self, buf, H, W, lo, hi):
+        """Circular width padding: copy the wrap-around columns inside the padded buffer (vertical borders stay zero)."""
+        if lo:
+            buf[:, lo:lo + H, :lo, :] = buf[:, lo:lo + H, W:W + lo, :]
+        if hi:
+            buf[:, lo:lo + H, lo + W:, :] = buf[:, lo:lo + H, lo:lo + hi, :]
+
+    def _act(self, x_nhwc: torch.Tensor, bias, pad=None, want_sum: bool = False):
+        """y = SiLU(x + bias) in ONE pass; optionally written into the interior of a padded staging buffer (pad = (lo, hi))
+        and/or accumulating the per-(b, c) sums the squeeze-excite gate needs.  CUDA bf16: libccvpe_b200's fused kernel;
+        otherwise (CPU / fp32 checks) the same arithmetic with torch ops.
+        Returns (y as NHWC view, padded NCHW-logical view or None, channel sums fp32 [B, C] or None)."""
+        B, H, W, C = x_nhwc.shape
+        buf = None
+        if pad is not None:
+            lo, hi = pad
+            buf = self._padded(B, C, H, W, lo, hi, "dw")
+            out = buf[:, lo:lo + H, lo:lo + W, :]
+        else:
+            out = torch.empty((B, H, W, C), dtype=x_nhwc.dtype, device=x_nhwc.device)
+        sums = None
+        if x_nhwc.is_cuda and x_nhwc.dtype == torch.bfloat16:
+            if want_sum:
+                sums = torch.zeros((B, C), dtype=torch.float32, device=x_nhwc.device)
+            cabi.bias_silu_nhwc(x_nhwc.contiguous(), bias, out, sums)
+        else:
+            t = x_nhwc if bias is None else x_nhwc + bias
+            torch.ops.aten.silu.out(t, out=out)
+            if want_sum:
+                sums = out.float().sum(dim=(1, 2))
+        padded_view = None
+        if buf is not None:
+            if self.circular:
+                self._wrap_columns(buf, H, W, pad[0], pad[1])
+            padded_view = buf.permute(0, 3, 1, 2)
+        return out, padded_view, sums
 
     # -- forward ------------------------------------------------------------------------------------------------
     @torch.no_grad()
@@ -110,47 +136,46 @@ class FastEncoder:
             x = F.pad(F.pad(x, (lo, hi, 0, 0), mode="circular"), (0, 0, lo, hi))     # 3-channel input: negligible
         else:
             x = F.pad(x, (lo, hi, lo, hi))
-        y = F.conv2d(x, self.stem_w, self.stem_b, stride=2)                          # [B,32,H/2,W/2] channels-last
-        cur = y.permute(0, 2, 3, 1)                                                  # NHWC view, pre-activation
-        pending_silu = True                                                          # `cur` still needs SiLU applied
+        pre = F.conv2d(x, self.stem_w, None, stride=2).permute(0, 2, 3, 1)          # NHWC, before bias + SiLU
+        pre_bias = self.stem_b
+        cur = None                                                                   # activated NHWC tensor
         outs: List[torch.Tensor] = []
-        for bi, o in enumerate(self.blocks):
-            B, H, W, Cin = cur.shape
-            if pending_silu and (o.has_expand or o.residual):
-                cur = F.silu(cur)                                                    # needed as GEMM input / residual
-                pending_silu = False
-            block_in = cur
-            if o.has_expand:
-                e = F.linear(cur.reshape(B * H * W, Cin), o.w_exp, o.b_exp).view(B, H, W, o.mid)
-                needs_silu = True
+        for o in self.blocks:
+            dw_pad = (o.pad_lo, o.pad_hi) if (self.circular or o.stride == 2) else None
+            if pre is not None and not o.has_expand and not o.residual:
+                # block 0: the stem's pending bias + SiLU is applied straight into the depthwise conv's input
+                plain, padded, _unused = self._act(pre, pre_bias, pad=dw_pad)
+                block_in = None
+                mid_in_plain, mid_in_padded = (plain if padded is None else None), padded
+                pre = None
             else:
-                e = cur
-                needs_silu = pending_silu
-            # depthwise conv input = SiLU(e) with TF-"same" padding
-            use_buffer = self.circular or o.stride == 2
-            if use_buffer:
-                if needs_silu:
-                    xin = self._silu_into_padded(e, o.pad_lo, o.pad_hi, "dw")
+                if pre is not None:
+                    cur = self._act(pre, pre_bias)[0]
+                    pre = None
+                block_in = cur
+                B, H, W, Cin = cur.shape
+                if o.has_expand:
+                    e = F.linear(cur.reshape(B * H * W, Cin), o.w_exp, o.b_exp).view(B, H, W, o.mid)
+                    plain, padded, _unused = self._act(e, None, pad=dw_pad)
+                    mid_in_plain, mid_in_padded = (plain if padded is None else None), padded
                 else:
-                    buf = self._padded(B, o.mid, H, W, o.pad_lo, o.pad_hi, "dw")
-                    buf[:, o.pad_lo:o.pad_lo + H, o.pad_lo:o.pad_lo + W, :] = e
-                    if self.circular:
-                        if o.pad_lo:
-                            buf[:, o.pad_lo:o.pad_lo + H, :o.pad_lo, :] = buf[:, o.pad_lo:o.pad_lo + H, W:W + o.pad_lo, :]
-                        if o.pad_hi:
-                            buf[:, o.pad_lo:o.pad_lo + H, o.pad_lo + W:, :] = \
-                                buf[:, o.pad_lo:o.pad_lo + H, o.pad_lo:o.pad_lo + o.pad_hi, :]
-                    xin = buf.permute(0, 3, 1, 2)
-                d = F.conv2d(xin, o.w_dw, o.b_dw, stride=o.stride, groups=o.mid)
+                    if dw_pad is not None:
+                        buf = self._padded(B, o.mid, H, W, o.pad_lo, o.pad_hi, "dw")
+                        buf[:, o.pad_lo:o.pad_lo + H, o.pad_lo:o.pad_lo + W, :] = cur
+                        if self.circular:
+                            self._wrap_columns(buf, H, W, o.pad_lo, o.pad_hi)
+                        mid_in_plain, mid_in_padded = None, buf.permute(0, 3, 1, 2)
+                    else:
+                        mid_in_plain, mid_in_padded = cur, None
+            if mid_in_padded is not None:
+                d = F.conv2d(mid_in_padded, o.w_dw, None, stride=o.stride, groups=o.mid)
             else:
-                xin = (F.silu(e) if needs_silu else e).permute(0, 3, 1, 2)
-                d = F.conv2d(xin, o.w_dw, o.b_dw, stride=1, padding=o.pad_lo, groups=o.mid)
-            pending_silu = False
-            d = F.silu(d.permute(0, 2, 3, 1))                                        # [B,Ho,Wo,mid] NHWC
+                d = F.conv2d(mid_in_plain.permute(0, 3, 1, 2), o.w_dw, None, stride=1, padding=o.pad_lo, groups=o.mid)
+            d, _unused, sums = self._act(d.permute(0, 2, 3, 1), o.b_dw, want_sum=True)     # [B,Ho,Wo,mid] NHWC + SE squeeze
             Bo, Ho, Wo, _ = d.shape
             # squeeze-excite gate folded into the projection weights
-            s = d.mean(dim=(1, 2), dtype=torch.float32).to(dt)                       # [B, mid]
-            g = torch.sigmoid(F.linear(F.silu(F.linear(s, o.w_red, o.b_red)), o.w_se, o.b_se))   # [B, mid]
+            sq = (sums / float(Ho * Wo)).to(dt)                                      # [B, mid]
+            g = torch.sigmoid(F.linear(F.silu(F.linear(sq, o.w_red, o.b_red)), o.w_se, o.b_se))   # [B, mid]
             wg = o.w_proj.unsqueeze(0) * g.unsqueeze(1)                              # [B, cout, mid]
             y = torch.baddbmm(o.b_proj.view(1, 1, -1), d.reshape(Bo, Ho * Wo, o.mid), wg.transpose(1, 2))
             y = y.view(Bo, Ho, Wo, o.cout)
@@ -160,7 +185,8 @@ class FastEncoder:
             if keep_blocks:
                 outs.append(cur.permute(0, 3, 1, 2))
         B, H, W, C = cur.shape
-        head = F.silu(F.linear(cur.reshape(B * H * W, C), self.head_w, self.head_b)).view(B, H, W, -1)
+        head_pre = F.linear(cur.reshape(B * H * W, C), self.head_w, self.head_b).view(B, H, W, -1)
+        head = self._act(head_pre, None)[0]
         return head.permute(0, 3, 1, 2), outs
 
     def extract_features(self, x):

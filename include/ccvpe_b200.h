@@ -148,6 +148,16 @@ int ccvpe_pose_decode(const float* heatmap, const float* ori, int B, int H, int 
                       int64_t* idx, int32_t* rc, float* cs, double* angle_deg, uint8_t* valid,
                       void* scratch, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Encoder glue (first step; the encoders themselves stay cuDNN/cuBLAS through PyTorch):
+ *   y[b,h,w,c] = SiLU(x[b,h,w,c] + bias[c]);   chan_sum[b,c] += sum_{h,w} y[b,h,w,c]   (optional, fp32, caller zeroes it)
+ * x: contiguous channels-last bf16 [B,H,W,C]; bias: bf16 [C] or NULL; y: bf16 with element strides (y_sb, y_sh, y_sw)
+ * between images / rows / pixels (channels contiguous) -- e.g. the interior of a padded buffer.  C % 8 == 0.
+ * Replaces x*sigmoid(x) after BN (reference efficientnet_pytorch/model.py:105-110) plus F.adaptive_avg_pool2d (:114).
+ * ------------------------------------------------------------------------------------------------------------- */
+int ccvpe_bias_silu_nhwc(const void* x, const void* bias, void* y, int64_t y_sb, int64_t y_sh, int64_t y_sw,
+                         int B, int H, int W, int C, float* chan_sum, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

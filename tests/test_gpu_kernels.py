@@ -380,3 +380,52 @@ def test_errors_are_loud(cuda_device):
     with pytest.raises(cabi.CcvpeError):
         cabi.match_level(x, torch.zeros(1, 12, device=cuda_device), 0, [0], 1,
                          scratch=torch.zeros(4096, device=cuda_device))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# encoder glue: fused bias + SiLU (+ squeeze-excite channel sums), strided output into a padded buffer
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,H,W,C,with_bias,padded", [(2, 33, 47, 96, True, True), (3, 16, 16, 1152, True, False),
+                                                      (1, 160, 320, 32, False, True), (2, 8, 8, 240, True, False)])
+def test_bias_silu_nhwc(cuda_device, B, H, W, C, with_bias, padded):
+    g = _gen(12)
+    dev = cuda_device
+    x = (torch.randn(B, H, W, C, generator=g) * 2).to(torch.bfloat16)
+    bias = torch.randn(C, generator=g).to(torch.bfloat16) if with_bias else None
+    ref = F.silu(x.float() + (bias.float() if with_bias else 0.0))
+    xd = x.to(dev)
+    if padded:
+        buf = torch.full((B, H + 3, W + 3, C), 5.0, device=dev, dtype=torch.bfloat16)
+        out = buf[:, 1:1 + H, 1:1 + W, :]
+    else:
+        out = torch.empty_like(xd)
+    sums = torch.zeros(B, C, device=dev)
+    cabi.bias_silu_nhwc(xd, bias.to(dev) if with_bias else None, out, sums)
+    torch.cuda.synchronize()
+    assert rel_err(out.float(), ref) < 1e-2                                   # bf16 output rounding
+    assert rel_err(sums, out.float().sum(dim=(1, 2))) < 1e-4                  # sums of what was stored
+    if padded:
+        assert torch.all(buf[:, 0] == 5.0) and torch.all(buf[:, :, 0] == 5.0) and torch.all(buf[:, H + 1:] == 5.0)
+
+
+def test_fast_encoder_bf16_on_gpu(cuda_device):
+    """The bf16 inference plan of the encoders (folded BN, fused bias+SiLU kernel, SE gate in the projection GEMM)
+    against the exact fp32 PyTorch encoder: rms error <= 3e-2 of rms(ref) on the head features and every skip."""
+    from ccvpe_b200.efficientnet import EfficientNetB0
+    from ccvpe_b200.fast_encoder import FastEncoder
+    from ccvpe_b200.synthetic import fill_deterministic
+
+    for circular, shape in ((True, (2, 3, 320, 640)), (False, (2, 3, 512, 512))):
+        enc = EfficientNetB0(circular=circular).eval()
+        fill_deterministic(enc.state_dict(), seed=7)
+        enc = enc.to(cuda_device)
+        x = torch.randn(*shape, generator=_gen(13)).to(cuda_device)
+        with torch.no_grad():
+            ref_head, ref_blocks = enc.extract_features_multiscale(x)
+        fast = FastEncoder(enc, torch.bfloat16)
+        for _ in range(2):
+            head, blocks = fast.extract_features_multiscale(x)
+        for a, b in [(head, ref_head)] + [(blocks[i], ref_blocks[i]) for i in (0, 2, 4, 10, 15)]:
+            assert a.shape == b.shape
+            rms = ((a.float() - b).pow(2).mean().sqrt() / b.pow(2).mean().sqrt()).item()
+            assert rms < 3e-2, rms
