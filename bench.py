@@ -259,6 +259,14 @@ def run_ours(args):
         layers = timer.summary()
         model.pipeline.timer = None
         # ---- timed region: end to end from host buffers ------------------------------------------------------
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0.record()
+        _g, _s, _ev = upload()
+        torch.cuda.current_stream().wait_event(_ev)
+        h1.record()
+        torch.cuda.synchronize()
+        h2d_ms = h0.elapsed_time(h1)                    # diagnostic: one un-overlapped H2D copy of a step's inputs
+        del _g, _s
         run_e2e(2)
         barrier()
         w0 = time.time()
@@ -338,6 +346,7 @@ def run_ours(args):
                        "l2": "per-step working set (inputs %.0f MB + >1 GB activations) exceeds the 126 MB L2" % (h2d / 1e6)},
             "e2e": {"value": round(e2e_value, 3), "unit": "pairs/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": round(ms_e2e / args.steps, 3),
+                    "h2d_alone_ms": round(h2d_ms, 3), "h2d_gbs": round(h2d / h2d_ms / 1e6, 1),
                     "note": "fp32 host images; the H2D copy of step i+1 overlaps the kernels of step i"},
             "gpu_launches": int(launches),
             "roofline": roofline, "kernels": kernels, "clocks": clocks,

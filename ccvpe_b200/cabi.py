@@ -18,7 +18,7 @@ BACKEND_AUTO, BACKEND_SIMT, BACKEND_TCGEN05 = 0, 1, 2
 
 EXPORTED_SYMBOLS = (
     "ccvpe_abi_version", "ccvpe_last_error", "ccvpe_launch_count", "ccvpe_reset_launch_count",
-    "ccvpe_grd_descriptor", "ccvpe_igemm", "ccvpe_igemm_plan", "ccvpe_match_scratch_elems", "ccvpe_match_level",
+    "ccvpe_grd_descriptor", "ccvpe_grd_descriptors", "ccvpe_igemm", "ccvpe_igemm_plan", "ccvpe_match_scratch_elems", "ccvpe_match_level",
     "ccvpe_softmax_scratch_elems", "ccvpe_softmax_heatmap", "ccvpe_ori_normalize",
     "ccvpe_pose_scratch_bytes", "ccvpe_pose_decode", "ccvpe_bias_silu_nhwc",
 )
@@ -70,6 +70,12 @@ def load() -> C.CDLL:
                                          C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                          C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ccvpe_grd_descriptors.restype = C.c_int
+    lib.ccvpe_grd_descriptors.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int,
+                                          C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                          C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.POINTER(C.c_void_p),
+                                          C.c_void_p, C.c_void_p]
     lib.ccvpe_igemm.restype = C.c_int
     lib.ccvpe_igemm.argtypes = [C.POINTER(IgemmDesc), C.c_void_p]
     lib.ccvpe_igemm_plan.restype = C.c_int
@@ -150,6 +156,21 @@ def grd_descriptor(feat: torch.Tensor, w1, b1, w2, b2, out: torch.Tensor, scratc
     _check(load().ccvpe_grd_descriptor(_ptr(feat), dtype_code(feat.dtype), B, K, H, W, sb, sk, sh, sw,
                                        _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), c, _ptr(out), _ptr(scratch), _stream()),
            "ccvpe_grd_descriptor")
+
+
+def grd_descriptors(feat: torch.Tensor, heads, outs, scratch: torch.Tensor):
+    """All heads at once.  heads: list of (w1 [c,K], b1 [c], w2 [H], b2 [1]) fp32 tensors; outs: list of fp32 [B, W*c]."""
+    B, K, H, W = feat.shape
+    sb, sk, sh, sw = feat.stride()
+    n = len(heads)
+    flat = [t for h in heads for t in h] + list(outs)
+    _require_cuda(feat, scratch, *flat)
+    arr = lambda ts: (C.c_void_p * n)(*[t.data_ptr() for t in ts])
+    cs = (C.c_int32 * n)(*[h[0].shape[0] for h in heads])
+    _check(load().ccvpe_grd_descriptors(_ptr(feat), dtype_code(feat.dtype), B, K, H, W, sb, sk, sh, sw, n,
+                                        arr([h[0] for h in heads]), arr([h[1] for h in heads]),
+                                        arr([h[2] for h in heads]), arr([h[3] for h in heads]), cs, arr(outs),
+                                        _ptr(scratch), _stream()), "ccvpe_grd_descriptors")
 
 
 def igemm(desc: IgemmDesc):

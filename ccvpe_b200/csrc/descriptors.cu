@@ -5,6 +5,8 @@
 //
 // Two small kernels: the height reduction (reads the 1 MB/pair feature volume once, any strides) and a warp-per-output
 // dot product over K = 1280 with coalesced reads of both operands.  HBM-bound, ~1 MB/pair; launch latency dominates.
+#include <cstring>
+
 #include "common.cuh"
 
 namespace ccvpe {
@@ -54,7 +56,120 @@ __global__ void grd_project_kernel(const float* __restrict__ S, const float* __r
   }
 }
 
+// ---- all six heads in two launches -----------------------------------------------------------------------------------
+constexpr int kMaxHeads = 6;
+struct HeadTable {
+  const float* w1[kMaxHeads];
+  const float* b1[kMaxHeads];
+  const float* w2[kMaxHeads];
+  const float* b2[kMaxHeads];
+  float* out[kMaxHeads];
+  int c[kMaxHeads];
+  int c_prefix[kMaxHeads + 1];
+  int n;
+};
+
+// S[l][b][w][k] = sum_h v_l[h] F[b,k,h,w]: the feature volume is read ONCE for all heads
+template <typename T>
+__global__ void grd_height_reduce_all_kernel(const T* __restrict__ feat, int B, int K, int H, int W, int64_t sb, int64_t sk,
+                                             int64_t sh, int64_t sw, HeadTable t, float* __restrict__ S, bool k_fastest) {
+  const int64_t total = (int64_t)B * K * W;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int b, k, w;
+    if (k_fastest) {
+      k = (int)(i % K);
+      w = (int)((i / K) % W);
+      b = (int)(i / ((int64_t)K * W));
+    } else {
+      w = (int)(i % W);
+      k = (int)((i / W) % K);
+      b = (int)(i / ((int64_t)K * W));
+    }
+    const T* p = feat + b * sb + k * sk + w * sw;
+    float acc[kMaxHeads];
+#pragma unroll
+    for (int l = 0; l < kMaxHeads; ++l) acc[l] = 0.f;
+    for (int h = 0; h < H; ++h) {
+      const float f = to_float(p[h * sh]);
+#pragma unroll
+      for (int l = 0; l < kMaxHeads; ++l)
+        if (l < t.n) acc[l] = fmaf(__ldg(t.w2[l] + h), f, acc[l]);
+    }
+#pragma unroll
+    for (int l = 0; l < kMaxHeads; ++l)
+      if (l < t.n) S[(((int64_t)l * B + b) * W + w) * K + k] = acc[l];
+  }
+}
+
+// one warp per output element over all heads: out_l[b, w*c_l + ch]
+__global__ void grd_project_all_kernel(const float* __restrict__ S, HeadTable t, int B, int W, int K, int H) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int64_t o = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const int ctot = t.c_prefix[t.n];
+  if (o >= (int64_t)B * W * ctot) return;
+  const int cc = (int)(o % ctot);
+  const int64_t bw = o / ctot;
+  int l = 0;
+#pragma unroll
+  for (int j = 1; j < kMaxHeads; ++j)
+    if (j < t.n && cc >= t.c_prefix[j]) l = j;
+  const int ch = cc - t.c_prefix[l];
+  const float* s = S + ((int64_t)l * B * W + bw) * K;
+  const float* w = t.w1[l] + (int64_t)ch * K;
+  float acc = 0.f;
+  for (int k = lane * 4; k < K; k += 128) {
+    const float4 a = *reinterpret_cast<const float4*>(w + k);
+    const float4 v = *reinterpret_cast<const float4*>(s + k);
+    acc = fmaf(a.x, v.x, acc);
+    acc = fmaf(a.y, v.y, acc);
+    acc = fmaf(a.z, v.z, acc);
+    acc = fmaf(a.w, v.w, acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    float vs = 0.f;
+    for (int h = 0; h < H; ++h) vs += t.w2[l][h];
+    t.out[l][bw * t.c[l] + ch] = acc + t.b1[l][ch] * vs + t.b2[l][0];
+  }
+}
+
 }  // namespace ccvpe
+
+extern "C" int ccvpe_grd_descriptors(const void* feat, int dtype, int B, int K, int H, int W, int64_t sb, int64_t sk,
+                                     int64_t sh, int64_t sw, int n_heads, const float* const* w1, const float* const* b1,
+                                     const float* const* w2, const float* const* b2, const int32_t* c, float* const* out,
+                                     float* scratch, void* stream) {
+  using namespace ccvpe;
+  CCVPE_REQUIRE(feat && w1 && b1 && w2 && b2 && c && out && scratch, "ccvpe_grd_descriptors: null pointer");
+  CCVPE_REQUIRE(n_heads >= 1 && n_heads <= kMaxHeads, "ccvpe_grd_descriptors: n_heads=%d out of range", n_heads);
+  CCVPE_REQUIRE(B > 0 && K > 0 && K % 4 == 0 && H > 0 && W > 0, "ccvpe_grd_descriptors: bad shape B=%d K=%d H=%d W=%d", B, K, H, W);
+  CCVPE_REQUIRE(dtype == CCVPE_F32 || dtype == CCVPE_BF16, "ccvpe_grd_descriptors: bad dtype %d", dtype);
+  HeadTable t;
+  memset(&t, 0, sizeof(t));
+  t.n = n_heads;
+  for (int l = 0; l < n_heads; ++l) {
+    CCVPE_REQUIRE(w1[l] && b1[l] && w2[l] && b2[l] && out[l] && c[l] > 0, "ccvpe_grd_descriptors: bad head %d", l);
+    CCVPE_REQUIRE(aligned16(w1[l]), "ccvpe_grd_descriptors: w1 must be 16-byte aligned");
+    t.w1[l] = w1[l]; t.b1[l] = b1[l]; t.w2[l] = w2[l]; t.b2[l] = b2[l]; t.out[l] = out[l]; t.c[l] = c[l];
+    t.c_prefix[l + 1] = t.c_prefix[l] + c[l];
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t total = (int64_t)B * K * W;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > sm_count() * 16) blocks = sm_count() * 16;
+  const bool k_fastest = (sk == 1);
+  if (dtype == CCVPE_F32)
+    grd_height_reduce_all_kernel<float><<<blocks, 256, 0, st>>>((const float*)feat, B, K, H, W, sb, sk, sh, sw, t, scratch, k_fastest);
+  else
+    grd_height_reduce_all_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)feat, B, K, H, W, sb, sk, sh, sw, t, scratch, k_fastest);
+  CCVPE_LAUNCH_CHECK("grd_height_reduce_all_kernel");
+  const int64_t outputs = (int64_t)B * W * t.c_prefix[n_heads];
+  const int wpb = 8;
+  grd_project_all_kernel<<<(unsigned)((outputs + wpb - 1) / wpb), wpb * 32, 0, st>>>(scratch, t, B, W, K, H);
+  CCVPE_LAUNCH_CHECK("grd_project_all_kernel");
+  return CCVPE_OK;
+}
 
 extern "C" int ccvpe_grd_descriptor(const void* feat, int dtype, int B, int K, int H, int W, int64_t sb, int64_t sk,
                                     int64_t sh, int64_t sw, const float* w1, const float* b1, const float* w2,

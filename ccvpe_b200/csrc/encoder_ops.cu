@@ -42,24 +42,35 @@ bias_silu_nhwc_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* 
   if (pl < lanes) {
     const __nv_bfloat16* xb = x + (int64_t)b * HW * C + cg * 8;
     __nv_bfloat16* yb = y + (int64_t)b * y_sb + cg * 8;
-    for (int p = p_lo + pl; p < p_hi; p += lanes) {
-      uint4 q = *reinterpret_cast<const uint4*>(xb + (int64_t)p * C);
-      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
+    constexpr int U = 4;                           // independent 16-byte loads in flight per thread
+    for (int p0 = p_lo + pl; p0 < p_hi; p0 += lanes * U) {
+      uint4 q[U];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float2 f = __bfloat1622float2(h[j]);
-        float a0 = f.x + bv[2 * j], a1 = f.y + bv[2 * j + 1];
-        a0 = a0 / (1.f + __expf(-a0));
-        a1 = a1 / (1.f + __expf(-a1));
-        h[j] = __floats2bfloat162_rn(a0, a1);
-        if (chan_sum) {                            // sum what is actually stored (bf16-rounded), like a mean of y
-          float2 r = __bfloat1622float2(h[j]);
-          acc[2 * j] += r.x;
-          acc[2 * j + 1] += r.y;
-        }
+      for (int u = 0; u < U; ++u) {
+        const int p = p0 + u * lanes;
+        if (p < p_hi) q[u] = __ldcs(reinterpret_cast<const uint4*>(xb + (int64_t)p * C));   // streamed: read once
       }
-      const int hh = p / W, ww = p - hh * W;
-      *reinterpret_cast<uint4*>(yb + hh * y_sh + ww * y_sw) = q;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int p = p0 + u * lanes;
+        if (p >= p_hi) break;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q[u]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float2 f = __bfloat1622float2(h[j]);
+          float a0 = f.x + bv[2 * j], a1 = f.y + bv[2 * j + 1];
+          a0 = __fdividef(a0, 1.f + __expf(-a0));
+          a1 = __fdividef(a1, 1.f + __expf(-a1));
+          h[j] = __floats2bfloat162_rn(a0, a1);
+          if (chan_sum) {                          // sum what is actually stored (bf16-rounded), like a mean of y
+            float2 r = __bfloat1622float2(h[j]);
+            acc[2 * j] += r.x;
+            acc[2 * j + 1] += r.y;
+          }
+        }
+        const int hh = p / W, ww = p - hh * W;
+        *reinterpret_cast<uint4*>(yb + hh * y_sh + ww * y_sw) = q[u];
+      }
     }
   }
   if (chan_sum) {

@@ -234,15 +234,13 @@ class PostEncoderPipeline:
         if Hg != spec.grd_feat_h:
             raise cabi.CcvpeError("ground feature height %d does not match the %s heads (%d)" % (Hg, spec.name,
                                                                                                spec.grd_feat_h))
-        scratch_g = torch.empty(Bg * Kg * Wg, dtype=f32, device=dev)
-        g: List[torch.Tensor] = []
-        for l in range(6):
-            w1, b1, w2, b2 = w["heads"][l]
-            out = torch.empty((Bg, Wg * w1.shape[0]), dtype=f32, device=dev)
-            self._op("grd_project_kernel:grd_descriptor|", 2.0 * Bg * Wg * Kg * (Hg + w1.shape[0]),
-                     grd_feat.numel() * grd_feat.element_size() + out.numel() * 4,
-                     lambda: cabi.grd_descriptor(grd_feat, w1, b1, w2, b2, out, scratch_g))
-            g.append(out)
+        scratch_g = torch.empty(6 * Bg * Kg * Wg, dtype=f32, device=dev)
+        g: List[torch.Tensor] = [torch.empty((Bg, Wg * h[0].shape[0]), dtype=f32, device=dev) for h in w["heads"]]
+        heads = w["heads"]
+        ctot = sum(h[0].shape[0] for h in heads)
+        self._op("grd_project_all_kernel:grd_descriptors|", 2.0 * Bg * Wg * Kg * (6 * Hg + ctot),
+                 grd_feat.numel() * grd_feat.element_size() + sum(t.numel() for t in g) * 4,
+                 lambda: cabi.grd_descriptors(grd_feat, heads, g, scratch_g))
 
         # a3 -- aerial cell descriptors: [B,16,16,1280] -> [B,8,8,D]
         fs = _cl(sat_feat, dtype)

@@ -61,6 +61,13 @@ int ccvpe_grd_descriptor(const void* feat, int dtype, int B, int K, int H, int W
                          const float* w1, const float* b1, const float* w2, const float* b2, int c,
                          float* out, float* scratch, void* stream);
 
+/* All heads of a model in two launches (the feature volume is read once): HOST arrays of n_heads (<= 6) device
+ * pointers / channel counts; out[l] fp32 [B, W*c[l]]; scratch fp32 >= n_heads*B*K*W elements; K % 4 == 0. */
+int ccvpe_grd_descriptors(const void* feat, int dtype, int B, int K, int H, int W,
+                          int64_t sb, int64_t sk, int64_t sh, int64_t sw, int n_heads,
+                          const float* const* w1, const float* const* b1, const float* const* w2, const float* const* b2,
+                          const int32_t* c, float* const* out, float* scratch, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * Generic implicit GEMM used for a3 (aerial cell descriptors), a8 (ConvTranspose2d k2 s2) and a9 (3x3 convs):
  *

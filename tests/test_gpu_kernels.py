@@ -429,3 +429,26 @@ def test_fast_encoder_bf16_on_gpu(cuda_device):
             assert a.shape == b.shape
             rms = ((a.float() - b).pow(2).mean().sqrt() / b.pow(2).mean().sqrt()).item()
             assert rms < 3e-2, rms
+
+
+@pytest.mark.parametrize("B,H,W,cs,layout,dtype", [(2, 10, 20, (64, 32, 16, 8, 4, 2), "nchw", torch.float32),
+                                                   (3, 8, 32, (16, 8, 4, 2, 1, 1), "nhwc", torch.bfloat16),
+                                                   (1, 4, 7, (32, 16, 8, 4, 2, 1), "nhwc", torch.float32)])
+def test_grd_descriptors_all_heads(cuda_device, B, H, W, cs, layout, dtype):
+    g = _gen(14)
+    dev = cuda_device
+    feat = torch.randn(B, 1280, H, W, generator=g)
+    heads, refs = [], []
+    for c in cs:
+        w1, b1 = torch.randn(c, 1280, 1, 1, generator=g) * 0.05, torch.randn(c, generator=g)
+        w2, b2 = torch.randn(1, H, 1, 1, generator=g), torch.randn(1, generator=g)
+        refs.append(orc.grd_descriptor(feat.to(dtype).float(), w1, b1, w2, b2))
+        heads.append((w1.reshape(c, 1280).contiguous().to(dev), b1.to(dev), w2.reshape(H).contiguous().to(dev), b2.to(dev)))
+    f = feat.to(dev, dtype)
+    if layout == "nhwc":
+        f = f.contiguous(memory_format=torch.channels_last)
+    outs = [torch.empty(B, W * c, device=dev) for c in cs]
+    scratch = torch.empty(6 * B * 1280 * W, device=dev)
+    cabi.grd_descriptors(f, heads, outs, scratch)
+    for o, r in zip(outs, refs):
+        assert rel_err(o, r) < FP32_TOL
