@@ -184,6 +184,9 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
+        # keep stdout to the one JSON line: NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 

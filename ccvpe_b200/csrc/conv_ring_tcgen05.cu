@@ -155,6 +155,13 @@ __global__ void __launch_bounds__(RING_THREADS, 1) conv_ring_tcgen05_kernel(cons
       const int depth = p.depth, H = p.H, R = p.R, chunks = p.chunks;
       const uint32_t bar_full0 = smem_u32(&bar_full[0]), bar_empty0 = smem_u32(&bar_empty[0]);
       const uint32_t bar_tf0 = smem_u32(&bar_tmem_full[0]), bar_te0 = smem_u32(&bar_tmem_empty[0]);
+      // fast path for a single 16-channel K block (all four 512x512 convs): everything in registers
+      const bool simple = (nblk == 1) && ((s_blk[0].w >> 16) == 1u);
+      const uint64_t simple_hi = (uint64_t)s_blk[0].z << 32;
+      const uint32_t simple_a = s_blk[0].x, simple_rowp = s_blk[0].w & 0xFFFFu;
+      uint32_t simple_w[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) simple_w[t] = w16 + (uint32_t)t * tap16 + s_blk[0].y;
       mbar_wait(smem_u32(&bar_w), 0);
       tc_fence_after();
       // ring position of the NEXT row to be consumed for the first time (same sequence as the producer)
@@ -183,37 +190,58 @@ __global__ void __launch_bounds__(RING_THREADS, 1) conv_ring_tcgen05_kernel(cons
           mbar_wait(bar_te0 + 8u * acc, (((uint32_t)it >> 1) & 1u) ^ 1u);
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + acc * (uint32_t)TC_MAX_N;
-          uint32_t accumulate = 0;
-#pragma unroll 1
-          for (int dy = 0; dy < 3; ++dy) {
-            const int sl = dy == 0 ? s_prev : (dy == 1 ? s_cur : s_next);
-            if (sl < 0) continue;                    // zero padding row: contributes nothing
-            const uint32_t a_row = ring16 + (uint32_t)sl * row16;
-            const uint32_t w_tap = w16 + (uint32_t)(dy * 3) * tap16;
-#pragma unroll 1
-            for (int g = 0; g < nblk; ++g) {
-              const uint4 bk = s_blk[g];             // {a offset, w offset, descriptor hi word, row pitch | k16 count << 16}
-              const uint64_t hi = (uint64_t)bk.z << 32;
-              const uint32_t rowp = bk.w & 0xFFFFu, nk16 = bk.w >> 16;
-              if (elect_one()) {
+          if (simple) {
+            // one 16-channel K block (the 512^2 level): nine MMAs, every descriptor word precomputed
+            if (elect_one()) {
+              uint32_t accumulate = 0;
 #pragma unroll
-                for (int dx = 0; dx < 3; ++dx) {
-                  // tap (dy, dx): rows [dx, dx + 128) of the halo'd row tile; weights of tap dy*3 + dx
-                  const uint64_t adesc = hi | (a_row + bk.x + (uint32_t)dx * rowp);
-                  const uint64_t bdesc = hi | (w_tap + (uint32_t)dx * tap16 + bk.y);
-                  umma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);
-                  accumulate = 1;
-                  if (nk16 > 1) {
-                    umma_bf16(tmem_d, adesc + 2, bdesc + 2, idesc, 1u);
-                    if (nk16 > 2) {
-                      umma_bf16(tmem_d, adesc + 4, bdesc + 4, idesc, 1u);
-                      if (nk16 > 3) umma_bf16(tmem_d, adesc + 6, bdesc + 6, idesc, 1u);
-                    }
+              for (int dy = 0; dy < 3; ++dy) {
+                const int sl = dy == 0 ? s_prev : (dy == 1 ? s_cur : s_next);
+                if (sl >= 0) {
+                  const uint32_t a_row = ring16 + (uint32_t)sl * row16 + simple_a;
+#pragma unroll
+                  for (int dx = 0; dx < 3; ++dx) {
+                    umma_bf16(tmem_d, simple_hi | (a_row + (uint32_t)dx * simple_rowp), simple_hi | simple_w[dy * 3 + dx],
+                              idesc, accumulate);
+                    accumulate = 1;
                   }
                 }
               }
-              accumulate = 1;
-              __syncwarp();
+            }
+            __syncwarp();
+          } else {
+          uint32_t accumulate = 0;
+#pragma unroll 1
+            for (int dy = 0; dy < 3; ++dy) {
+              const int sl = dy == 0 ? s_prev : (dy == 1 ? s_cur : s_next);
+              if (sl < 0) continue;                    // zero padding row: contributes nothing
+              const uint32_t a_row = ring16 + (uint32_t)sl * row16;
+              const uint32_t w_tap = w16 + (uint32_t)(dy * 3) * tap16;
+#pragma unroll 1
+              for (int g = 0; g < nblk; ++g) {
+                const uint4 bk = s_blk[g];             // {a offset, w offset, descriptor hi word, row pitch | k16 count << 16}
+                const uint64_t hi = (uint64_t)bk.z << 32;
+                const uint32_t rowp = bk.w & 0xFFFFu, nk16 = bk.w >> 16;
+                if (elect_one()) {
+#pragma unroll
+                  for (int dx = 0; dx < 3; ++dx) {
+                    // tap (dy, dx): rows [dx, dx + 128) of the halo'd row tile; weights of tap dy*3 + dx
+                    const uint64_t adesc = hi | (a_row + bk.x + (uint32_t)dx * rowp);
+                    const uint64_t bdesc = hi | (w_tap + (uint32_t)dx * tap16 + bk.y);
+                    umma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);
+                    accumulate = 1;
+                    if (nk16 > 1) {
+                      umma_bf16(tmem_d, adesc + 2, bdesc + 2, idesc, 1u);
+                      if (nk16 > 2) {
+                        umma_bf16(tmem_d, adesc + 4, bdesc + 4, idesc, 1u);
+                        if (nk16 > 3) umma_bf16(tmem_d, adesc + 6, bdesc + 6, idesc, 1u);
+                      }
+                    }
+                  }
+                }
+                accumulate = 1;
+                __syncwarp();
+              }
             }
           }
           if (elect_one()) {

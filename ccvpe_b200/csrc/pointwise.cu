@@ -35,14 +35,27 @@ softmax_partial_kernel(const float* __restrict__ logits, int64_t n, int segs, fl
   float m = -INFINITY, s = 0.f;
   const bool vec_ok = (n % 4 == 0);
   if (vec_ok) {
-    for (int64_t i = lo + threadIdx.x * 4; i < hi; i += kRowThreads * 4) {
-      float4 v = *reinterpret_cast<const float4*>(row + i);
-      float mx = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+    constexpr int U = 4;                                   // independent 16-byte loads in flight per thread
+    for (int64_t i0 = lo + threadIdx.x * 4; i0 < hi; i0 += (int64_t)kRowThreads * 4 * U) {
+      float4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t i = i0 + (int64_t)u * kRowThreads * 4;
+        v[u] = i < hi ? __ldg(reinterpret_cast<const float4*>(row + i))
+                      : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      }
+      float mx = -INFINITY;
+#pragma unroll
+      for (int u = 0; u < U; ++u) mx = fmaxf(mx, fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w)));
       if (mx > m) {
         s *= expf(m - mx);
         m = mx;
       }
-      s += expf(v.x - m) + expf(v.y - m) + expf(v.z - m) + expf(v.w - m);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t i = i0 + (int64_t)u * kRowThreads * 4;
+        if (i < hi) s += expf(v[u].x - m) + expf(v[u].y - m) + expf(v[u].z - m) + expf(v[u].w - m);
+      }
     }
   } else {
     for (int64_t i = lo + threadIdx.x; i < hi; i += kRowThreads) {
@@ -90,13 +103,24 @@ softmax_finish_kernel(const float* __restrict__ logits, float* __restrict__ heat
   const float* row = logits + (int64_t)b * n;
   float* out = heat + (int64_t)b * n;
   if (n % 4 == 0) {
-    for (int64_t i = lo + threadIdx.x * 4; i < hi; i += kRowThreads * 4) {
-      float4 v = *reinterpret_cast<const float4*>(row + i);
-      v.x = expf(v.x - M) * inv;
-      v.y = expf(v.y - M) * inv;
-      v.z = expf(v.z - M) * inv;
-      v.w = expf(v.w - M) * inv;
-      *reinterpret_cast<float4*>(out + i) = v;
+    constexpr int U = 4;
+    for (int64_t i0 = lo + threadIdx.x * 4; i0 < hi; i0 += (int64_t)kRowThreads * 4 * U) {
+      float4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t i = i0 + (int64_t)u * kRowThreads * 4;
+        if (i < hi) v[u] = __ldg(reinterpret_cast<const float4*>(row + i));
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t i = i0 + (int64_t)u * kRowThreads * 4;
+        if (i >= hi) break;
+        v[u].x = expf(v[u].x - M) * inv;
+        v[u].y = expf(v[u].y - M) * inv;
+        v[u].z = expf(v[u].z - M) * inv;
+        v[u].w = expf(v[u].w - M) * inv;
+        __stcs(reinterpret_cast<float4*>(out + i), v[u]);
+      }
     }
   } else {
     for (int64_t i = lo + threadIdx.x; i < hi; i += kRowThreads) out[i] = expf(row[i] - M) * inv;
@@ -109,23 +133,59 @@ softmax_finish_kernel(const float* __restrict__ logits, float* __restrict__ heat
 template <typename T>
 __global__ void ori_normalize_kernel(const T* __restrict__ in, int ld, float* __restrict__ out, int64_t HW,
                                      int64_t total) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t b = i / HW, p = i - b * HW;
-    const T* src = in + i * ld;
-    float c, s;
-    if constexpr (sizeof(T) == 4) {
-      float2 v = *reinterpret_cast<const float2*>(src);
-      c = v.x;
-      s = v.y;
+  // 4 consecutive pixels per thread: with ld == 2 that is one 32-byte (fp32) / 16-byte (bf16) load and two float4 stores
+  const int64_t groups = (total + 3) / 4;
+  for (int64_t gidx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; gidx < groups; gidx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i0 = gidx * 4;
+    float c[4], s[4];
+    const bool fast = (ld == 2) && (i0 + 3 < total) && (HW % 4 == 0);
+    if (fast) {
+      if constexpr (sizeof(T) == 4) {
+        const float4 a = __ldcs(reinterpret_cast<const float4*>(in + i0 * 2));
+        const float4 b = __ldcs(reinterpret_cast<const float4*>(in + i0 * 2 + 4));
+        c[0] = a.x; s[0] = a.y; c[1] = a.z; s[1] = a.w; c[2] = b.x; s[2] = b.y; c[3] = b.z; s[3] = b.w;
+      } else {
+        const uint4 q = __ldcs(reinterpret_cast<const uint4*>(in + i0 * 2));
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __bfloat1622float2(h[j]);
+          c[j] = f.x;
+          s[j] = f.y;
+        }
+      }
     } else {
-      __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(src);
-      float2 f = __bfloat1622float2(v);
-      c = f.x;
-      s = f.y;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int64_t i = i0 + j;
+        c[j] = s[j] = 0.f;
+        if (i < total) {
+          c[j] = to_float(in[i * ld]);
+          s[j] = to_float(in[i * ld + 1]);
+        }
+      }
     }
-    float nrm = fmaxf(sqrtf(c * c + s * s), 1e-12f);
-    out[(b * 2 + 0) * HW + p] = c / nrm;
-    out[(b * 2 + 1) * HW + p] = s / nrm;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float nrm = fmaxf(sqrtf(c[j] * c[j] + s[j] * s[j]), 1e-12f);
+      c[j] /= nrm;
+      s[j] /= nrm;
+    }
+    if (fast) {
+      const int64_t b = i0 / HW, p = i0 - b * HW;      // HW % 4 == 0: the 4 pixels share one image
+      __stcs(reinterpret_cast<float4*>(out + (b * 2 + 0) * HW + p), make_float4(c[0], c[1], c[2], c[3]));
+      __stcs(reinterpret_cast<float4*>(out + (b * 2 + 1) * HW + p), make_float4(s[0], s[1], s[2], s[3]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int64_t i = i0 + j;
+        if (i < total) {
+          const int64_t b = i / HW, p = i - b * HW;
+          out[(b * 2 + 0) * HW + p] = c[j];
+          out[(b * 2 + 1) * HW + p] = s[j];
+        }
+      }
+    }
   }
 }
 
@@ -283,8 +343,9 @@ extern "C" int ccvpe_ori_normalize(const void* in, int dtype, int ld, float* out
   CCVPE_REQUIRE(dtype == CCVPE_F32 || dtype == CCVPE_BF16, "ccvpe_ori_normalize: bad dtype %d", dtype);
   cudaStream_t st = (cudaStream_t)stream;
   int64_t total = (int64_t)B * HW;
-  int blocks = (int)((total + 255) / 256);
+  int blocks = (int)(((total + 3) / 4 + 255) / 256);
   if (blocks > sm_count() * 16) blocks = sm_count() * 16;
+  CCVPE_REQUIRE(aligned16(in) && aligned16(out), "ccvpe_ori_normalize: pointers must be 16-byte aligned");
   if (dtype == CCVPE_F32)
     ori_normalize_kernel<float><<<blocks, 256, 0, st>>>((const float*)in, ld, out, HW, total);
   else
