@@ -144,10 +144,10 @@ __device__ __forceinline__ void epi_store_row(const EpiParams& e, uint32_t taddr
                                               bool valid, int m_glob, float rs, float r1, const float* s_bias,
                                               const float* s_r1w) {
   const bool has_r1 = (e.row_r1 != nullptr);
-  int64_t base_px[4];
-  int64_t plane0 = 0;
+  // element offsets of this row's output pixel(s); 4 scalars (not an indexed array: that would live in local memory)
+  int64_t px0 = 0, px1 = 0, px2 = 0, px3 = 0, plane0 = 0;
   if (e.out_mode == 0) {
-    base_px[0] = (int64_t)m_glob * e.ldo;
+    px0 = (int64_t)m_glob * e.ldo;
   } else {
     const int b_img = m_glob / e.HWo;
     const int hw = m_glob - b_img * e.HWo;
@@ -155,9 +155,11 @@ __device__ __forceinline__ void epi_store_row(const EpiParams& e, uint32_t taddr
       plane0 = (int64_t)b_img * e.N * e.HWo + hw;
     } else {
       const int h = hw / e.Wout, w = hw - h * e.Wout;
-#pragma unroll
-      for (int ij = 0; ij < 4; ++ij)
-        base_px[ij] = (((int64_t)b_img * 2 * e.Hout + 2 * h + (ij >> 1)) * (2 * e.Wout) + 2 * w + (ij & 1)) * e.ldo;
+      const int64_t row_pitch = (int64_t)2 * e.Wout * e.ldo;
+      px0 = (((int64_t)b_img * 2 * e.Hout + 2 * h) * (2 * e.Wout) + 2 * w) * e.ldo;   // quadrant (i, j) = (0, 0)
+      px1 = px0 + e.ldo;                                                               // (0, 1)
+      px2 = px0 + row_pitch;                                                           // (1, 0)
+      px3 = px2 + e.ldo;                                                               // (1, 1)
     }
   }
   const int cout = e.out_mode == 1 ? (e.N >> 2) : e.N;
@@ -196,7 +198,7 @@ __device__ __forceinline__ void epi_store_row(const EpiParams& e, uint32_t taddr
           if (n + j < e.N) o[(int64_t)(n + j) * e.HWo] = y[j];
         continue;
       }
-      const int64_t off = (e.out_mode == 0 ? base_px[0] : base_px[ij]) + co;
+      const int64_t off = (ij == 0 ? px0 : (ij == 1 ? px1 : (ij == 2 ? px2 : px3))) + co;
       const bool full8 = (n + 8 <= e.N);
       if (e.out_f32) {
         float* o = static_cast<float*>(e.out) + off;
