@@ -15,7 +15,8 @@
 
 namespace ccvpe {
 
-constexpr int RING_THREADS = 384;
+constexpr int RING_THREADS = 192;     // warp 0 producer, warp 1 MMA issuer + TMEM owner, warps 2-5 epilogue
+constexpr int RING_EPI_THREADS = 128;
 constexpr int RING_MAX_DEPTH = 8;
 constexpr int RING_HALO_W = TC_BM + 2;
 constexpr int RING_SMEM_BUDGET = 208 * 1024;
@@ -23,7 +24,7 @@ constexpr int RING_SMEM_BUDGET = 208 * 1024;
 struct RingParams {
   CUtensorMap tm_a0, tm_a1, tm_b0, tm_b1;
   int nb0, nb1, c0, c1, kw0, kw1, kpad0, kpad1;
-  int block_n, depth;
+  int block_n, depth, tmem_cols;
   int B, H, W, strips, R, chunks, total_units;
   int a_blk0, a_blk1, row_bytes;      // ring slot geometry
   int w_blk0, w_blk1, w_tap_bytes;    // resident weight geometry
@@ -39,7 +40,7 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm,
       : "memory");
 }
 
-__global__ void __launch_bounds__(RING_THREADS, 1) conv_ring_tcgen05_kernel(const __grid_constant__ RingParams p) {
+__global__ void __launch_bounds__(RING_THREADS, 2) conv_ring_tcgen05_kernel(const __grid_constant__ RingParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[RING_MAX_DEPTH];
   __shared__ __align__(8) uint64_t bar_empty[RING_MAX_DEPTH];
@@ -76,7 +77,7 @@ __global__ void __launch_bounds__(RING_THREADS, 1) conv_ring_tcgen05_kernel(cons
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&bar_tmem_full[a]), 1);
-      mbar_init(smem_u32(&bar_tmem_empty[a]), TC_EPI_THREADS / 32);
+      mbar_init(smem_u32(&bar_tmem_empty[a]), RING_EPI_THREADS / 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -88,9 +89,9 @@ __global__ void __launch_bounds__(RING_THREADS, 1) conv_ring_tcgen05_kernel(cons
       prefetch_tmap(&p.tm_b1);
     }
   }
-  if (warp == 2) {
+  if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
-                 "r"(512)
+                 "r"(p.tmem_cols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(RING_THREADS, 1) conv_ring_tcgen05_kernel(cons
           const uint32_t acc = (uint32_t)it & 1u;
           mbar_wait(bar_te0 + 8u * acc, (((uint32_t)it >> 1) & 1u) ^ 1u);
           tc_fence_after();
-          const uint32_t tmem_d = tmem_base + acc * (uint32_t)TC_MAX_N;
+          const uint32_t tmem_d = tmem_base + acc * (uint32_t)p.block_n;
           if (simple) {
             // one 16-channel K block (the 512^2 level): nine MMAs, every descriptor word precomputed
             if (elect_one()) {
@@ -259,13 +260,12 @@ __global__ void __launch_bounds__(RING_THREADS, 1) conv_ring_tcgen05_kernel(cons
         }
       }
     }
-  } else if (warp >= 4) {
-    // ===================== epilogue =====================
+  } else {
+    // ===================== epilogue: warps 2..5, warp w owns TMEM lanes 32*(w%4) .. +31 and all column chunks ==========
     const int ew = warp & 3;
-    const int half = (warp - 4) >> 2;
     const int row = ew * 32 + lane;
-    const int et = threadIdx.x - 128;
-    epi_stage_vectors(p.e, s_bias, s_r1w, 0, p.block_n, et);
+    const int et = threadIdx.x - 64;
+    epi_stage_vectors(p.e, s_bias, s_r1w, 0, p.block_n, et, RING_EPI_THREADS);
     int it = 0;
     for (int unit = blockIdx.x; unit < p.total_units; unit += gridDim.x) {
       const int rc = unit % p.chunks;
@@ -281,8 +281,8 @@ __global__ void __launch_bounds__(RING_THREADS, 1) conv_ring_tcgen05_kernel(cons
         if (p.e.row_r1) r1 = __ldg(p.e.row_r1 + m_glob);
         mbar_wait(smem_u32(&bar_tmem_full[acc]), acc_phase);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * TC_MAX_N);
-        epi_store_row(p.e, taddr, half, p.block_n, 0, true, m_glob, rs, r1, s_bias, s_r1w);
+        const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * p.block_n);
+        epi_store_row(p.e, taddr, 0, p.block_n, 0, true, m_glob, rs, r1, s_bias, s_r1w, 1);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty[acc]));
@@ -292,9 +292,9 @@ __global__ void __launch_bounds__(RING_THREADS, 1) conv_ring_tcgen05_kernel(cons
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
   }
 }
 
@@ -316,6 +316,8 @@ static bool ring_plan(const ccvpe_igemm_desc& d, RingParams* p) {
   p->c0 = d.c0;
   p->c1 = d.c1;
   p->block_n = (d.N + 15) / 16 * 16;
+  p->tmem_cols = 32;
+  while (p->tmem_cols < 2 * p->block_n) p->tmem_cols <<= 1;
   p->a_blk0 = round1k(RING_HALO_W * p->kw0 * 2);
   p->a_blk1 = round1k(RING_HALO_W * p->kw1 * 2);
   p->row_bytes = p->nb0 * p->a_blk0 + p->nb1 * p->a_blk1;
@@ -328,6 +330,14 @@ static bool ring_plan(const ccvpe_igemm_desc& d, RingParams* p) {
   if (avail < 4 * p->row_bytes) return false;
   int depth = avail / p->row_bytes;
   p->depth = depth > RING_MAX_DEPTH ? RING_MAX_DEPTH : depth;
+  // prefer a shallower ring if that lets two CTAs (two MMA issuers, two producers, eight epilogue warps) share an SM:
+  // the narrow levels are bound by single-thread issue latency, not by pipeline depth
+  for (int dd = p->depth; dd >= 4; --dd) {
+    if (2 * (9 * p->w_tap_bytes + dd * p->row_bytes + 4096) <= 224 * 1024) {
+      p->depth = dd;
+      break;
+    }
+  }
   p->B = d.B;
   p->H = d.Hout;
   p->W = d.Wout;
@@ -366,8 +376,7 @@ int conv_ring_tcgen05(const ccvpe_igemm_desc& d, cudaStream_t st) {
     if ((rc = encode_map(s ? &p.tm_b1 : &p.tm_b0, d.w_nk, 2, wdims, wstr, wbox, kw)) != CCVPE_OK) return rc;
   }
   fill_epi(p.e, d);
-  int smem = 9 * p.w_tap_bytes + p.depth * p.row_bytes + 1024;
-  if (smem < 120 * 1024) smem = 120 * 1024;   // one CTA per SM: each CTA allocates all 512 TMEM columns
+  const int smem = 9 * p.w_tap_bytes + p.depth * p.row_bytes + 1024;
   static thread_local bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_ring_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -375,7 +384,12 @@ int conv_ring_tcgen05(const ccvpe_igemm_desc& d, cudaStream_t st) {
     if (e != cudaSuccess) return fail(CCVPE_ERR_CUDA, "cudaFuncSetAttribute(ring): %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  const int grid = p.total_units < sm_count() ? p.total_units : sm_count();
+  int ctas_per_sm = (224 * 1024) / (smem + 3072);          // shared memory (+ static) ...
+  if (ctas_per_sm > 512 / p.tmem_cols) ctas_per_sm = 512 / p.tmem_cols;   // ... TMEM columns ...
+  if (ctas_per_sm > 2) ctas_per_sm = 2;                                  // ... registers (launch bounds)
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  const int max_grid = ctas_per_sm * sm_count();
+  const int grid = p.total_units < max_grid ? p.total_units : max_grid;
   conv_ring_tcgen05_kernel<<<grid, RING_THREADS, smem, st>>>(p);
   return check_launch("conv_ring_tcgen05_kernel");
 }

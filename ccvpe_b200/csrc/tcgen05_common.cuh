@@ -129,20 +129,21 @@ struct EpiParams {
 
 // Stages bias / rank-1 vectors of the N tile [n0, n0 + block_n) into shared memory (all TC_EPI_THREADS threads call).
 __device__ __forceinline__ void epi_stage_vectors(const EpiParams& e, float* s_bias, float* s_r1w, int n0, int block_n,
-                                                  int et) {
-  for (int c = et; c < block_n; c += TC_EPI_THREADS) {
+                                                  int et, int epi_threads = TC_EPI_THREADS) {
+  for (int c = et; c < block_n; c += epi_threads) {
     const int n = n0 + c;
     s_bias[c] = (e.bias && n < e.N) ? __ldg(e.bias + n) : 0.f;
     s_r1w[c] = (e.row_r1 && n < e.N) ? __ldg(e.r1_w + n) : 0.f;
   }
-  asm volatile("bar.sync 1, 256;" ::: "memory");
+  asm volatile("bar.sync 1, %0;" ::"r"(epi_threads) : "memory");
 }
 
 // One thread = one accumulator row (output pixel m_glob); `half` selects the interleaved set of 32-column chunks this
 // warp handles.  taddr = TMEM address of (lane group, first column of the accumulator stage).
+// `halves` = number of warps sharing a TMEM lane group (each takes every `halves`-th 32-column chunk, starting at `half`).
 __device__ __forceinline__ void epi_store_row(const EpiParams& e, uint32_t taddr, int half, int block_n, int n0,
                                               bool valid, int m_glob, float rs, float r1, const float* s_bias,
-                                              const float* s_r1w) {
+                                              const float* s_r1w, int halves = 2) {
   const bool has_r1 = (e.row_r1 != nullptr);
   // element offsets of this row's output pixel(s); 4 scalars (not an indexed array: that would live in local memory)
   int64_t px0 = 0, px1 = 0, px2 = 0, px3 = 0, plane0 = 0;
@@ -237,17 +238,17 @@ __device__ __forceinline__ void epi_store_row(const EpiParams& e, uint32_t taddr
 
   // TMEM -> registers, double buffered: the load of the next chunk is in flight while this one is processed
   uint32_t va[32], vb2[32];
-  const int cfirst = half * 32;
+  const int cfirst = half * 32, cstep = 32 * halves;
   if (cfirst < block_n) tmem_ld32(taddr + (uint32_t)cfirst, va);
-  for (int c0 = cfirst; c0 < block_n; c0 += 128) {
+  for (int c0 = cfirst; c0 < block_n; c0 += 2 * cstep) {
     tmem_ld_wait();
-    const bool more1 = (c0 + 64 < block_n);
-    if (more1) tmem_ld32(taddr + (uint32_t)(c0 + 64), vb2);
+    const bool more1 = (c0 + cstep < block_n);
+    if (more1) tmem_ld32(taddr + (uint32_t)(c0 + cstep), vb2);
     process(va, c0);
     if (more1) {
       tmem_ld_wait();
-      if (c0 + 128 < block_n) tmem_ld32(taddr + (uint32_t)(c0 + 128), va);
-      process(vb2, c0 + 64);
+      if (c0 + 2 * cstep < block_n) tmem_ld32(taddr + (uint32_t)(c0 + 2 * cstep), va);
+      process(vb2, c0 + cstep);
     }
   }
 }
