@@ -40,7 +40,7 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm,
       : "memory");
 }
 
-__global__ void __launch_bounds__(RING_THREADS, 2) conv_ring_tcgen05_kernel(const __grid_constant__ RingParams p) {
+__global__ void __launch_bounds__(RING_THREADS, 3) conv_ring_tcgen05_kernel(const __grid_constant__ RingParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[RING_MAX_DEPTH];
   __shared__ __align__(8) uint64_t bar_empty[RING_MAX_DEPTH];
@@ -332,10 +332,14 @@ static bool ring_plan(const ccvpe_igemm_desc& d, RingParams* p) {
   p->depth = depth > RING_MAX_DEPTH ? RING_MAX_DEPTH : depth;
   // prefer a shallower ring if that lets two CTAs (two MMA issuers, two producers, eight epilogue warps) share an SM:
   // the narrow levels are bound by single-thread issue latency, not by pipeline depth
-  for (int dd = p->depth; dd >= 4; --dd) {
-    if (2 * (9 * p->w_tap_bytes + dd * p->row_bytes + 4096) <= 224 * 1024) {
-      p->depth = dd;
-      break;
+  bool placed = false;
+  for (int ctas = 3; ctas >= 2 && !placed; --ctas) {
+    for (int dd = p->depth; dd >= 4; --dd) {
+      if (ctas * (9 * p->w_tap_bytes + dd * p->row_bytes + 4096) <= 224 * 1024) {
+        p->depth = dd;
+        placed = true;
+        break;
+      }
     }
   }
   p->B = d.B;
@@ -386,7 +390,7 @@ int conv_ring_tcgen05(const ccvpe_igemm_desc& d, cudaStream_t st) {
   }
   int ctas_per_sm = (224 * 1024) / (smem + 3072);          // shared memory (+ static) ...
   if (ctas_per_sm > 512 / p.tmem_cols) ctas_per_sm = 512 / p.tmem_cols;   // ... TMEM columns ...
-  if (ctas_per_sm > 2) ctas_per_sm = 2;                                  // ... registers (launch bounds)
+  if (ctas_per_sm > 3) ctas_per_sm = 3;                                  // ... registers (launch bounds: 96 regs)
   if (ctas_per_sm < 1) ctas_per_sm = 1;
   const int max_grid = ctas_per_sm * sm_count();
   const int grid = p.total_units < max_grid ? p.total_units : max_grid;

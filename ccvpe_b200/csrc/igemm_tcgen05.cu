@@ -16,13 +16,16 @@
 
 namespace ccvpe {
 
-constexpr int TC_THREADS = 384;      // 4 control warps + 8 epilogue warps
+// warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2.. = epilogue.  Two instantiations: 8 epilogue warps
+// (one fat CTA per SM, wide compute-bound tiles) and 4 epilogue warps (192 threads; two CTAs share an SM, which doubles
+// the single-thread issue capacity the narrow HBM-bound layers are limited by).
 constexpr int TC_MAX_STAGES = 16;
 constexpr int TC_SMEM_BUDGET = 200 * 1024;
 
 struct TcParams {
   CUtensorMap tm_a0, tm_a1, tm_b0, tm_b1;
   int nb0, nb1, c0, c1, kw0, kw1, kpad0, kpad1, taps, n_tiles_n, total_tiles, block_n, stages, a_bytes, stage_bytes;
+  int tmem_cols;
   int tiles[4], box[4];
   int tap_off[9][4];
   int out_stride[4], extent[4];
@@ -30,7 +33,10 @@ struct TcParams {
 };
 
 // ---- kernel ------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TC_THREADS, 1) igemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
+template <int EPI_WARPS>
+__global__ void __launch_bounds__(64 + 32 * EPI_WARPS, EPI_WARPS == 4 ? 2 : 1)
+igemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
+  constexpr int EPI_THREADS = 32 * EPI_WARPS;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[TC_MAX_STAGES];
   __shared__ __align__(8) uint64_t bar_empty[TC_MAX_STAGES];
@@ -53,7 +59,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) igemm_tcgen05_kernel(const __gr
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&bar_tmem_full[a]), 1);
-      mbar_init(smem_u32(&bar_tmem_empty[a]), TC_EPI_THREADS / 32);
+      mbar_init(smem_u32(&bar_tmem_empty[a]), EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -65,9 +71,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) igemm_tcgen05_kernel(const __gr
       prefetch_tmap(&p.tm_b1);
     }
   }
-  if (warp == 2) {
+  if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
-                 "r"(512)
+                 "r"(p.tmem_cols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -142,7 +148,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) igemm_tcgen05_kernel(const __gr
         const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
         mbar_wait(smem_u32(&bar_tmem_empty[acc]), acc_phase ^ 1u);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * TC_MAX_N);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.block_n);
         uint32_t accumulate = 0;
         for (int tap = 0; tap < p.taps; ++tap) {
 #pragma unroll 1
@@ -179,12 +185,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) igemm_tcgen05_kernel(const __gr
         __syncwarp();
       }
     }
-  } else if (warp >= 4) {
+  } else {
     // ===== epilogue: 8 warps; warp w reads TMEM lanes 32*(w%4) .. +31 and every other 32-column chunk ((w-4)/4) =====
     const int ew = warp & 3;
-    const int half = (warp - 4) >> 2;                 // which interleaved set of 32-column chunks
+    const int half = (warp - 2) >> 2;                 // which interleaved set of 32-column chunks
     const int row = ew * 32 + lane;
-    const int et = threadIdx.x - 128;                 // 0..255 within the epilogue group
+    const int et = threadIdx.x - 64;                  // index within the epilogue group
     const bool fixed_n = (p.n_tiles_n == 1);
     const bool has_r1 = (p.e.row_r1 != nullptr), has_rs = (p.e.row_scale != nullptr);
     // row -> output pixel of a tile
@@ -203,7 +209,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) igemm_tcgen05_kernel(const __gr
       }
     };
 
-    if (fixed_n) epi_stage_vectors(p.e, s_bias[0], s_r1w[0], 0, p.block_n, et);
+    if (fixed_n) epi_stage_vectors(p.e, s_bias[0], s_r1w[0], 0, p.block_n, et, EPI_THREADS);
     int m_glob, m_next = 0;
     bool valid, valid_next = false;
     float rs = 1.f, r1 = 0.f, rs_next = 1.f, r1_next = 0.f;
@@ -233,11 +239,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) igemm_tcgen05_kernel(const __gr
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       const int vb = fixed_n ? 0 : acc;
-      if (!fixed_n) epi_stage_vectors(p.e, s_bias[acc], s_r1w[acc], n0, p.block_n, et);
+      if (!fixed_n) epi_stage_vectors(p.e, s_bias[acc], s_r1w[acc], n0, p.block_n, et, EPI_THREADS);
       mbar_wait(smem_u32(&bar_tmem_full[acc]), acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * TC_MAX_N);
-      epi_store_row(p.e, taddr, half, p.block_n, n0, valid, m_glob, rs, r1, s_bias[vb], s_r1w[vb]);
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * p.block_n);
+      epi_store_row(p.e, taddr, half, p.block_n, n0, valid, m_glob, rs, r1, s_bias[vb], s_r1w[vb], EPI_WARPS / 4);
       // release the accumulator stage back to the MMA issuer
       tc_fence_before();
       __syncwarp();
@@ -247,9 +253,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) igemm_tcgen05_kernel(const __gr
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
   }
 }
 
@@ -316,7 +322,14 @@ int igemm_tcgen05(const ccvpe_igemm_desc& d, cudaStream_t st) {
   p.a_bytes = TC_BM * kw_max * 2;                                   // multiple of 1024 for every kw
   const int stage_bytes = p.a_bytes + (block_n * kw_max * 2 + 1023) / 1024 * 1024;
   p.stage_bytes = stage_bytes;
-  int stages = TC_SMEM_BUDGET / stage_bytes;
+  p.tmem_cols = 32;
+  while (p.tmem_cols < 2 * block_n) p.tmem_cols <<= 1;
+  // narrow tiles (<= 128 accumulator columns): small CTAs, two per SM; wide tiles: one fat CTA per SM
+  int light_ctas = 0;                       // CTAs per SM in the light configuration (0 = heavy)
+  // (three CTAs would need <= 112 registers/thread: measured slower, the epilogue spills)
+  if (p.tmem_cols <= 256 && (104 * 1024) / stage_bytes >= 3) light_ctas = 2;
+  const bool light = light_ctas > 0;
+  int stages = (light_ctas == 3 ? 68 * 1024 : (light_ctas == 2 ? 104 * 1024 : TC_SMEM_BUDGET)) / stage_bytes;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   p.stages = stages;
   const int64_t ktot = (int64_t)p.taps * (p.kpad0 + p.kpad1);
@@ -375,14 +388,20 @@ int igemm_tcgen05(const ccvpe_igemm_desc& d, cudaStream_t st) {
   fill_epi(p.e, d);
 
   const int smem = stages * stage_bytes + 1024;
-  static thread_local int smem_attr_set = 0;
-  if (smem_attr_set < smem) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8192);
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_tcgen05_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8192);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(igemm_tcgen05_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8192);
     if (e != cudaSuccess) return fail(CCVPE_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    smem_attr_set = 227 * 1024;
+    attr_set = true;
   }
-  int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
-  igemm_tcgen05_kernel<<<grid, TC_THREADS, smem, st>>>(p);
+  const int max_grid = (light ? light_ctas : 1) * sm_count();
+  const int grid = p.total_tiles < max_grid ? p.total_tiles : max_grid;
+  if (light)
+    igemm_tcgen05_kernel<4><<<grid, 64 + 32 * 4, smem, st>>>(p);
+  else
+    igemm_tcgen05_kernel<8><<<grid, 64 + 32 * 8, smem, st>>>(p);
   return check_launch("igemm_tcgen05_kernel");
 }
 
