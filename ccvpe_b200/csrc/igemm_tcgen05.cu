@@ -25,7 +25,7 @@ constexpr int TC_SMEM_BUDGET = 200 * 1024;
 struct TcParams {
   CUtensorMap tm_a0, tm_a1, tm_b0, tm_b1;
   int nb0, nb1, c0, c1, kw0, kw1, kpad0, kpad1, taps, n_tiles_n, total_tiles, block_n, stages, a_bytes, stage_bytes;
-  int tmem_cols;
+  int tmem_cols, a_rank;      // a_rank: rank of the A tensor maps (2 = flattened pixels, 4 = [C,W,H,B], 5 = cell gather)
   int tiles[4], box[4];
   int tap_off[9][4];
   int out_stride[4], extent[4];
@@ -113,7 +113,10 @@ igemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
                 const uint32_t full = smem_u32(&bar_full[stage]);
                 const uint32_t a_dst = smem_base + stage * stage_bytes;
                 mbar_arrive_expect_tx(full, tx);
-                tma_load_5d(a_dst, tm, full, cb * kw, c1, c2, c3, c4);
+                // lowest-rank map that expresses the access: TMA issue cost grows with rank (scripts/tma_probe.cu)
+                if (p.a_rank == 2) tma_load_2d(a_dst, tm, full, cb * kw, c1);
+                else if (p.a_rank == 4) tma_load_4d(a_dst, tm, full, cb * kw, c1, c2, c3);
+                else tma_load_5d(a_dst, tm, full, cb * kw, c1, c2, c3, c4);
                 tma_load_2d(a_dst + p.a_bytes, tmb, full, kbase + cb * kw, n0);
               }
               __syncwarp();
@@ -275,6 +278,12 @@ static bool tc_geometry(const ccvpe_igemm_desc& d, TcGeometry* g) {
   }
   if (d.stride != 1 || d.kh != d.kw || !(d.kh == 1 || d.kh == 3) || d.pad != (d.kh - 1) / 2) return false;
   if (d.Hin != d.Hout || d.Win != d.Wout) return false;
+  if (d.kh == 1) {   // 1x1: flattened pixel tiles, any spatial size
+    g->cell = false;
+    g->tw = TC_BM;
+    g->th = g->tb = 1;
+    return true;
+  }
   if (!is_pow2(d.Wout) || !is_pow2(d.Hout)) return false;
   int tw = d.Wout < TC_BM ? d.Wout : TC_BM;
   int th = TC_BM / tw;
@@ -343,6 +352,7 @@ int igemm_tcgen05(const ccvpe_igemm_desc& d, cudaStream_t st) {
                        2ull * d.Win * d.ld0 * esz};
     uint32_t box[5] = {(uint32_t)p.kw0, 1, 8, 1, 16};
     if ((rc = encode_map(&p.tm_a0, d.a0, 5, dims, str, box, p.kw0)) != CCVPE_OK) return rc;
+    p.a_rank = 5;
     p.tiles[0] = 1; p.tiles[1] = 1; p.tiles[2] = 1; p.tiles[3] = (8 * d.B + 15) / 16;
     p.box[0] = 1; p.box[1] = 8; p.box[2] = 1; p.box[3] = 16;
     for (int t = 0; t < 4; ++t) {
@@ -353,17 +363,35 @@ int igemm_tcgen05(const ccvpe_igemm_desc& d, cudaStream_t st) {
     }
     p.out_stride[0] = 0; p.out_stride[1] = 1; p.out_stride[2] = 0; p.out_stride[3] = 8;
     p.extent[0] = 1 << 30; p.extent[1] = 8; p.extent[2] = 1 << 30; p.extent[3] = 8 * d.B;
-  } else {
+  } else if (d.kh == 1) {
+    // 1x1 (transposed convs): the M axis is just the flattened pixel index -> 2-D maps, 128 consecutive pixels per tile
+    const int64_t M = (int64_t)d.B * d.Hout * d.Wout;
     for (int s = 0; s < 2; ++s) {
       const void* base = s ? d.a1 : d.a0;
       const int c = s ? d.c1 : d.c0, ld = s ? d.ld1 : d.ld0;
       if (!c) continue;
-      uint64_t dims[5] = {(uint64_t)c, (uint64_t)d.Win, (uint64_t)d.Hin, (uint64_t)d.B, 1};
-      uint64_t str[4] = {(uint64_t)ld * esz, (uint64_t)d.Win * ld * esz, (uint64_t)d.Hin * d.Win * ld * esz,
-                         (uint64_t)d.B * d.Hin * d.Win * ld * esz};
       const int kw = s ? p.kw1 : p.kw0;
-      uint32_t box[5] = {(uint32_t)kw, (uint32_t)g.tw, (uint32_t)g.th, (uint32_t)g.tb, 1};
-      if ((rc = encode_map(s ? &p.tm_a1 : &p.tm_a0, base, 5, dims, str, box, kw)) != CCVPE_OK) return rc;
+      uint64_t dims[2] = {(uint64_t)c, (uint64_t)M};
+      uint64_t str[1] = {(uint64_t)ld * esz};
+      uint32_t box[2] = {(uint32_t)kw, TC_BM};
+      if ((rc = encode_map(s ? &p.tm_a1 : &p.tm_a0, base, 2, dims, str, box, kw)) != CCVPE_OK) return rc;
+    }
+    p.a_rank = 2;
+    p.tiles[0] = (int)((M + TC_BM - 1) / TC_BM); p.tiles[1] = p.tiles[2] = p.tiles[3] = 1;
+    p.box[0] = TC_BM; p.box[1] = p.box[2] = p.box[3] = 1;
+    p.out_stride[0] = 1; p.out_stride[1] = p.out_stride[2] = p.out_stride[3] = 0;
+    p.extent[0] = (int)M; p.extent[1] = p.extent[2] = p.extent[3] = 1;
+  } else {
+    p.a_rank = 4;
+    for (int s = 0; s < 2; ++s) {
+      const void* base = s ? d.a1 : d.a0;
+      const int c = s ? d.c1 : d.c0, ld = s ? d.ld1 : d.ld0;
+      if (!c) continue;
+      uint64_t dims[4] = {(uint64_t)c, (uint64_t)d.Win, (uint64_t)d.Hin, (uint64_t)d.B};
+      uint64_t str[3] = {(uint64_t)ld * esz, (uint64_t)d.Win * ld * esz, (uint64_t)d.Hin * d.Win * ld * esz};
+      const int kw = s ? p.kw1 : p.kw0;
+      uint32_t box[4] = {(uint32_t)kw, (uint32_t)g.tw, (uint32_t)g.th, (uint32_t)g.tb};
+      if ((rc = encode_map(s ? &p.tm_a1 : &p.tm_a0, base, 4, dims, str, box, kw)) != CCVPE_OK) return rc;
     }
     p.tiles[0] = d.Wout / g.tw; p.tiles[1] = d.Hout / g.th; p.tiles[2] = (d.B + g.tb - 1) / g.tb; p.tiles[3] = 1;
     p.box[0] = g.tw; p.box[1] = g.th; p.box[2] = g.tb; p.box[3] = 1;

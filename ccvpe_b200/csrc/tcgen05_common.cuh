@@ -65,6 +65,13 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm,
       ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
@@ -300,7 +307,7 @@ inline int encode_map(CUtensorMap* tm, const void* base, int rank, const uint64_
 // K-block width (bf16 channels) used for a source with c channels; one block is one swizzle row of 2*width bytes.
 // Narrow sources get narrow blocks so TMA neither over-fetches nor zero-fills most of the tile (include/ccvpe_b200.h
 // documents the same rule for the w_nk weight layout).
-inline int tc_block_width(int c) { return c <= 16 ? 16 : (c < 96 ? 32 : 64); }
+inline int tc_block_width(int c) { return c <= 16 ? 16 : (c < 64 ? 32 : 64); }
 
 inline void fill_epi(EpiParams& e, const ccvpe_igemm_desc& d) {
   e.N = d.N;

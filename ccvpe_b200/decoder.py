@@ -109,7 +109,7 @@ class PostEncoderPipeline:
         def nk(per_tap_rows: torch.Tensor, splits: Sequence[int]) -> torch.Tensor:
             """[N, taps, K] -> [N, taps, sum(pad64(split))] bf16 with every source K range zero padded to its K-block width (see ccvpe_b200.h)."""
             N_, taps, _ = per_tap_rows.shape
-            pads = [-(-c // kw) * kw for c, kw in ((c, 16 if c <= 16 else (32 if c < 96 else 64)) for c in splits)]
+            pads = [-(-c // kw) * kw for c, kw in ((c, 16 if c <= 16 else (32 if c < 64 else 64)) for c in splits)]
             out = torch.zeros((N_, taps, sum(pads)), dtype=torch.bfloat16, device=per_tap_rows.device)
             src = dst = 0
             for c, cp in zip(splits, pads):

@@ -91,7 +91,7 @@ typedef struct ccvpe_igemm_desc {
   /* weights, one of (depending on backend):
    *   w_kn : [taps][c0 + c1][N]                     (N contiguous)       -- SIMT backend
    *   w_nk : [N][taps][pad(c0) + pad(c1)]           (K contiguous, bf16) -- tcgen05 backend; pad(c) rounds c up to
-   *          a multiple of the source's K-block width kw(c) = 16 if c <= 16, 32 if c < 96, else 64 (zero filled)   */
+   *          a multiple of the source's K-block width kw(c) = 16 if c <= 16, 32 if c < 64, else 64 (zero filled)   */
   const void* w_kn; const void* w_nk;
   const float* bias;             /* [N] fp32 or NULL                                                                */
   const float* row_scale;        /* [M] fp32 or NULL                                                                */

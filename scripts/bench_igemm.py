@@ -14,7 +14,7 @@ from ccvpe_b200 import cabi  # noqa: E402
 
 def nk(rows, splits):
     N_, taps, _ = rows.shape
-    pads = [-(-c // kw) * kw for c, kw in ((c, 16 if c <= 16 else (32 if c < 96 else 64)) for c in splits)]
+    pads = [-(-c // kw) * kw for c, kw in ((c, 16 if c <= 16 else (32 if c < 64 else 64)) for c in splits)]
     out = torch.zeros((N_, taps, sum(pads)), dtype=torch.bfloat16, device=rows.device)
     src = dst = 0
     for c, cp in zip(splits, pads):

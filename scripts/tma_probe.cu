@@ -16,6 +16,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void tma5(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
   asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3,%4,%5,%6,%7}], [%2];" ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
 }
+__device__ __forceinline__ void tma3(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3,%4,%5}], [%2];" ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void tma2(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3,%4}], [%2];" ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
@@ -42,6 +45,9 @@ __global__ void probe(const __grid_constant__ CUtensorMap tm, int mode, int box_
         if (mode == 0) {
           int xs = tile % (W / 128), y = (tile / (W / 128)) % H, b = tile / ((W / 128) * H);
           tma5(base + s * 16384, &tm, smem_u32(&bar[s]), 0, xs * 128, y, b, 0);
+        } else if (mode == 2) {
+          int xs = tile % (W / 128), yb = tile / (W / 128);
+          tma3(base + s * 16384, &tm, smem_u32(&bar[s]), 0, xs * 128, yb);
         } else {
           tma2(base + s * 16384, &tm, smem_u32(&bar[s]), 0, tile * 128);
         }
@@ -62,7 +68,7 @@ int main() {
   long long* out; cudaMalloc(&out, sms * sizeof(long long));
   cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGES * 16384 + 2048);
   int chans[] = {16, 32, 40, 64, 128};
-  for (int ci = 0; ci < 5; ++ci) for (int mode = 0; mode < 2; ++mode) {
+  for (int ci = 0; ci < 5; ++ci) for (int mode = 0; mode < 3; ++mode) {
     int C = chans[ci];
     int kw = C <= 16 ? 16 : (C < 96 ? 32 : 64);
     void* x; size_t n = (size_t)B * H * W * C * 2; cudaMalloc(&x, n); cudaMemset(x, 0, n);
@@ -74,6 +80,11 @@ int main() {
       cuuint64_t str[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2, (cuuint64_t)B * H * W * C * 2};
       cuuint32_t box[5] = {(cuuint32_t)kw, 128, 1, 1, 1}, es[5] = {1, 1, 1, 1, 1};
       r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, x, dims, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else if (mode == 2) {
+      cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)B * H};
+      cuuint64_t str[2] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2};
+      cuuint32_t box[3] = {(cuuint32_t)kw, 128, 1}, es[3] = {1, 1, 1};
+      r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, x, dims, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     } else {
       cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)B * H * W};
       cuuint64_t str[1] = {(cuuint64_t)C * 2};
@@ -87,7 +98,7 @@ int main() {
     if (e != cudaSuccess) { printf("kernel failed: %s\n", cudaGetErrorString(e)); return 1; }
     long long h[148]; cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
     double avg = 0; for (int i = 0; i < sms; ++i) avg += h[i]; avg /= sms;
-    printf("C=%3d kw=%2d mode=%s box=%5d B : %.0f cycles/load  (%.1f B/cycle/SM useful, 148 SMs concurrently)\n", C, kw, mode ? "2D" : "5D", box_bytes, avg / iters, box_bytes / (avg / iters));
+    printf("C=%3d kw=%2d mode=%s box=%5d B : %.0f cycles/load  (%.1f B/cycle/SM useful, 148 SMs concurrently)\n", C, kw, mode == 0 ? "5D" : (mode == 1 ? "2D" : "3D"), box_bytes, avg / iters, box_bytes / (avg / iters));
     cudaFree(x);
   }
   return 0;

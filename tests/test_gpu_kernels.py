@@ -59,7 +59,7 @@ def test_grd_descriptor(cuda_device, B, H, W, c, layout, dtype):
 def _nk(rows, splits):
     """[N, taps, K] -> tcgen05 weight layout [N, taps, sum(pad64(split))] bf16 (see include/ccvpe_b200.h)."""
     N_, taps, _ = rows.shape
-    pads = [-(-c // kw) * kw for c, kw in ((c, 16 if c <= 16 else (32 if c < 96 else 64)) for c in splits)]
+    pads = [-(-c // kw) * kw for c, kw in ((c, 16 if c <= 16 else (32 if c < 64 else 64)) for c in splits)]
     out = torch.zeros((N_, taps, sum(pads)), dtype=torch.bfloat16)
     src = dst = 0
     for c, cp in zip(splits, pads):
