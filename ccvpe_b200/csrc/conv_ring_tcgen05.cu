@@ -40,6 +40,7 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm,
       : "memory");
 }
 
+template <int MODE, bool HAS_R1, bool OUT_F32>
 __global__ void __launch_bounds__(RING_THREADS, 3) conv_ring_tcgen05_kernel(const __grid_constant__ RingParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[RING_MAX_DEPTH];
@@ -282,7 +283,7 @@ __global__ void __launch_bounds__(RING_THREADS, 3) conv_ring_tcgen05_kernel(cons
         mbar_wait(smem_u32(&bar_tmem_full[acc]), acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * p.block_n);
-        epi_store_row(p.e, taddr, 0, p.block_n, 0, true, m_glob, rs, r1, s_bias, s_r1w, 1);
+        epi_store_row<MODE, HAS_R1, OUT_F32>(p.e, taddr, 0, p.block_n, 0, true, m_glob, rs, r1, s_bias, s_r1w, 1);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty[acc]));
@@ -381,20 +382,26 @@ int conv_ring_tcgen05(const ccvpe_igemm_desc& d, cudaStream_t st) {
   }
   fill_epi(p.e, d);
   const int smem = 9 * p.w_tap_bytes + p.depth * p.row_bytes + 1024;
-  static thread_local bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_ring_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         RING_SMEM_BUDGET + 2048);
-    if (e != cudaSuccess) return fail(CCVPE_ERR_CUDA, "cudaFuncSetAttribute(ring): %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
   int ctas_per_sm = (224 * 1024) / (smem + 3072);          // shared memory (+ static) ...
   if (ctas_per_sm > 512 / p.tmem_cols) ctas_per_sm = 512 / p.tmem_cols;   // ... TMEM columns ...
   if (ctas_per_sm > 3) ctas_per_sm = 3;                                  // ... registers (launch bounds: 96 regs)
   if (ctas_per_sm < 1) ctas_per_sm = 1;
   const int max_grid = ctas_per_sm * sm_count();
   const int grid = p.total_units < max_grid ? p.total_units : max_grid;
-  conv_ring_tcgen05_kernel<<<grid, RING_THREADS, smem, st>>>(p);
+  cudaError_t attr_err = cudaSuccess;
+#define CCVPE_LAUNCH_RING(MODE, R1, F32)                                                                         \
+  do {                                                                                                           \
+    static thread_local bool attr = false;                                                                       \
+    if (!attr) {                                                                                                 \
+      attr_err = cudaFuncSetAttribute(conv_ring_tcgen05_kernel<MODE, R1, F32>,                                   \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, RING_SMEM_BUDGET + 2048);     \
+      attr = true;                                                                                               \
+    }                                                                                                            \
+    conv_ring_tcgen05_kernel<MODE, R1, F32><<<grid, RING_THREADS, smem, st>>>(p);                                 \
+  } while (0)
+  CCVPE_EPI_SWITCH(epi_variant(p.e), CCVPE_LAUNCH_RING)
+#undef CCVPE_LAUNCH_RING
+  if (attr_err != cudaSuccess) return fail(CCVPE_ERR_CUDA, "cudaFuncSetAttribute(ring): %s", cudaGetErrorString(attr_err));
   return check_launch("conv_ring_tcgen05_kernel");
 }
 

@@ -33,7 +33,7 @@ struct TcParams {
 };
 
 // ---- kernel ------------------------------------------------------------------------------------------------------
-template <int EPI_WARPS>
+template <int EPI_WARPS, int MODE, bool HAS_R1, bool OUT_F32>
 __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, EPI_WARPS == 4 ? 2 : 1)
 igemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
   constexpr int EPI_THREADS = 32 * EPI_WARPS;
@@ -246,7 +246,8 @@ igemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
       mbar_wait(smem_u32(&bar_tmem_full[acc]), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * p.block_n);
-      epi_store_row(p.e, taddr, half, p.block_n, n0, valid, m_glob, rs, r1, s_bias[vb], s_r1w[vb], EPI_WARPS / 4);
+      epi_store_row<MODE, HAS_R1, OUT_F32>(p.e, taddr, half, p.block_n, n0, valid, m_glob, rs, r1, s_bias[vb], s_r1w[vb],
+                                           EPI_WARPS / 4);
       // release the accumulator stage back to the MMA issuer
       tc_fence_before();
       __syncwarp();
@@ -323,7 +324,9 @@ int igemm_tcgen05(const ccvpe_igemm_desc& d, cudaStream_t st) {
   p.c0 = d.c0;
   p.c1 = d.c1;
   p.taps = d.kh * d.kw;
-  const int n_tiles_n = (d.N + TC_MAX_N - 1) / TC_MAX_N;
+  // shallow-K layers are HBM / issue bound, not tensor bound: keep their tiles <= 128 columns so that two CTAs fit an SM
+  const int max_n = (p.taps * (d.c0 + d.c1) <= 256) ? 128 : TC_MAX_N;
+  const int n_tiles_n = (d.N + max_n - 1) / max_n;
   int block_n = ((d.N + n_tiles_n - 1) / n_tiles_n + 15) / 16 * 16;
   p.n_tiles_n = n_tiles_n;
   p.block_n = block_n;
@@ -416,20 +419,31 @@ int igemm_tcgen05(const ccvpe_igemm_desc& d, cudaStream_t st) {
   fill_epi(p.e, d);
 
   const int smem = stages * stage_bytes + 1024;
-  static thread_local bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_tcgen05_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8192);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(igemm_tcgen05_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8192);
-    if (e != cudaSuccess) return fail(CCVPE_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
   const int max_grid = (light ? light_ctas : 1) * sm_count();
   const int grid = p.total_tiles < max_grid ? p.total_tiles : max_grid;
-  if (light)
-    igemm_tcgen05_kernel<4><<<grid, 64 + 32 * 4, smem, st>>>(p);
-  else
-    igemm_tcgen05_kernel<8><<<grid, 64 + 32 * 8, smem, st>>>(p);
+  cudaError_t attr_err = cudaSuccess;
+#define CCVPE_LAUNCH_IGEMM(MODE, R1, F32)                                                                              \
+  do {                                                                                                                 \
+    static thread_local bool attr4 = false, attr8 = false;                                                             \
+    if (light) {                                                                                                       \
+      if (!attr4) {                                                                                                    \
+        attr_err = cudaFuncSetAttribute(igemm_tcgen05_kernel<4, MODE, R1, F32>,                                        \
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8192);               \
+        attr4 = true;                                                                                                  \
+      }                                                                                                                \
+      igemm_tcgen05_kernel<4, MODE, R1, F32><<<grid, 64 + 32 * 4, smem, st>>>(p);                                       \
+    } else {                                                                                                           \
+      if (!attr8) {                                                                                                    \
+        attr_err = cudaFuncSetAttribute(igemm_tcgen05_kernel<8, MODE, R1, F32>,                                        \
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8192);               \
+        attr8 = true;                                                                                                  \
+      }                                                                                                                \
+      igemm_tcgen05_kernel<8, MODE, R1, F32><<<grid, 64 + 32 * 8, smem, st>>>(p);                                       \
+    }                                                                                                                  \
+  } while (0)
+  CCVPE_EPI_SWITCH(epi_variant(p.e), CCVPE_LAUNCH_IGEMM)
+#undef CCVPE_LAUNCH_IGEMM
+  if (attr_err != cudaSuccess) return fail(CCVPE_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
   return check_launch("igemm_tcgen05_kernel");
 }
 

@@ -145,21 +145,22 @@ __device__ __forceinline__ void epi_stage_vectors(const EpiParams& e, float* s_b
   asm volatile("bar.sync 1, %0;" ::"r"(epi_threads) : "memory");
 }
 
-// One thread = one accumulator row (output pixel m_glob); `half` selects the interleaved set of 32-column chunks this
-// warp handles.  taddr = TMEM address of (lane group, first column of the accumulator stage).
-// `halves` = number of warps sharing a TMEM lane group (each takes every `halves`-th 32-column chunk, starting at `half`).
+// One thread = one accumulator row (output pixel m_glob).  `halves` = number of warps sharing a TMEM lane group (each takes
+// every `halves`-th 32-column chunk, starting at `half`).  taddr = TMEM address of (lane group, first column of the stage).
+// Specialised at compile time on (output mode, rank-1 term, fp32 output): the kernels are instantiated once per
+// variant, so the per-column code carries no runtime branches (the epilogue is the bottleneck of the HBM-bound levels).
+template <int MODE, bool HAS_R1, bool OUT_F32>
 __device__ __forceinline__ void epi_store_row(const EpiParams& e, uint32_t taddr, int half, int block_n, int n0,
                                               bool valid, int m_glob, float rs, float r1, const float* s_bias,
-                                              const float* s_r1w, int halves = 2) {
-  const bool has_r1 = (e.row_r1 != nullptr);
-  // element offsets of this row's output pixel(s); 4 scalars (not an indexed array: that would live in local memory)
+                                              const float* s_r1w, int halves) {
+  // element offsets of this row's output pixel(s); scalars, not an indexed array (that would live in local memory)
   int64_t px0 = 0, px1 = 0, px2 = 0, px3 = 0, plane0 = 0;
-  if (e.out_mode == 0) {
+  if (MODE == 0) {
     px0 = (int64_t)m_glob * e.ldo;
   } else {
     const int b_img = m_glob / e.HWo;
     const int hw = m_glob - b_img * e.HWo;
-    if (e.out_mode == 2) {
+    if (MODE == 2) {
       plane0 = (int64_t)b_img * e.N * e.HWo + hw;
     } else {
       const int h = hw / e.Wout, w = hw - h * e.Wout;
@@ -170,12 +171,15 @@ __device__ __forceinline__ void epi_store_row(const EpiParams& e, uint32_t taddr
       px3 = px2 + e.ldo;                                                               // (1, 1)
     }
   }
-  const int cout = e.out_mode == 1 ? (e.N >> 2) : e.N;
+  const int cout = MODE == 1 ? (e.N >> 2) : e.N;
+  const int N = e.N;
+  const float lower = e.relu ? 0.f : -INFINITY;          // branch-free ReLU
+  const bool vec_ok = OUT_F32 ? ((e.ldo & 3) == 0) : ((e.ldo & 7) == 0);
 
   auto process = [&](const uint32_t (&v)[32], int c0) {
     if (!valid) return;
     int ij = 0, co = n0 + c0;                // (quadrant, channel) of the chunk's first column
-    if (e.out_mode == 1) {
+    if (MODE == 1) {
       ij = co / cout;
       co -= ij * cout;
     }
@@ -183,11 +187,11 @@ __device__ __forceinline__ void epi_store_row(const EpiParams& e, uint32_t taddr
     for (int g8 = 0; g8 < 4; ++g8) {
       const int cl = c0 + g8 * 8;             // column within the tile
       const int n = n0 + cl;
-      if (n >= e.N || cl >= block_n) break;
+      if (n >= N || cl >= block_n) break;
       const float4 b0 = *reinterpret_cast<const float4*>(&s_bias[cl]);
       const float4 b1 = *reinterpret_cast<const float4*>(&s_bias[cl + 4]);
       float y[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-      if (has_r1) {
+      if (HAS_R1) {
         const float4 w0 = *reinterpret_cast<const float4*>(&s_r1w[cl]);
         const float4 w1 = *reinterpret_cast<const float4*>(&s_r1w[cl + 4]);
         const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
@@ -195,32 +199,29 @@ __device__ __forceinline__ void epi_store_row(const EpiParams& e, uint32_t taddr
         for (int j = 0; j < 8; ++j) y[j] = fmaf(r1, wv[j], y[j]);
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        y[j] = fmaf(__uint_as_float(v[g8 * 8 + j]), rs, y[j]);
-        if (e.relu) y[j] = fmaxf(y[j], 0.f);
-      }
-      if (e.out_mode == 2) {
+      for (int j = 0; j < 8; ++j) y[j] = fmaxf(fmaf(__uint_as_float(v[g8 * 8 + j]), rs, y[j]), lower);
+      if (MODE == 2) {
         float* o = static_cast<float*>(e.out) + plane0;
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          if (n + j < e.N) o[(int64_t)(n + j) * e.HWo] = y[j];
+          if (n + j < N) o[(int64_t)(n + j) * e.HWo] = y[j];
         continue;
       }
-      const int64_t off = (ij == 0 ? px0 : (ij == 1 ? px1 : (ij == 2 ? px2 : px3))) + co;
-      const bool full8 = (n + 8 <= e.N);
-      if (e.out_f32) {
+      const int64_t off = (MODE == 0 ? px0 : (ij == 0 ? px0 : (ij == 1 ? px1 : (ij == 2 ? px2 : px3)))) + co;
+      const bool full8 = (n + 8 <= N) && vec_ok;
+      if (OUT_F32) {
         float* o = static_cast<float*>(e.out) + off;
-        if (full8 && (e.ldo & 3) == 0) {
+        if (full8) {
           *reinterpret_cast<float4*>(o) = make_float4(y[0], y[1], y[2], y[3]);
           *reinterpret_cast<float4*>(o + 4) = make_float4(y[4], y[5], y[6], y[7]);
         } else {
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            if (n + j < e.N) o[j] = y[j];
+            if (n + j < N) o[j] = y[j];
         }
       } else {
         __nv_bfloat16* o = static_cast<__nv_bfloat16*>(e.out) + off;
-        if (full8 && (e.ldo & 7) == 0) {
+        if (full8) {
           __nv_bfloat162 q0 = __floats2bfloat162_rn(y[0], y[1]), q1 = __floats2bfloat162_rn(y[2], y[3]);
           __nv_bfloat162 q2 = __floats2bfloat162_rn(y[4], y[5]), q3 = __floats2bfloat162_rn(y[6], y[7]);
           uint4 pk;
@@ -232,11 +233,11 @@ __device__ __forceinline__ void epi_store_row(const EpiParams& e, uint32_t taddr
         } else {
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            if (n + j < e.N) o[j] = __float2bfloat16_rn(y[j]);
+            if (n + j < N) o[j] = __float2bfloat16_rn(y[j]);
         }
       }
       co += 8;
-      if (e.out_mode == 1 && co >= cout) {
+      if (MODE == 1 && co >= cout) {
         co -= cout;
         ++ij;
       }
@@ -259,6 +260,24 @@ __device__ __forceinline__ void epi_store_row(const EpiParams& e, uint32_t taddr
     }
   }
 }
+
+// Epilogue variant of a descriptor: 0 conv bf16 | 1 conv bf16 + rank-1 | 2 conv fp32 channels-last | 3 planar fp32 |
+// 4 pixel-shuffle bf16 | 5 pixel-shuffle bf16 + rank-1.  CCVPE_EPI_SWITCH expands `X(MODE, HAS_R1, OUT_F32)` for it.
+inline int epi_variant(const EpiParams& e) {
+  if (e.out_mode == 1) return e.row_r1 ? 5 : 4;
+  if (e.out_mode == 2) return 3;
+  if (e.out_f32) return 2;
+  return e.row_r1 ? 1 : 0;
+}
+#define CCVPE_EPI_SWITCH(variant, X) \
+  switch (variant) {                 \
+    case 0: X(0, false, false); break; \
+    case 1: X(0, true, false); break;  \
+    case 2: X(0, false, true); break;  \
+    case 3: X(2, false, true); break;  \
+    case 4: X(1, false, false); break; \
+    default: X(1, true, false); break; \
+  }
 
 // ---- host side ---------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
