@@ -20,7 +20,7 @@ EXPORTED_SYMBOLS = (
     "ccvpe_abi_version", "ccvpe_last_error", "ccvpe_launch_count", "ccvpe_reset_launch_count",
     "ccvpe_grd_descriptor", "ccvpe_grd_descriptors", "ccvpe_igemm", "ccvpe_igemm_plan", "ccvpe_match_scratch_elems", "ccvpe_match_level",
     "ccvpe_softmax_scratch_elems", "ccvpe_softmax_heatmap", "ccvpe_ori_normalize",
-    "ccvpe_pose_scratch_bytes", "ccvpe_pose_decode", "ccvpe_bias_silu_nhwc",
+    "ccvpe_pose_scratch_bytes", "ccvpe_pose_decode", "ccvpe_bias_silu_nhwc", "ccvpe_dwconv_bias_silu_nhwc",
 )
 
 
@@ -102,6 +102,10 @@ def load() -> C.CDLL:
     lib.ccvpe_bias_silu_nhwc.restype = C.c_int
     lib.ccvpe_bias_silu_nhwc.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
                                          C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.ccvpe_dwconv_bias_silu_nhwc.restype = C.c_int
+    lib.ccvpe_dwconv_bias_silu_nhwc.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int,
+                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                C.c_void_p, C.c_void_p]
     if lib.ccvpe_abi_version() != 1:
         raise CcvpeError("libccvpe_b200.so ABI version mismatch")
     _lib = lib
@@ -245,3 +249,15 @@ def bias_silu_nhwc(x: torch.Tensor, bias: Optional[torch.Tensor], y: torch.Tenso
         raise CcvpeError("bias_silu_nhwc: x must be contiguous NHWC and y an NHWC view of the same shape")
     _check(load().ccvpe_bias_silu_nhwc(_ptr(x), _ptr(bias), _ptr(y), y.stride(0), y.stride(1), y.stride(2), B, H, W, Cc,
                                        _ptr(chan_sum), _stream()), "ccvpe_bias_silu_nhwc")
+
+
+def dwconv_bias_silu_nhwc(x_pad: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, y: torch.Tensor, k: int, stride: int,
+                          chan_sum: Optional[torch.Tensor] = None):
+    """x_pad: pre-padded NHWC bf16 view [B,Hp,Wp,C] (channels contiguous); w bf16 [k*k, C]; y contiguous NHWC bf16."""
+    _require_cuda(x_pad, w, bias, y, chan_sum)
+    B, Hp, Wp, Cc = x_pad.shape
+    if x_pad.stride(3) != 1 or not y.is_contiguous():
+        raise CcvpeError("dwconv_bias_silu_nhwc: channels must be contiguous and y contiguous")
+    _check(load().ccvpe_dwconv_bias_silu_nhwc(_ptr(x_pad), x_pad.stride(0), x_pad.stride(1), x_pad.stride(2), Hp, Wp,
+                                              _ptr(w), _ptr(bias), _ptr(y), B, Cc, k, stride, _ptr(chan_sum), _stream()),
+           "ccvpe_dwconv_bias_silu_nhwc")

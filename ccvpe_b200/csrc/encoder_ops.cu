@@ -108,3 +108,158 @@ extern "C" int ccvpe_bias_silu_nhwc(const void* x, const void* bias, void* y, in
   CCVPE_LAUNCH_CHECK("bias_silu_nhwc_kernel");
   return CCVPE_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Depthwise KxK convolution (stride 1 or 2) over a pre-padded channels-last buffer, fused with the folded-BN bias, SiLU
+// and the squeeze-excite channel sums:
+//     y[b, ho, wo, c] = SiLU( sum_{ky,kx} x[b, ho*S + ky, wo*S + kx, c] * w[ky, kx, c] + bias[c] ),   chan_sum[b, c] += y
+// One thread owns 8 channels (16-byte vectors) and a strip of TW horizontally adjacent outputs, so every input vector is
+// loaded once per strip and feeds up to K/S outputs per row; neighbouring strips share their halo through L1.
+// Replaces cuDNN's depthwise conv + a separate bias/SiLU pass + a mean pass (reference model.py:108-114): one read of
+// the padded input and one write of the activated output.  HBM-bound.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace ccvpe {
+
+template <int K, int S>
+__global__ void __launch_bounds__(256)
+dwconv_bias_silu_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_sb, int64_t x_sh, int64_t x_sw,
+                        const __nv_bfloat16* __restrict__ w, const __nv_bfloat16* __restrict__ bias,
+                        __nv_bfloat16* __restrict__ y, int Ho, int Wo, int C, int strips_per_block,
+                        float* __restrict__ chan_sum) {
+  constexpr int TW = 4;                              // outputs per thread along W
+  constexpr int IW = (TW - 1) * S + K;               // input columns a strip touches
+  extern __shared__ float s_sum[];                   // [C]
+  const int G = C >> 3;
+  const int lanes = blockDim.x / G;
+  const int cg = threadIdx.x % G, pl = threadIdx.x / G;
+  const int b = blockIdx.y;
+  const int strips_row = (Wo + TW - 1) / TW;
+  const int n_strips = Ho * strips_row;
+  const int s_lo = blockIdx.x * strips_per_block;
+  const int s_hi = min(n_strips, s_lo + strips_per_block);
+  if (chan_sum) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) s_sum[c] = 0.f;
+    __syncthreads();
+  }
+  float csum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (pl < lanes) {
+    float bv[8];
+    {
+      const uint4 q = *reinterpret_cast<const uint4*>(bias + cg * 8);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(h[j]);
+        bv[2 * j] = f.x;
+        bv[2 * j + 1] = f.y;
+      }
+    }
+    const __nv_bfloat16* xb = x + (int64_t)b * x_sb + cg * 8;
+    const __nv_bfloat16* wb = w + cg * 8;
+    __nv_bfloat16* yb = y + (int64_t)b * Ho * Wo * C + cg * 8;
+    for (int sidx = s_lo + pl; sidx < s_hi; sidx += lanes) {
+      const int ho = sidx / strips_row;
+      const int wo0 = (sidx - ho * strips_row) * TW;
+      float acc[TW][8];
+#pragma unroll
+      for (int t = 0; t < TW; ++t)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[t][j] = bv[j];
+      // columns beyond the padded buffer can only feed outputs >= Wo (never stored): clamp them to stay in bounds
+      const int iw_max = (Wo - 1) * S + K - 1;
+#pragma unroll 1
+      for (int ky = 0; ky < K; ++ky) {                // not unrolled: keeps the register footprint at ~2 CTAs/SM
+        const __nv_bfloat16* xrow = xb + (int64_t)(ho * S + ky) * x_sh;
+#pragma unroll
+        for (int ix = 0; ix < IW; ++ix) {
+          const int iw = min(wo0 * S + ix, iw_max);
+          const uint4 q = __ldg(reinterpret_cast<const uint4*>(xrow + (int64_t)iw * x_sw));
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+          float xv[8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = __bfloat1622float2(h[j]);
+            xv[2 * j] = f.x;
+            xv[2 * j + 1] = f.y;
+          }
+#pragma unroll
+          for (int t = 0; t < TW; ++t) {
+            const int kx = ix - t * S;
+            if (kx >= 0 && kx < K) {                  // compile-time after unrolling
+              const uint4 wq = __ldg(reinterpret_cast<const uint4*>(wb + (ky * K + kx) * C));
+              const __nv_bfloat162* wh = reinterpret_cast<const __nv_bfloat162*>(&wq);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 wf = __bfloat1622float2(wh[j]);
+                acc[t][2 * j] = fmaf(xv[2 * j], wf.x, acc[t][2 * j]);
+                acc[t][2 * j + 1] = fmaf(xv[2 * j + 1], wf.y, acc[t][2 * j + 1]);
+              }
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < TW; ++t) {
+        const int wo = wo0 + t;
+        if (wo < Wo) {
+          uint4 q;
+          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float a0 = acc[t][2 * j], a1 = acc[t][2 * j + 1];
+            a0 = __fdividef(a0, 1.f + __expf(-a0));
+            a1 = __fdividef(a1, 1.f + __expf(-a1));
+            h[j] = __floats2bfloat162_rn(a0, a1);
+            const float2 r = __bfloat1622float2(h[j]);
+            csum[2 * j] += r.x;
+            csum[2 * j + 1] += r.y;
+          }
+          *reinterpret_cast<uint4*>(yb + ((int64_t)ho * Wo + wo) * C) = q;
+        }
+      }
+    }
+  }
+  if (chan_sum) {
+    if (pl < lanes) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&s_sum[cg * 8 + j], csum[j]);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(chan_sum + (int64_t)b * C + c, s_sum[c]);
+  }
+}
+
+}  // namespace ccvpe
+
+extern "C" int ccvpe_dwconv_bias_silu_nhwc(const void* x, int64_t x_sb, int64_t x_sh, int64_t x_sw, int Hp, int Wp,
+                                           const void* w, const void* bias, void* y, int B, int C, int K, int S,
+                                           float* chan_sum, void* stream) {
+  using namespace ccvpe;
+  CCVPE_REQUIRE(x && w && bias && y, "ccvpe_dwconv_bias_silu_nhwc: null pointer");
+  CCVPE_REQUIRE(B > 0 && C > 0 && C % 8 == 0 && C <= 2048, "ccvpe_dwconv_bias_silu_nhwc: bad shape B=%d C=%d", B, C);
+  CCVPE_REQUIRE((K == 3 || K == 5) && (S == 1 || S == 2) && Hp >= K && Wp >= K, "ccvpe_dwconv_bias_silu_nhwc: K=%d S=%d Hp=%d Wp=%d unsupported", K, S, Hp, Wp);
+  CCVPE_REQUIRE(aligned16(x) && aligned16(w) && aligned16(bias) && aligned16(y), "ccvpe_dwconv_bias_silu_nhwc: pointers must be 16-byte aligned");
+  CCVPE_REQUIRE(x_sb % 8 == 0 && x_sh % 8 == 0 && x_sw % 8 == 0, "ccvpe_dwconv_bias_silu_nhwc: input strides must be multiples of 8");
+  const int Ho = (Hp - K) / S + 1, Wo = (Wp - K) / S + 1;
+  const int G = C / 8, lanes = 256 / G;
+  const int64_t n_strips = (int64_t)Ho * ((Wo + 3) / 4);
+  int blocks_x = (int)((8LL * sm_count() + B - 1) / B);
+  int64_t spb = (n_strips + blocks_x - 1) / blocks_x;
+  spb = (spb + lanes - 1) / lanes * lanes;
+  if (spb < lanes) spb = lanes;
+  blocks_x = (int)((n_strips + spb - 1) / spb);
+  const dim3 grid(blocks_x, B);
+  const size_t sm = chan_sum ? C * sizeof(float) : 0;
+  cudaStream_t st = (cudaStream_t)stream;
+#define CCVPE_DW(KK, SS)                                                                                              \
+  dwconv_bias_silu_kernel<KK, SS><<<grid, 256, sm, st>>>((const __nv_bfloat16*)x, x_sb, x_sh, x_sw,                   \
+                                                         (const __nv_bfloat16*)w, (const __nv_bfloat16*)bias,         \
+                                                         (__nv_bfloat16*)y, Ho, Wo, C, (int)spb, chan_sum)
+  if (K == 3 && S == 1) CCVPE_DW(3, 1);
+  else if (K == 3 && S == 2) CCVPE_DW(3, 2);
+  else if (K == 5 && S == 1) CCVPE_DW(5, 1);
+  else CCVPE_DW(5, 2);
+#undef CCVPE_DW
+  CCVPE_LAUNCH_CHECK("dwconv_bias_silu_kernel");
+  return CCVPE_OK;
+}

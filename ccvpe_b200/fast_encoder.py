@@ -40,7 +40,7 @@ def _fold(conv: torch.nn.Conv2d, bn: torch.nn.BatchNorm2d) -> Tuple[torch.Tensor
 
 class _Block:
     __slots__ = ("has_expand", "residual", "stride", "kernel", "pad_lo", "pad_hi", "w_exp", "b_exp", "w_dw", "b_dw",
-                 "w_red", "b_red", "w_se", "b_se", "w_proj", "b_proj", "mid", "cout")
+                 "w_red", "b_red", "w_se", "b_se", "w_proj", "b_proj", "mid", "cout", "w_dw_taps")
 
 
 class FastEncoder:
@@ -69,6 +69,7 @@ class FastEncoder:
             w, b = _fold(dw, blk._bn1)
             o.w_dw, o.b_dw = cast(w).contiguous(memory_format=torch.channels_last), cast(b)
             o.mid = w.shape[0]
+            o.w_dw_taps = cast(w.reshape(o.mid, -1).t())                             # [k*k, mid] for the fused kernel
             o.w_red, o.b_red = cast(blk._se_reduce.weight.detach().flatten(1)), cast(blk._se_reduce.bias.detach())
             o.w_se, o.b_se = cast(blk._se_expand.weight.detach().flatten(1)), cast(blk._se_expand.bias.detach())
             w, b = _fold(blk._project_conv, blk._bn2)
@@ -140,8 +141,9 @@ class FastEncoder:
         pre_bias = self.stem_b
         cur = None                                                                   # activated NHWC tensor
         outs: List[torch.Tensor] = []
+        fused_dw = x.is_cuda and dt == torch.bfloat16      # libccvpe_b200's depthwise conv + bias + SiLU + SE-sum kernel
         for o in self.blocks:
-            dw_pad = (o.pad_lo, o.pad_hi) if (self.circular or o.stride == 2) else None
+            dw_pad = (o.pad_lo, o.pad_hi) if (self.circular or o.stride == 2 or fused_dw) else None
             if pre is not None and not o.has_expand and not o.residual:
                 # block 0: the stem's pending bias + SiLU is applied straight into the depthwise conv's input
                 plain, padded, _unused = self._act(pre, pre_bias, pad=dw_pad)
@@ -167,11 +169,20 @@ class FastEncoder:
                         mid_in_plain, mid_in_padded = None, buf.permute(0, 3, 1, 2)
                     else:
                         mid_in_plain, mid_in_padded = cur, None
-            if mid_in_padded is not None:
-                d = F.conv2d(mid_in_padded, o.w_dw, None, stride=o.stride, groups=o.mid)
+            if fused_dw:
+                xp = mid_in_padded.permute(0, 2, 3, 1)                               # padded NHWC view
+                Bp, Hp, Wp, _ = xp.shape
+                Ho, Wo = (Hp - o.kernel) // o.stride + 1, (Wp - o.kernel) // o.stride + 1
+                d = torch.empty((Bp, Ho, Wo, o.mid), dtype=dt, device=xp.device)
+                sums = torch.zeros((Bp, o.mid), dtype=torch.float32, device=xp.device)
+                cabi.dwconv_bias_silu_nhwc(xp, o.w_dw_taps, o.b_dw, d, o.kernel, o.stride, sums)
             else:
-                d = F.conv2d(mid_in_plain.permute(0, 3, 1, 2), o.w_dw, None, stride=1, padding=o.pad_lo, groups=o.mid)
-            d, _unused, sums = self._act(d.permute(0, 2, 3, 1), o.b_dw, want_sum=True)     # [B,Ho,Wo,mid] NHWC + SE squeeze
+                if mid_in_padded is not None:
+                    d = F.conv2d(mid_in_padded, o.w_dw, None, stride=o.stride, groups=o.mid)
+                else:
+                    d = F.conv2d(mid_in_plain.permute(0, 3, 1, 2), o.w_dw, None, stride=1, padding=o.pad_lo,
+                                 groups=o.mid)
+                d, _unused, sums = self._act(d.permute(0, 2, 3, 1), o.b_dw, want_sum=True)  # [B,Ho,Wo,mid] + SE squeeze
             Bo, Ho, Wo, _ = d.shape
             # squeeze-excite gate folded into the projection weights
             sq = (sums / float(Ho * Wo)).to(dt)                                      # [B, mid]

@@ -165,6 +165,15 @@ int ccvpe_pose_decode(const float* heatmap, const float* ori, int B, int H, int 
 int ccvpe_bias_silu_nhwc(const void* x, const void* bias, void* y, int64_t y_sb, int64_t y_sh, int64_t y_sw,
                          int B, int H, int W, int C, float* chan_sum, void* stream);
 
+/* Depthwise KxK conv (K in {3,5}, stride S in {1,2}) over a PRE-PADDED channels-last bf16 buffer, fused with bias, SiLU
+ * and the squeeze-excite channel sums (reference efficientnet_pytorch/model.py:108-114 in eval mode, BN folded):
+ *   y[b,ho,wo,c] = SiLU(sum_{ky,kx} x[b, ho*S+ky, wo*S+kx, c] * w[ky,kx,c] + bias[c]);  chan_sum[b,c] += sum_{ho,wo} y
+ * x: bf16, logical padded size [B,Hp,Wp,C] with element strides (x_sb, x_sh, x_sw), channels contiguous;
+ * w: bf16 [K*K, C]; bias: bf16 [C]; y: contiguous bf16 [B,Ho,Wo,C], Ho=(Hp-K)/S+1, Wo=(Wp-K)/S+1; chan_sum fp32 or NULL. */
+int ccvpe_dwconv_bias_silu_nhwc(const void* x, int64_t x_sb, int64_t x_sh, int64_t x_sw, int Hp, int Wp,
+                                const void* w, const void* bias, void* y, int B, int C, int K, int S,
+                                float* chan_sum, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

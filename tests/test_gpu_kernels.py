@@ -452,3 +452,27 @@ def test_grd_descriptors_all_heads(cuda_device, B, H, W, cs, layout, dtype):
     cabi.grd_descriptors(f, heads, outs, scratch)
     for o, r in zip(outs, refs):
         assert rel_err(o, r) < FP32_TOL
+
+
+@pytest.mark.parametrize("B,H,W,C,K,S", [(2, 33, 47, 96, 3, 1), (2, 32, 48, 144, 5, 2), (1, 64, 64, 32, 3, 2),
+                                         (3, 16, 16, 1152, 5, 1), (2, 17, 9, 240, 3, 1)])
+def test_dwconv_bias_silu_nhwc(cuda_device, B, H, W, C, K, S):
+    """fused depthwise conv + bias + SiLU + SE channel sums over a pre-padded buffer vs torch (fp32 math on bf16 data)."""
+    g = _gen(15)
+    dev = cuda_device
+    lo = (K - S) // 2 if S == 2 else (K - 1) // 2
+    hi = (K - S) - lo if S == 2 else (K - 1) // 2
+    x = torch.randn(B, H, W, C, generator=g).to(torch.bfloat16)
+    w = (torch.randn(C, 1, K, K, generator=g) * 0.3).to(torch.bfloat16)
+    bias = torch.randn(C, generator=g).to(torch.bfloat16)
+    xp = F.pad(x.float().permute(0, 3, 1, 2), (lo, hi, lo, hi))
+    ref = F.silu(F.conv2d(xp, w.float(), bias.float(), stride=S, groups=C)).permute(0, 2, 3, 1)
+    buf = torch.zeros(B, H + lo + hi, W + lo + hi, C, device=dev, dtype=torch.bfloat16)
+    buf[:, lo:lo + H, lo:lo + W, :] = x.to(dev)
+    Ho, Wo = ref.shape[1], ref.shape[2]
+    y = torch.empty(B, Ho, Wo, C, device=dev, dtype=torch.bfloat16)
+    sums = torch.zeros(B, C, device=dev)
+    cabi.dwconv_bias_silu_nhwc(buf, w.reshape(C, K * K).t().contiguous().to(dev), bias.to(dev), y, K, S, sums)
+    torch.cuda.synchronize()
+    assert rel_err(y.float(), ref) < 1e-2
+    assert rel_err(sums, y.float().sum(dim=(1, 2))) < 1e-4
