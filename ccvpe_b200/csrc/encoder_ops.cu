@@ -128,19 +128,20 @@ dwconv_bias_silu_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_sb, int64
                         float* __restrict__ chan_sum) {
   constexpr int TW = 4;                              // outputs per thread along W
   constexpr int IW = (TW - 1) * S + K;               // input columns a strip touches
-  extern __shared__ float s_sum[];                   // [C]
+  extern __shared__ __align__(16) float s_sum[];     // [C] channel sums, then the bf16 weights [K*K][C]
+  __nv_bfloat16* s_w = reinterpret_cast<__nv_bfloat16*>(s_sum + C);
   const int G = C >> 3;
   const int lanes = blockDim.x / G;
   const int cg = threadIdx.x % G, pl = threadIdx.x / G;
   const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < (K * K * C) / 8; i += blockDim.x)
+    reinterpret_cast<uint4*>(s_w)[i] = __ldg(reinterpret_cast<const uint4*>(w) + i);
   const int strips_row = (Wo + TW - 1) / TW;
   const int n_strips = Ho * strips_row;
   const int s_lo = blockIdx.x * strips_per_block;
   const int s_hi = min(n_strips, s_lo + strips_per_block);
-  if (chan_sum) {
-    for (int c = threadIdx.x; c < C; c += blockDim.x) s_sum[c] = 0.f;
-    __syncthreads();
-  }
+  for (int c = threadIdx.x; c < C; c += blockDim.x) s_sum[c] = 0.f;
+  __syncthreads();
   float csum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (pl < lanes) {
     float bv[8];
@@ -155,7 +156,6 @@ dwconv_bias_silu_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_sb, int64
       }
     }
     const __nv_bfloat16* xb = x + (int64_t)b * x_sb + cg * 8;
-    const __nv_bfloat16* wb = w + cg * 8;
     __nv_bfloat16* yb = y + (int64_t)b * Ho * Wo * C + cg * 8;
     for (int sidx = s_lo + pl; sidx < s_hi; sidx += lanes) {
       const int ho = sidx / strips_row;
@@ -168,32 +168,33 @@ dwconv_bias_silu_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_sb, int64
       // columns beyond the padded buffer can only feed outputs >= Wo (never stored): clamp them to stay in bounds
       const int iw_max = (Wo - 1) * S + K - 1;
 #pragma unroll 1
-      for (int ky = 0; ky < K; ++ky) {                // not unrolled: keeps the register footprint at ~2 CTAs/SM
+      for (int ky = 0; ky < K; ++ky) {                // not unrolled: bounds the register footprint
         const __nv_bfloat16* xrow = xb + (int64_t)(ho * S + ky) * x_sh;
+        uint4 xin[IW];                                // the row segment this strip needs, still packed bf16
 #pragma unroll
         for (int ix = 0; ix < IW; ++ix) {
           const int iw = min(wo0 * S + ix, iw_max);
-          const uint4 q = __ldg(reinterpret_cast<const uint4*>(xrow + (int64_t)iw * x_sw));
-          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
-          float xv[8];
+          xin[ix] = __ldg(reinterpret_cast<const uint4*>(xrow + (int64_t)iw * x_sw));
+        }
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) {
+          const uint4 wq = *reinterpret_cast<const uint4*>(s_w + ((ky * K + kx) * C + cg * 8));   // one weight vector per tap
+          const __nv_bfloat162* wh = reinterpret_cast<const __nv_bfloat162*>(&wq);
+          float wf[8];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float2 f = __bfloat1622float2(h[j]);
-            xv[2 * j] = f.x;
-            xv[2 * j + 1] = f.y;
+            const float2 f = __bfloat1622float2(wh[j]);
+            wf[2 * j] = f.x;
+            wf[2 * j + 1] = f.y;
           }
 #pragma unroll
           for (int t = 0; t < TW; ++t) {
-            const int kx = ix - t * S;
-            if (kx >= 0 && kx < K) {                  // compile-time after unrolling
-              const uint4 wq = __ldg(reinterpret_cast<const uint4*>(wb + (ky * K + kx) * C));
-              const __nv_bfloat162* wh = reinterpret_cast<const __nv_bfloat162*>(&wq);
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&xin[t * S + kx]);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 wf = __bfloat1622float2(wh[j]);
-                acc[t][2 * j] = fmaf(xv[2 * j], wf.x, acc[t][2 * j]);
-                acc[t][2 * j + 1] = fmaf(xv[2 * j + 1], wf.y, acc[t][2 * j + 1]);
-              }
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = __bfloat1622float2(h[j]);
+              acc[t][2 * j] = fmaf(f.x, wf[2 * j], acc[t][2 * j]);
+              acc[t][2 * j + 1] = fmaf(f.y, wf[2 * j + 1], acc[t][2 * j + 1]);
             }
           }
         }
@@ -249,7 +250,16 @@ extern "C" int ccvpe_dwconv_bias_silu_nhwc(const void* x, int64_t x_sb, int64_t 
   if (spb < lanes) spb = lanes;
   blocks_x = (int)((n_strips + spb - 1) / spb);
   const dim3 grid(blocks_x, B);
-  const size_t sm = chan_sum ? C * sizeof(float) : 0;
+  const size_t sm = C * sizeof(float) + (size_t)K * K * C * 2;
+  CCVPE_REQUIRE(sm <= 96 * 1024, "ccvpe_dwconv_bias_silu_nhwc: K*K*C too large for shared memory");
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(dwconv_bias_silu_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(dwconv_bias_silu_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(dwconv_bias_silu_kernel<5, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(dwconv_bias_silu_kernel<5, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    attr_set = true;
+  }
   cudaStream_t st = (cudaStream_t)stream;
 #define CCVPE_DW(KK, SS)                                                                                              \
   dwconv_bias_silu_kernel<KK, SS><<<grid, 256, sm, st>>>((const __nv_bfloat16*)x, x_sb, x_sh, x_sw,                   \
