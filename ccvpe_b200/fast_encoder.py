@@ -54,6 +54,11 @@ class FastEncoder:
         self.stem_b = cast(b)
         self.stem_pad = (enc._conv_stem._pad_lo, enc._conv_stem._pad_hi)
         self.blocks: List[_Block] = []
+        # The projection bias (folded BN shift) of every block is a constant per-channel vector.  Instead of adding it
+        # (a broadcast pass per block) it is carried as a "pending" constant: folded into the next expand GEMM's bias
+        # (W_e (y + p) + b_e = W_e y + (W_e p + b_e)), accumulated through residual connections (which become the GEMM's
+        # beta = 1 accumulate), and only materialised where a tensor leaves the encoder (decoder skips, head).
+        pending = None                                                               # fp32 [C] or None
         for blk in enc._blocks:
             assert isinstance(blk, MBConv)
             o = _Block()
@@ -63,8 +68,11 @@ class FastEncoder:
             o.pad_lo, o.pad_hi = dw._pad_lo, dw._pad_hi
             if o.has_expand:
                 w, b = _fold(blk._expand_conv, blk._bn0)
+                if pending is not None:
+                    b = b + w.flatten(1) @ pending.to(w.device)
                 o.w_exp, o.b_exp = cast(w.flatten(1)), cast(b)                       # [mid, cin]
             else:
+                assert pending is None                                               # only the first block has no expand
                 o.w_exp = o.b_exp = None
             w, b = _fold(dw, blk._bn1)
             o.w_dw, o.b_dw = cast(w).contiguous(memory_format=torch.channels_last), cast(b)
@@ -73,12 +81,15 @@ class FastEncoder:
             o.w_red, o.b_red = cast(blk._se_reduce.weight.detach().flatten(1)), cast(blk._se_reduce.bias.detach())
             o.w_se, o.b_se = cast(blk._se_expand.weight.detach().flatten(1)), cast(blk._se_expand.bias.detach())
             w, b = _fold(blk._project_conv, blk._bn2)
-            o.w_proj, o.b_proj = cast(w.flatten(1)), cast(b)                         # [cout, mid]
+            pending = b + (pending if (o.residual and pending is not None) else 0.0)
+            o.w_proj, o.b_proj = cast(w.flatten(1)), cast(pending)                   # [cout, mid]; b_proj = pending AFTER this block
             o.cout = w.shape[0]
             self.blocks.append(o)
         w, b = _fold(enc._conv_head, enc._bn1)
+        b = b + w.flatten(1) @ pending.to(w.device)
         self.head_w, self.head_b = cast(w.flatten(1)), cast(b)
         self._buffers: Dict[tuple, torch.Tensor] = {}
+        self.keep = set(range(len(self.blocks)))        # block outputs materialised by extract_features_multiscale
 
     # -- padded staging buffers (borders zeroed once, interior rewritten on every use) ---------------------------
     def _padded(self, B, C, H, W, lo, hi, tag) -> torch.Tensor:
@@ -188,13 +199,15 @@ class FastEncoder:
             sq = (sums / float(Ho * Wo)).to(dt)                                      # [B, mid]
             g = torch.sigmoid(F.linear(F.silu(F.linear(sq, o.w_red, o.b_red)), o.w_se, o.b_se))   # [B, mid]
             wg = o.w_proj.unsqueeze(0) * g.unsqueeze(1)                              # [B, cout, mid]
-            y = torch.baddbmm(o.b_proj.view(1, 1, -1), d.reshape(Bo, Ho * Wo, o.mid), wg.transpose(1, 2))
-            y = y.view(Bo, Ho, Wo, o.cout)
-            if o.residual:
-                y = y + block_in
-            cur = y
+            dm = d.reshape(Bo, Ho * Wo, o.mid)
+            if o.residual:                                                           # residual add = beta 1 of the GEMM
+                y = torch.baddbmm(block_in.reshape(Bo, Ho * Wo, o.cout), dm, wg.transpose(1, 2))
+            else:
+                y = torch.bmm(dm, wg.transpose(1, 2))
+            cur = y.view(Bo, Ho, Wo, o.cout)                                         # true value = cur + o.b_proj (pending)
             if keep_blocks:
-                outs.append(cur.permute(0, 3, 1, 2))
+                bi = len(outs)
+                outs.append((cur + o.b_proj).permute(0, 3, 1, 2) if bi in self.keep else None)
         B, H, W, C = cur.shape
         head_pre = F.linear(cur.reshape(B * H * W, C), self.head_w, self.head_b).view(B, H, W, -1)
         head = self._act(head_pre, None)[0]

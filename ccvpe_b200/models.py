@@ -23,7 +23,7 @@ from . import cabi
 from .decoder import PostEncoderPipeline, decode_pose
 from .efficientnet import EfficientNetB0
 from .fast_encoder import FastEncoder
-from .specs import KITTI, OXFORD, SKIP_CHANNELS, VIGOR, VariantSpec
+from .specs import KITTI, OXFORD, SKIP_BLOCKS, SKIP_CHANNELS, VIGOR, VariantSpec
 
 
 class _Permute(nn.Module):
@@ -122,8 +122,9 @@ class _CVMBase(nn.Module):
                     for p in list(enc.parameters()) + list(enc.buffers()))
         cached = self._fast_encoders[0]
         if cached is None or cached[0] != sig:
-            cached = (sig, FastEncoder(self.grd_efficientnet, torch.bfloat16),
-                      FastEncoder(self.sat_efficientnet, torch.bfloat16))
+            sat_plan = FastEncoder(self.sat_efficientnet, torch.bfloat16)
+            sat_plan.keep = set(SKIP_BLOCKS)            # only the decoder's skips are materialised
+            cached = (sig, FastEncoder(self.grd_efficientnet, torch.bfloat16), sat_plan)
             self._fast_encoders[0] = cached
         return cached[1], cached[2]
 
