@@ -21,6 +21,7 @@ EXPORTED_SYMBOLS = (
     "ccvpe_grd_descriptor", "ccvpe_grd_descriptors", "ccvpe_igemm", "ccvpe_igemm_plan", "ccvpe_match_scratch_elems", "ccvpe_match_level",
     "ccvpe_softmax_scratch_elems", "ccvpe_softmax_heatmap", "ccvpe_ori_normalize",
     "ccvpe_pose_scratch_bytes", "ccvpe_pose_decode", "ccvpe_bias_silu_nhwc", "ccvpe_dwconv_bias_silu_nhwc",
+    "ccvpe_pointwise_silu_nhwc",
 )
 
 
@@ -106,6 +107,9 @@ def load() -> C.CDLL:
     lib.ccvpe_dwconv_bias_silu_nhwc.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int,
                                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                                 C.c_void_p, C.c_void_p]
+    lib.ccvpe_pointwise_silu_nhwc.restype = C.c_int
+    lib.ccvpe_pointwise_silu_nhwc.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                              C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     if lib.ccvpe_abi_version() != 1:
         raise CcvpeError("libccvpe_b200.so ABI version mismatch")
     _lib = lib
@@ -261,3 +265,30 @@ def dwconv_bias_silu_nhwc(x_pad: torch.Tensor, w: torch.Tensor, bias: torch.Tens
     _check(load().ccvpe_dwconv_bias_silu_nhwc(_ptr(x_pad), x_pad.stride(0), x_pad.stride(1), x_pad.stride(2), Hp, Wp,
                                               _ptr(w), _ptr(bias), _ptr(y), B, Cc, k, stride, _ptr(chan_sum), _stream()),
            "ccvpe_dwconv_bias_silu_nhwc")
+
+
+def pad_k_blocks(w: torch.Tensor) -> torch.Tensor:
+    """[N, K] weights -> bf16 [N, pad(K)] in the tcgen05 backend's K-block padded layout (include/ccvpe_b200.h: block width
+    16 if K <= 16, 32 if K < 64, else 64; zero filled)."""
+    N, K = w.shape
+    kw = 16 if K <= 16 else (32 if K < 64 else 64)
+    out = torch.zeros((N, -(-K // kw) * kw), dtype=torch.bfloat16, device=w.device)
+    out[:, :K] = w
+    return out.contiguous()
+
+
+def pointwise_silu_nhwc(x: torch.Tensor, w_nk: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor,
+                        pad_lo: int = 0, pad_hi: int = 0):
+    """out[b, lo+h, lo+w, :] = SiLU(x[b,h,w,:] @ W^T + bias).  x: contiguous NHWC bf16 [B,H,W,K]; w_nk = pad_k_blocks(W);
+    bias fp32 [N]; out: contiguous bf16 [B, H+lo+hi, W+lo+hi, N] (only its interior is written)."""
+    _require_cuda(x, w_nk, bias, out)
+    B, H, W, K = x.shape
+    N = w_nk.shape[0]
+    if not x.is_contiguous() or not out.is_contiguous() or x.dtype != torch.bfloat16 or out.dtype != torch.bfloat16:
+        raise CcvpeError("pointwise_silu_nhwc: x and out must be contiguous bf16")
+    if tuple(out.shape) != (B, H + pad_lo + pad_hi, W + pad_lo + pad_hi, N):
+        raise CcvpeError(f"pointwise_silu_nhwc: out has shape {tuple(out.shape)}")
+    if bias is not None and bias.dtype != torch.float32:
+        raise CcvpeError("pointwise_silu_nhwc: bias must be fp32")
+    _check(load().ccvpe_pointwise_silu_nhwc(_ptr(x), B, H, W, K, K, _ptr(w_nk), _ptr(bias), N, _ptr(out), pad_lo, pad_hi,
+                                            _stream()), "ccvpe_pointwise_silu_nhwc")

@@ -42,6 +42,12 @@ inline int check_launch(const char* what) {
     if (_rc != CCVPE_OK) return _rc;            \
   } while (0)
 
+// Optional output placement of the 1x1 SiLU epilogue: pixel (b, h, w) goes to (b, h + lo, w + lo) of a [B, Hp, Wp, ldo]
+// image (the pre-zeroed padded staging buffer the depthwise convolution reads).
+struct TcOutPad {
+  int Hp, Wp, lo;
+};
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 int sm_count();  // cached cudaDevAttrMultiProcessorCount of the current device (148 on B200)

@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(RING_THREADS, 3) conv_ring_tcgen05_kernel(cons
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(16) float s_bias[TC_MAX_N];
   __shared__ __align__(16) float s_r1w[TC_MAX_N];
+  __shared__ int s_off[TC_MAX_N / 8];
   __shared__ __align__(16) uint4 s_blk[4];   // per K block: descriptor offsets (16-byte units) for the MMA issuer
 
   const int warp = threadIdx.x >> 5;
@@ -266,7 +267,7 @@ __global__ void __launch_bounds__(RING_THREADS, 3) conv_ring_tcgen05_kernel(cons
     const int ew = warp & 3;
     const int row = ew * 32 + lane;
     const int et = threadIdx.x - 64;
-    epi_stage_vectors(p.e, s_bias, s_r1w, 0, p.block_n, et, RING_EPI_THREADS);
+    epi_stage_vectors(p.e, s_bias, s_r1w, s_off, 0, p.block_n, et, RING_EPI_THREADS);
     int it = 0;
     for (int unit = blockIdx.x; unit < p.total_units; unit += gridDim.x) {
       const int rc = unit % p.chunks;
@@ -283,7 +284,8 @@ __global__ void __launch_bounds__(RING_THREADS, 3) conv_ring_tcgen05_kernel(cons
         mbar_wait(smem_u32(&bar_tmem_full[acc]), acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * p.block_n);
-        epi_store_row<MODE, HAS_R1, OUT_F32>(p.e, taddr, 0, p.block_n, 0, true, m_glob, rs, r1, s_bias, s_r1w, 1);
+        epi_store_row<MODE, HAS_R1, OUT_F32>(p.e, taddr, 0, p.block_n, 0, true, m_glob, epi_row_base<MODE>(p.e, m_glob),
+                                             rs, r1, s_bias, s_r1w, s_off, 1);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty[acc]));
@@ -306,7 +308,7 @@ static bool ring_plan(const ccvpe_igemm_desc& d, RingParams* p) {
   if (d.dtype != CCVPE_BF16 || !d.w_nk) return false;
   if (d.stride != 1 || d.kh != 3 || d.kw != 3 || d.pad != 1) return false;
   if (d.Hin != d.Hout || d.Win != d.Wout || d.Wout % TC_BM != 0) return false;
-  if (d.out_mode == 1 || d.N > TC_MAX_N) return false;
+  if (d.out_mode == 1 || d.N > TC_MAX_N || d.relu == 2 || !tc_epilogue_supported(d)) return false;
   p->kw0 = tc_block_width(d.c0);
   p->kw1 = d.c1 ? tc_block_width(d.c1) : 64;
   p->nb0 = (d.c0 + p->kw0 - 1) / p->kw0;

@@ -7,6 +7,8 @@
 // the TensorFlow-"same" / circular padding of the following depthwise conv costs no extra copy); the channel sums feed
 // the squeeze-excite gate, so the separate mean pass over the 6x-expanded activation disappears as well.
 // HBM-bound: one read + one write of the tensor, 16-byte accesses.
+#include <cstring>
+
 #include "common.cuh"
 
 namespace ccvpe {
@@ -230,7 +232,31 @@ dwconv_bias_silu_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_sb, int64
   }
 }
 
+int igemm_tcgen05(const ccvpe_igemm_desc& d, cudaStream_t st, const TcOutPad* out_pad);  // igemm_tcgen05.cu
+
 }  // namespace ccvpe
+
+extern "C" int ccvpe_pointwise_silu_nhwc(const void* x, int B, int H, int W, int K, int ldx, const void* w_nk,
+                                         const float* bias, int N, void* out, int pad_lo, int pad_hi, void* stream) {
+  using namespace ccvpe;
+  CCVPE_REQUIRE(x && w_nk && out, "ccvpe_pointwise_silu_nhwc: null pointer");
+  CCVPE_REQUIRE(B > 0 && H > 0 && W > 0 && (int64_t)B * H * W < (1LL << 31) - 256, "ccvpe_pointwise_silu_nhwc: bad shape");
+  CCVPE_REQUIRE(K > 0 && K % 8 == 0 && N > 0 && N % 8 == 0 && ldx >= K && ldx % 8 == 0,
+                "ccvpe_pointwise_silu_nhwc: K=%d N=%d ldx=%d must be positive multiples of 8", K, N, ldx);
+  CCVPE_REQUIRE(pad_lo >= 0 && pad_hi >= 0, "ccvpe_pointwise_silu_nhwc: negative padding");
+  CCVPE_REQUIRE(aligned16(x) && aligned16(w_nk) && aligned16(out), "ccvpe_pointwise_silu_nhwc: pointers must be 16-byte aligned");
+  ccvpe_igemm_desc d;
+  memset(&d, 0, sizeof(d));
+  d.a0 = x; d.c0 = K; d.ld0 = ldx;
+  d.B = B; d.Hin = d.Hout = H; d.Win = d.Wout = W;
+  d.stride = 1; d.kh = d.kw = 1; d.pad = 0;
+  d.N = N; d.dtype = CCVPE_BF16; d.w_nk = w_nk; d.bias = bias;
+  d.relu = 2;                                   // SiLU epilogue
+  d.out_mode = 0; d.out_dtype = CCVPE_BF16; d.ldo = N; d.out = out;
+  d.backend = CCVPE_BACKEND_TCGEN05;
+  const TcOutPad padded = {H + pad_lo + pad_hi, W + pad_lo + pad_hi, pad_lo};
+  return igemm_tcgen05(d, (cudaStream_t)stream, (pad_lo || pad_hi) ? &padded : nullptr);
+}
 
 extern "C" int ccvpe_dwconv_bias_silu_nhwc(const void* x, int64_t x_sb, int64_t x_sh, int64_t x_sw, int Hp, int Wp,
                                            const void* w, const void* bias, void* y, int B, int C, int K, int S,

@@ -209,7 +209,7 @@ int igemm_simt(const ccvpe_igemm_desc& d, cudaStream_t st) {
   return check_launch("igemm_simt_kernel");
 }
 
-int igemm_tcgen05(const ccvpe_igemm_desc& d, cudaStream_t st);  // igemm_tcgen05.cu
+int igemm_tcgen05(const ccvpe_igemm_desc& d, cudaStream_t st, const TcOutPad* out_pad);  // igemm_tcgen05.cu
 bool igemm_tcgen05_supported(const ccvpe_igemm_desc& d);
 int conv_ring_tcgen05(const ccvpe_igemm_desc& d, cudaStream_t st);  // conv_ring_tcgen05.cu
 bool conv_ring_supported(const ccvpe_igemm_desc& d);
@@ -248,6 +248,7 @@ extern "C" int ccvpe_igemm(const ccvpe_igemm_desc* desc, void* stream) {
   CCVPE_REQUIRE(d.c1 == 0 || (d.a1 && d.ld1 >= d.c1 && d.ld1 % 8 == 0), "ccvpe_igemm: bad second source");
   CCVPE_REQUIRE(d.stride >= 1 && d.kh >= 1 && d.kw >= 1 && d.kh * d.kw <= 9 && d.pad >= 0, "ccvpe_igemm: bad window");
   CCVPE_REQUIRE(!d.row_r1 || d.r1_w, "ccvpe_igemm: row_r1 needs r1_w");
+  CCVPE_REQUIRE(d.relu == 0 || d.relu == 1, "ccvpe_igemm: relu must be 0 or 1");
   CCVPE_REQUIRE(d.out_mode >= 0 && d.out_mode <= 2, "ccvpe_igemm: bad out_mode %d", d.out_mode);
   CCVPE_REQUIRE(d.out_mode != 2 || d.out_dtype == CCVPE_F32, "ccvpe_igemm: planar output must be fp32");
   CCVPE_REQUIRE(d.out_mode != 1 || (d.N % 4 == 0 && (d.N / 4) % 8 == 0), "ccvpe_igemm: pixel-shuffle needs N = 4*Cout, Cout%%8==0");
@@ -261,7 +262,7 @@ extern "C" int ccvpe_igemm(const ccvpe_igemm_desc* desc, void* stream) {
   if (backend == CCVPE_BACKEND_TCGEN05) {
     // wide shallow 3x3 levels take the row-ring kernel (CCVPE_DISABLE_RING=1 forces the generic pipeline: A/B tests)
     if (!ring_disabled() && conv_ring_supported(d)) return conv_ring_tcgen05(d, st);
-    return igemm_tcgen05(d, st);
+    return igemm_tcgen05(d, st, nullptr);
   }
   if (backend == CCVPE_BACKEND_SIMT) return igemm_simt(d, st);
   return fail(CCVPE_ERR_BAD_ARGUMENT, "ccvpe_igemm: unknown backend %d", d.backend);

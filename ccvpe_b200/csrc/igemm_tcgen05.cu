@@ -27,8 +27,10 @@ struct TcParams {
   int nb0, nb1, c0, c1, kw0, kw1, kpad0, kpad1, taps, n_tiles_n, total_tiles, block_n, stages, a_bytes, stage_bytes;
   int tmem_cols, a_rank;      // a_rank: rank of the A tensor maps (2 = flattened pixels, 4 = [C,W,H,B], 5 = cell gather)
   int tiles[4], box[4];
+  int tile_shift[4], box_shift[4];   // tiles[] / box[] are powers of two (the last non-unit tiles[] entry takes "the rest")
   int tap_off[9][4];
   int out_stride[4], extent[4];
+  int pad_w, pad_h, pad_wp, pad_hp, pad_lo;   // MODE 3 only: rows are written into the interior of a padded image
   EpiParams e;
 };
 
@@ -45,6 +47,7 @@ igemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(16) float s_bias[2][TC_MAX_N];
   __shared__ __align__(16) float s_r1w[2][TC_MAX_N];
+  __shared__ int s_off[2][TC_MAX_N / 8];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -88,13 +91,13 @@ igemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.n_tiles_n;
         int mt = tile / p.n_tiles_n;
+        const int nt = tile - mt * p.n_tiles_n;
         int base[4];
 #pragma unroll
         for (int d = 0; d < 4; ++d) {
-          base[d] = (mt % p.tiles[d]) * p.box[d];
-          mt /= p.tiles[d];
+          base[d] = (mt & ((1 << p.tile_shift[d]) - 1)) << p.box_shift[d];
+          mt >>= p.tile_shift[d];
         }
         const int n0 = nt * p.block_n;
         for (int tap = 0; tap < p.taps; ++tap) {
@@ -197,27 +200,41 @@ igemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
     const bool fixed_n = (p.n_tiles_n == 1);
     const bool has_r1 = (p.e.row_r1 != nullptr), has_rs = (p.e.row_scale != nullptr);
     // row -> output pixel of a tile
-    auto locate = [&](int tile, int& m_glob, bool& valid) {
-      int mt = tile / p.n_tiles_n;
-      int r = row;
-      m_glob = 0;
-      valid = true;
+    // (shifts and masks only: this runs per tile in every epilogue thread)
+    auto locate = [&](int tile, int& m_glob, bool& valid, int64_t& row_base) {
+      int mt = fixed_n ? tile : tile / p.n_tiles_n;
+      if (p.a_rank == 2) {
+        m_glob = mt * TC_BM + row;
+        valid = m_glob < p.extent[0];
+      } else {
+        int r = row;
+        m_glob = 0;
+        valid = true;
 #pragma unroll
-      for (int d = 0; d < 4; ++d) {
-        const int coord = (mt % p.tiles[d]) * p.box[d] + (r % p.box[d]);
-        mt /= p.tiles[d];
-        r /= p.box[d];
-        valid = valid && (coord < p.extent[d]);
-        m_glob += coord * p.out_stride[d];
+        for (int d = 0; d < 4; ++d) {
+          const int coord = ((mt & ((1 << p.tile_shift[d]) - 1)) << p.box_shift[d]) + (r & ((1 << p.box_shift[d]) - 1));
+          mt >>= p.tile_shift[d];
+          r >>= p.box_shift[d];
+          valid = valid && (coord < p.extent[d]);
+          m_glob += coord * p.out_stride[d];
+        }
       }
+      int m_out = m_glob;
+      if (MODE == 3 && p.pad_w) {   // (b, h, w) -> interior pixel of the padded [B, Hp, Wp] staging image
+        const int q = m_glob / p.pad_w, w = m_glob - q * p.pad_w;
+        const int b = q / p.pad_h, h = q - b * p.pad_h;
+        m_out = (b * p.pad_hp + h + p.pad_lo) * p.pad_wp + w + p.pad_lo;
+      }
+      row_base = epi_row_base<MODE>(p.e, m_out);
     };
 
-    if (fixed_n) epi_stage_vectors(p.e, s_bias[0], s_r1w[0], 0, p.block_n, et, EPI_THREADS);
+    if (fixed_n) epi_stage_vectors(p.e, s_bias[0], s_r1w[0], s_off[0], 0, p.block_n, et, EPI_THREADS);
     int m_glob, m_next = 0;
+    int64_t row_base, base_next = 0;
     bool valid, valid_next = false;
     float rs = 1.f, r1 = 0.f, rs_next = 1.f, r1_next = 0.f;
     if ((int)blockIdx.x < p.total_tiles) {
-      locate(blockIdx.x, m_next, valid_next);
+      locate(blockIdx.x, m_next, valid_next, base_next);
       if (valid_next) {
         if (has_rs) rs_next = __ldg(p.e.row_scale + m_next);
         if (has_r1) r1_next = __ldg(p.e.row_r1 + m_next);
@@ -225,29 +242,28 @@ igemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
     }
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      m_glob = m_next; valid = valid_next; rs = rs_next; r1 = r1_next;
+      m_glob = m_next; valid = valid_next; rs = rs_next; r1 = r1_next; row_base = base_next;
       {  // prefetch the per-row scalars of the next tile: their latency hides behind this tile's epilogue
         const int nxt = tile + gridDim.x;
         rs_next = 1.f; r1_next = 0.f; valid_next = false;
         if (nxt < p.total_tiles) {
-          locate(nxt, m_next, valid_next);
+          locate(nxt, m_next, valid_next, base_next);
           if (valid_next) {
             if (has_rs) rs_next = __ldg(p.e.row_scale + m_next);
             if (has_r1) r1_next = __ldg(p.e.row_r1 + m_next);
           }
         }
       }
-      const int nt = tile % p.n_tiles_n;
-      const int n0 = nt * p.block_n;
+      const int n0 = fixed_n ? 0 : (tile % p.n_tiles_n) * p.block_n;
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       const int vb = fixed_n ? 0 : acc;
-      if (!fixed_n) epi_stage_vectors(p.e, s_bias[acc], s_r1w[acc], n0, p.block_n, et, EPI_THREADS);
+      if (!fixed_n) epi_stage_vectors(p.e, s_bias[acc], s_r1w[acc], s_off[acc], n0, p.block_n, et, EPI_THREADS);
       mbar_wait(smem_u32(&bar_tmem_full[acc]), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * p.block_n);
-      epi_store_row<MODE, HAS_R1, OUT_F32>(p.e, taddr, half, p.block_n, n0, valid, m_glob, rs, r1, s_bias[vb], s_r1w[vb],
-                                           EPI_WARPS / 4);
+      epi_store_row<MODE, HAS_R1, OUT_F32>(p.e, taddr, half, p.block_n, n0, valid, m_glob, row_base, rs, r1, s_bias[vb],
+                                           s_r1w[vb], s_off[vb], EPI_WARPS / 4);
       // release the accumulator stage back to the MMA issuer
       tc_fence_before();
       __syncwarp();
@@ -303,15 +319,27 @@ bool igemm_tcgen05_supported(const ccvpe_igemm_desc& d) {
   if (d.dtype != CCVPE_BF16 || !d.w_nk) return false;
   if (!tc_geometry(d, &g)) return false;
   if (d.out_mode == 1 && (d.kh != 1)) return false;
+  if (!tc_epilogue_supported(d)) return false;
   return true;
 }
 
-int igemm_tcgen05(const ccvpe_igemm_desc& d, cudaStream_t st) {
+static int ilog2(int v) {
+  int s = 0;
+  while ((1 << s) < v) ++s;
+  return s;
+}
+
+int igemm_tcgen05(const ccvpe_igemm_desc& d, cudaStream_t st, const TcOutPad* out_pad) {
   TcGeometry g;
   if (d.dtype != CCVPE_BF16) return fail(CCVPE_ERR_UNSUPPORTED, "ccvpe_igemm(tcgen05): bf16 operands only");
   if (!d.w_nk) return fail(CCVPE_ERR_BAD_ARGUMENT, "ccvpe_igemm(tcgen05): w_nk is null");
   if (!tc_geometry(d, &g)) return fail(CCVPE_ERR_UNSUPPORTED, "ccvpe_igemm(tcgen05): unsupported geometry");
   if (!aligned16(d.w_nk)) return fail(CCVPE_ERR_BAD_ARGUMENT, "ccvpe_igemm(tcgen05): w_nk must be 16-byte aligned");
+  if (!tc_epilogue_supported(d))
+    return fail(CCVPE_ERR_UNSUPPORTED, "ccvpe_igemm(tcgen05): bf16 outputs need channel counts / ldo that are multiples "
+                                       "of 8 and a 16-byte aligned base");
+  if (d.relu == 2 && (d.out_mode != 0 || d.out_dtype != CCVPE_BF16 || d.row_r1))
+    return fail(CCVPE_ERR_UNSUPPORTED, "ccvpe_igemm(tcgen05): SiLU epilogue is channels-last bf16 only");
 
   static thread_local TcParams p;   // > 1 KB: keep it off the stack; it is copied at launch
   memset(&p, 0, sizeof(p));
@@ -416,7 +444,25 @@ int igemm_tcgen05(const ccvpe_igemm_desc& d, cudaStream_t st) {
   }
   const int m_tiles = p.tiles[0] * p.tiles[1] * p.tiles[2] * p.tiles[3];
   p.total_tiles = m_tiles * n_tiles_n;
+  // the kernel decomposes tile / row indices with shifts: box[] are powers of two by construction, tiles[] too except the
+  // last non-unit one, which takes whatever is left of the tile index
+  {
+    int last = 0;
+    for (int i = 0; i < 4; ++i)
+      if (p.tiles[i] > 1) last = i;
+    for (int i = 0; i < 4; ++i) {
+      if (!is_pow2(p.box[i]) || (i < last && !is_pow2(p.tiles[i])))
+        return fail(CCVPE_ERR_UNSUPPORTED, "ccvpe_igemm(tcgen05): tile decomposition is not a power of two");
+      p.box_shift[i] = ilog2(p.box[i]);
+      p.tile_shift[i] = i < last ? ilog2(p.tiles[i]) : (i == last ? 30 : 0);
+    }
+  }
   fill_epi(p.e, d);
+  if (out_pad) {
+    if (d.relu != 2 || d.kh != 1)
+      return fail(CCVPE_ERR_UNSUPPORTED, "ccvpe_igemm(tcgen05): padded output is a feature of the 1x1 SiLU epilogue");
+    p.pad_w = d.Wout; p.pad_h = d.Hout; p.pad_wp = out_pad->Wp; p.pad_hp = out_pad->Hp; p.pad_lo = out_pad->lo;
+  }
 
   const int smem = stages * stage_bytes + 1024;
   const int max_grid = (light ? light_ctas : 1) * sm_count();
@@ -441,7 +487,11 @@ int igemm_tcgen05(const ccvpe_igemm_desc& d, cudaStream_t st) {
       igemm_tcgen05_kernel<8, MODE, R1, F32><<<grid, 64 + 32 * 8, smem, st>>>(p);                                       \
     }                                                                                                                  \
   } while (0)
-  CCVPE_EPI_SWITCH(epi_variant(p.e), CCVPE_LAUNCH_IGEMM)
+  if (epi_variant(p.e) == 6) {
+    CCVPE_LAUNCH_IGEMM(3, false, false);
+  } else {
+    CCVPE_EPI_SWITCH(epi_variant(p.e), CCVPE_LAUNCH_IGEMM)
+  }
 #undef CCVPE_LAUNCH_IGEMM
   if (attr_err != cudaSuccess) return fail(CCVPE_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
   return check_launch("igemm_tcgen05_kernel");

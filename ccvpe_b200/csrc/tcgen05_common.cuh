@@ -134,60 +134,70 @@ struct EpiParams {
   void* out;
 };
 
-// Stages bias / rank-1 vectors of the N tile [n0, n0 + block_n) into shared memory (all TC_EPI_THREADS threads call).
-__device__ __forceinline__ void epi_stage_vectors(const EpiParams& e, float* s_bias, float* s_r1w, int n0, int block_n,
-                                                  int et, int epi_threads = TC_EPI_THREADS) {
+// Stages the per-column epilogue constants of the N tile [n0, n0 + block_n) into shared memory (all epilogue threads
+// call): bias, rank-1 weights and -- so that the per-row store loop carries no index arithmetic -- the element offset of
+// every 8-column group relative to the row's first output pixel (channel, plus the quadrant displacement of the k2 s2
+// transposed conv's pixel shuffle).  SiLU (relu == 2) is evaluated as h + h*tanh(h) with h = x/2, so its bias is staged
+// pre-halved.
+__device__ __forceinline__ void epi_stage_vectors(const EpiParams& e, float* s_bias, float* s_r1w, int* s_off, int n0,
+                                                  int block_n, int et, int epi_threads = TC_EPI_THREADS) {
+  const float bscale = e.relu == 2 ? 0.5f : 1.f;
   for (int c = et; c < block_n; c += epi_threads) {
     const int n = n0 + c;
-    s_bias[c] = (e.bias && n < e.N) ? __ldg(e.bias + n) : 0.f;
+    s_bias[c] = (e.bias && n < e.N) ? bscale * __ldg(e.bias + n) : 0.f;
     s_r1w[c] = (e.row_r1 && n < e.N) ? __ldg(e.r1_w + n) : 0.f;
+    if ((c & 7) == 0) {
+      int off = n;
+      if (e.out_mode == 1) {
+        const int cout = e.N >> 2;
+        const int ij = n / cout, co = n - ij * cout;
+        off = (ij >> 1) * 2 * e.Wout * e.ldo + (ij & 1) * e.ldo + co;
+      }
+      s_off[c >> 3] = off;
+    }
   }
   asm volatile("bar.sync 1, %0;" ::"r"(epi_threads) : "memory");
 }
 
-// One thread = one accumulator row (output pixel m_glob).  `halves` = number of warps sharing a TMEM lane group (each takes
-// every `halves`-th 32-column chunk, starting at `half`).  taddr = TMEM address of (lane group, first column of the stage).
-// Specialised at compile time on (output mode, rank-1 term, fp32 output): the kernels are instantiated once per
-// variant, so the per-column code carries no runtime branches (the epilogue is the bottleneck of the HBM-bound levels).
+// Element offset of the first output pixel of accumulator row m (m = flattened (b, h, w) of the GEMM's M axis).
+template <int MODE>
+__device__ __forceinline__ int64_t epi_row_base(const EpiParams& e, int m) {
+  if (MODE == 1) {   // pixel shuffle: pixel (q = b*H + h, w) -> (2q, 2w) of the [B*2H, 2W] output
+    const int q = m / e.Wout, w = m - q * e.Wout;
+    return ((int64_t)q * 4 * e.Wout + 2 * w) * e.ldo;
+  }
+  return (int64_t)m * e.ldo;
+}
+
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// One thread = one accumulator row.  `halves` = number of warps sharing a TMEM lane group (each takes every
+// `halves`-th 32-column chunk, starting at `half`).  taddr = TMEM address of (lane group, first column of the stage).
+// Specialised at compile time on (output mode, rank-1 term, fp32 output); the kernels are instantiated once per variant.
+//   MODE 0 channels-last | 1 pixel shuffle | 2 planar fp32 NCHW | 3 channels-last bf16 with SiLU
+// bf16 outputs take the lean path: per 8 columns two LDS.128 (bias), 8 FFMA (+8 FMNMX or the SiLU), 4 F2FP, one LDS (group
+// offset) and ONE 16-byte store -- the host guarantees 8-column groups never straddle N / a quadrant and 16-byte alignment
+// (tc_epilogue_supported).  The epilogue, not the tensor pipe, bounds the shallow-K layers, so its instruction count is
+// what is being minimised here.  row_base = epi_row_base() of the row (m_glob itself is only used by the planar mode).
 template <int MODE, bool HAS_R1, bool OUT_F32>
 __device__ __forceinline__ void epi_store_row(const EpiParams& e, uint32_t taddr, int half, int block_n, int n0,
-                                              bool valid, int m_glob, float rs, float r1, const float* s_bias,
-                                              const float* s_r1w, int halves) {
-  // element offsets of this row's output pixel(s); scalars, not an indexed array (that would live in local memory)
-  int64_t px0 = 0, px1 = 0, px2 = 0, px3 = 0, plane0 = 0;
-  if (MODE == 0) {
-    px0 = (int64_t)m_glob * e.ldo;
-  } else {
-    const int b_img = m_glob / e.HWo;
-    const int hw = m_glob - b_img * e.HWo;
-    if (MODE == 2) {
-      plane0 = (int64_t)b_img * e.N * e.HWo + hw;
-    } else {
-      const int h = hw / e.Wout, w = hw - h * e.Wout;
-      const int64_t row_pitch = (int64_t)2 * e.Wout * e.ldo;
-      px0 = (((int64_t)b_img * 2 * e.Hout + 2 * h) * (2 * e.Wout) + 2 * w) * e.ldo;   // quadrant (i, j) = (0, 0)
-      px1 = px0 + e.ldo;                                                               // (0, 1)
-      px2 = px0 + row_pitch;                                                           // (1, 0)
-      px3 = px2 + e.ldo;                                                               // (1, 1)
-    }
-  }
-  const int cout = MODE == 1 ? (e.N >> 2) : e.N;
+                                              bool valid, int m_glob, int64_t row_base, float rs, float r1,
+                                              const float* s_bias, const float* s_r1w, const int* s_off, int halves) {
   const int N = e.N;
+  const int ncols = min(block_n, N - n0);               // accumulator columns of this tile that exist
   const float lower = e.relu ? 0.f : -INFINITY;          // branch-free ReLU
-  const bool vec_ok = OUT_F32 ? ((e.ldo & 3) == 0) : ((e.ldo & 7) == 0);
+  if (MODE == 3) rs *= 0.5f;
 
   auto process = [&](const uint32_t (&v)[32], int c0) {
     if (!valid) return;
-    int ij = 0, co = n0 + c0;                // (quadrant, channel) of the chunk's first column
-    if (MODE == 1) {
-      ij = co / cout;
-      co -= ij * cout;
-    }
 #pragma unroll
     for (int g8 = 0; g8 < 4; ++g8) {
       const int cl = c0 + g8 * 8;             // column within the tile
-      const int n = n0 + cl;
-      if (n >= N || cl >= block_n) break;
+      if (cl >= ncols) break;
       const float4 b0 = *reinterpret_cast<const float4*>(&s_bias[cl]);
       const float4 b1 = *reinterpret_cast<const float4*>(&s_bias[cl + 4]);
       float y[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
@@ -198,20 +208,26 @@ __device__ __forceinline__ void epi_store_row(const EpiParams& e, uint32_t taddr
 #pragma unroll
         for (int j = 0; j < 8; ++j) y[j] = fmaf(r1, wv[j], y[j]);
       }
+      if (MODE == 3) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) y[j] = fmaxf(fmaf(__uint_as_float(v[g8 * 8 + j]), rs, y[j]), lower);
+        for (int j = 0; j < 8; ++j) {
+          const float h = fmaf(__uint_as_float(v[g8 * 8 + j]), rs, y[j]);
+          y[j] = fmaf(h, tanh_approx(h), h);               // SiLU(x) = x * sigmoid(x) = h + h * tanh(h), h = x / 2
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] = fmaxf(fmaf(__uint_as_float(v[g8 * 8 + j]), rs, y[j]), lower);
+      }
       if (MODE == 2) {
-        float* o = static_cast<float*>(e.out) + plane0;
+        const int n = n0 + cl;
+        float* o = static_cast<float*>(e.out) + (int64_t)(m_glob / e.HWo) * N * e.HWo + (m_glob % e.HWo);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           if (n + j < N) o[(int64_t)(n + j) * e.HWo] = y[j];
-        continue;
-      }
-      const int64_t off = (MODE == 0 ? px0 : (ij == 0 ? px0 : (ij == 1 ? px1 : (ij == 2 ? px2 : px3)))) + co;
-      const bool full8 = (n + 8 <= N) && vec_ok;
-      if (OUT_F32) {
-        float* o = static_cast<float*>(e.out) + off;
-        if (full8) {
+      } else if (OUT_F32) {
+        const int n = n0 + cl;
+        float* o = static_cast<float*>(e.out) + row_base + n;
+        if ((n + 8 <= N) && ((e.ldo & 3) == 0)) {
           *reinterpret_cast<float4*>(o) = make_float4(y[0], y[1], y[2], y[3]);
           *reinterpret_cast<float4*>(o + 4) = make_float4(y[4], y[5], y[6], y[7]);
         } else {
@@ -220,26 +236,15 @@ __device__ __forceinline__ void epi_store_row(const EpiParams& e, uint32_t taddr
             if (n + j < N) o[j] = y[j];
         }
       } else {
-        __nv_bfloat16* o = static_cast<__nv_bfloat16*>(e.out) + off;
-        if (full8) {
-          __nv_bfloat162 q0 = __floats2bfloat162_rn(y[0], y[1]), q1 = __floats2bfloat162_rn(y[2], y[3]);
-          __nv_bfloat162 q2 = __floats2bfloat162_rn(y[4], y[5]), q3 = __floats2bfloat162_rn(y[6], y[7]);
-          uint4 pk;
-          pk.x = *reinterpret_cast<uint32_t*>(&q0);
-          pk.y = *reinterpret_cast<uint32_t*>(&q1);
-          pk.z = *reinterpret_cast<uint32_t*>(&q2);
-          pk.w = *reinterpret_cast<uint32_t*>(&q3);
-          *reinterpret_cast<uint4*>(o) = pk;
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (n + j < N) o[j] = __float2bfloat16_rn(y[j]);
-        }
-      }
-      co += 8;
-      if (MODE == 1 && co >= cout) {
-        co -= cout;
-        ++ij;
+        __nv_bfloat16* o = static_cast<__nv_bfloat16*>(e.out) + (row_base + s_off[cl >> 3]);
+        __nv_bfloat162 q0 = __floats2bfloat162_rn(y[0], y[1]), q1 = __floats2bfloat162_rn(y[2], y[3]);
+        __nv_bfloat162 q2 = __floats2bfloat162_rn(y[4], y[5]), q3 = __floats2bfloat162_rn(y[6], y[7]);
+        uint4 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&q0);
+        pk.y = *reinterpret_cast<uint32_t*>(&q1);
+        pk.z = *reinterpret_cast<uint32_t*>(&q2);
+        pk.w = *reinterpret_cast<uint32_t*>(&q3);
+        *reinterpret_cast<uint4*>(o) = pk;
       }
     }
   };
@@ -261,9 +266,20 @@ __device__ __forceinline__ void epi_store_row(const EpiParams& e, uint32_t taddr
   }
 }
 
+// bf16 outputs use 16-byte stores of 8-column groups: channel counts / strides must be multiples of 8, base 16-B aligned.
+inline bool tc_epilogue_supported(const ccvpe_igemm_desc& d) {
+  if (d.out_dtype != CCVPE_BF16) return true;
+  if (d.out_mode == 2) return false;
+  const int cout = d.out_mode == 1 ? d.N / 4 : d.N;
+  return (cout % 8 == 0) && (d.ldo % 8 == 0) && ((reinterpret_cast<uintptr_t>(d.out) & 15) == 0) &&
+         (d.out_mode != 1 || d.N % 4 == 0);
+}
+
 // Epilogue variant of a descriptor: 0 conv bf16 | 1 conv bf16 + rank-1 | 2 conv fp32 channels-last | 3 planar fp32 |
-// 4 pixel-shuffle bf16 | 5 pixel-shuffle bf16 + rank-1.  CCVPE_EPI_SWITCH expands `X(MODE, HAS_R1, OUT_F32)` for it.
+// 4 pixel-shuffle bf16 | 5 pixel-shuffle bf16 + rank-1 | 6 channels-last bf16 + SiLU (generic igemm kernel only).
+// CCVPE_EPI_SWITCH expands `X(MODE, HAS_R1, OUT_F32)` for variants 0..5.
 inline int epi_variant(const EpiParams& e) {
+  if (e.relu == 2) return 6;
   if (e.out_mode == 1) return e.row_r1 ? 5 : 4;
   if (e.out_mode == 2) return 3;
   if (e.out_f32) return 2;

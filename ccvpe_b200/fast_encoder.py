@@ -6,7 +6,9 @@ broadcast multiplies / padding copies 34 %, SiLU 8 %, all convolutions together 
 same arithmetic with far fewer passes over the (6x expanded) activations -- algebra only, no new kernels:
 
   * BatchNorm (eval) is folded into the preceding convolution's weight and bias;
-  * 1x1 convolutions on channels-last tensors are plain GEMMs (`F.linear`, bias in the cuBLAS epilogue);
+  * 1x1 convolutions on channels-last tensors are plain GEMMs; on the CUDA bf16 path the expand / head GEMMs run on
+    libccvpe_b200's tcgen05 pipeline with bias + SiLU in the epilogue, stored straight into the depthwise conv's padded
+    input image (`ccvpe_pointwise_silu_nhwc`), elsewhere `F.linear`;
   * the squeeze-excite gate is folded into the 1x1 projection:  W (g (.) x) = (W diag(g)) x  -> one `baddbmm` per block
     instead of a broadcast multiply over the expanded tensor followed by a convolution;
   * TensorFlow-style "same" padding (asymmetric for stride 2) and the ground encoder's circular width padding are
@@ -39,7 +41,8 @@ def _fold(conv: torch.nn.Conv2d, bn: torch.nn.BatchNorm2d) -> Tuple[torch.Tensor
 
 
 class _Block:
-    __slots__ = ("has_expand", "residual", "stride", "kernel", "pad_lo", "pad_hi", "w_exp", "b_exp", "w_dw", "b_dw",
+    __slots__ = ("has_expand", "residual", "stride", "kernel", "pad_lo", "pad_hi", "w_exp", "b_exp", "w_exp_nk",
+                 "b_exp_f32", "w_dw", "b_dw",
                  "w_red", "b_red", "w_se", "b_se", "w_proj", "b_proj", "mid", "cout", "w_dw_taps")
 
 
@@ -71,6 +74,9 @@ class FastEncoder:
                 if pending is not None:
                     b = b + w.flatten(1) @ pending.to(w.device)
                 o.w_exp, o.b_exp = cast(w.flatten(1)), cast(b)                       # [mid, cin]
+                # operands of libccvpe_b200's tcgen05 pointwise conv (+ bias + SiLU epilogue)
+                o.w_exp_nk = cabi.pad_k_blocks(o.w_exp)
+                o.b_exp_f32 = b.to(device=dev, dtype=torch.float32).contiguous()
             else:
                 assert pending is None                                               # only the first block has no expand
                 o.w_exp = o.b_exp = None
@@ -88,6 +94,8 @@ class FastEncoder:
         w, b = _fold(enc._conv_head, enc._bn1)
         b = b + w.flatten(1) @ pending.to(w.device)
         self.head_w, self.head_b = cast(w.flatten(1)), cast(b)
+        self.head_w_nk = cabi.pad_k_blocks(self.head_w)
+        self.head_b_f32 = b.to(device=dev, dtype=torch.float32).contiguous()
         self._buffers: Dict[tuple, torch.Tensor] = {}
         self.keep = set(range(len(self.blocks)))        # block outputs materialised by extract_features_multiscale
 
@@ -167,7 +175,15 @@ class FastEncoder:
                     pre = None
                 block_in = cur
                 B, H, W, Cin = cur.shape
-                if o.has_expand:
+                if o.has_expand and fused_dw:
+                    # expand GEMM + bias + SiLU in one tcgen05 kernel, written straight into the depthwise conv's
+                    # padded input image
+                    buf = self._padded(B, o.mid, H, W, o.pad_lo, o.pad_hi, "dw")
+                    cabi.pointwise_silu_nhwc(cur, o.w_exp_nk, o.b_exp_f32, buf, o.pad_lo, o.pad_hi)
+                    if self.circular:
+                        self._wrap_columns(buf, H, W, o.pad_lo, o.pad_hi)
+                    mid_in_plain, mid_in_padded = None, buf.permute(0, 3, 1, 2)
+                elif o.has_expand:
                     e = F.linear(cur.reshape(B * H * W, Cin), o.w_exp, o.b_exp).view(B, H, W, o.mid)
                     plain, padded, _unused = self._act(e, None, pad=dw_pad)
                     mid_in_plain, mid_in_padded = (plain if padded is None else None), padded
@@ -209,8 +225,12 @@ class FastEncoder:
                 bi = len(outs)
                 outs.append((cur + o.b_proj).permute(0, 3, 1, 2) if bi in self.keep else None)
         B, H, W, C = cur.shape
-        head_pre = F.linear(cur.reshape(B * H * W, C), self.head_w, self.head_b).view(B, H, W, -1)
-        head = self._act(head_pre, None)[0]
+        if fused_dw:
+            head = torch.empty((B, H, W, self.head_w.shape[0]), dtype=dt, device=cur.device)
+            cabi.pointwise_silu_nhwc(cur, self.head_w_nk, self.head_b_f32, head)
+        else:
+            head_pre = F.linear(cur.reshape(B * H * W, C), self.head_w, self.head_b).view(B, H, W, -1)
+            head = self._act(head_pre, None)[0]
         return head.permute(0, 3, 1, 2), outs
 
     def extract_features(self, x):

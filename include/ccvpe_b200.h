@@ -174,6 +174,15 @@ int ccvpe_dwconv_bias_silu_nhwc(const void* x, int64_t x_sb, int64_t x_sh, int64
                                 const void* w, const void* bias, void* y, int B, int C, int K, int S,
                                 float* chan_sum, void* stream);
 
+/* Pointwise (1x1) convolution + bias + SiLU over channels-last bf16 pixels on the tcgen05 pipeline -- the MBConv expand
+ * step and the encoder head (reference efficientnet_pytorch/model.py:100-106, 312-314 in eval mode, BN folded):
+ *   out[b, h + pad_lo, w + pad_lo, n] = SiLU(sum_k x[(b,h,w), k] * w_nk[n, k] + bias[n])
+ * x: bf16 [B*H*W, K] with row stride ldx (elements); w_nk: bf16 [N][pad(K)] in the K-block padded layout documented for
+ * ccvpe_igemm_desc.w_nk; bias fp32 [N] or NULL; out: bf16 image [B, H+pad_lo+pad_hi, W+pad_lo+pad_hi, N] whose interior is
+ * written (the border is left untouched: the depthwise convolution's zero padding lives there).  K % 8 == N % 8 == 0. */
+int ccvpe_pointwise_silu_nhwc(const void* x, int B, int H, int W, int K, int ldx, const void* w_nk, const float* bias,
+                              int N, void* out, int pad_lo, int pad_hi, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -476,3 +476,25 @@ def test_dwconv_bias_silu_nhwc(cuda_device, B, H, W, C, K, S):
     torch.cuda.synchronize()
     assert rel_err(y.float(), ref) < 1e-2
     assert rel_err(sums, y.float().sum(dim=(1, 2))) < 1e-4
+
+
+@pytest.mark.parametrize("B,H,W,K,N,lo,hi", [(2, 20, 36, 16, 96, 0, 1), (1, 33, 17, 24, 144, 1, 1), (3, 16, 16, 40, 240, 2, 2),
+                                            (2, 10, 20, 112, 672, 2, 2), (1, 16, 16, 192, 1152, 1, 1),
+                                            (2, 10, 20, 320, 1280, 0, 0), (1, 5, 7, 80, 480, 1, 2)])
+def test_pointwise_silu_nhwc(cuda_device, B, H, W, K, N, lo, hi):
+    """tcgen05 1x1 conv + bias + SiLU written into the interior of a padded image vs torch (fp32 math on bf16 data);
+    the border of the image must be left untouched."""
+    g = _gen(16)
+    dev = cuda_device
+    x = torch.randn(B, H, W, K, generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K) * 2.0).to(torch.bfloat16)
+    bias = torch.randn(N, generator=g)
+    ref = F.silu(x.float() @ w.float().t() + bias)
+    out = torch.full((B, H + lo + hi, W + lo + hi, N), 7.0, device=dev, dtype=torch.bfloat16)
+    cabi.pointwise_silu_nhwc(x.to(dev), cabi.pad_k_blocks(w.to(dev)), bias.to(dev), out, lo, hi)
+    torch.cuda.synchronize()
+    got = out[:, lo:lo + H, lo:lo + W, :].float()
+    assert rel_err(got, ref) < 1e-2
+    border = out.clone()
+    border[:, lo:lo + H, lo:lo + W, :] = 7.0
+    assert bool((border == 7.0).all())
