@@ -16,9 +16,10 @@
 
 namespace ccvpe {
 
-// warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2.. = epilogue.  Two instantiations: 8 epilogue warps
-// (one fat CTA per SM, wide compute-bound tiles) and 4 epilogue warps (192 threads; two CTAs share an SM, which doubles
-// the single-thread issue capacity the narrow HBM-bound layers are limited by).
+// warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..9 = epilogue.  Two instantiations: HEAVY (one CTA per
+// SM, all of its shared memory as pipeline stages: wide compute-bound tiles) and LIGHT (two CTAs share an SM: two
+// producers / MMA issuers and 16 epilogue warps for the narrow HBM-bound layers, which are limited by single-thread issue
+// and by the epilogue's instruction latencies; its rows leave through shared-memory staging tiles).
 constexpr int TC_MAX_STAGES = 16;
 constexpr int TC_SMEM_BUDGET = 200 * 1024;
 
@@ -31,15 +32,20 @@ struct TcParams {
   int tap_off[9][4];
   int out_stride[4], extent[4];
   int pad_w, pad_h, pad_wp, pad_hp, pad_lo;   // MODE 3 only: rows are written into the interior of a padded image
+  int epi_off;                                // byte offset of the epilogue staging tile behind the pipeline stages
   EpiParams e;
 };
 
 // ---- kernel ------------------------------------------------------------------------------------------------------
-template <int EPI_WARPS, int MODE, bool HAS_R1, bool OUT_F32>
-__global__ void __launch_bounds__(64 + 32 * EPI_WARPS, EPI_WARPS == 4 ? 2 : 1)
+template <bool LIGHT, int MODE, bool HAS_R1, bool OUT_F32>
+__global__ void __launch_bounds__(64 + 32 * TC_EPI_WARPS, LIGHT ? 2 : 1)
 igemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
+  constexpr int EPI_WARPS = TC_EPI_WARPS;
   constexpr int EPI_THREADS = 32 * EPI_WARPS;
+  // the light (two CTAs per SM) configuration runs the HBM-bound layers: its bf16 rows leave through per-warp staging tiles
+  constexpr bool STAGED = LIGHT && !OUT_F32 && MODE != 2;
   extern __shared__ uint8_t smem_raw[];
+  __shared__ int64_t s_rowbase[STAGED ? 32 * EPI_WARPS : 1];
   __shared__ __align__(8) uint64_t bar_full[TC_MAX_STAGES];
   __shared__ __align__(8) uint64_t bar_empty[TC_MAX_STAGES];
   __shared__ __align__(8) uint64_t bar_tmem_full[2];
@@ -262,12 +268,18 @@ igemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
       mbar_wait(smem_u32(&bar_tmem_full[acc]), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * p.block_n);
-      epi_store_row<MODE, HAS_R1, OUT_F32>(p.e, taddr, half, p.block_n, n0, valid, m_glob, row_base, rs, r1, s_bias[vb],
-                                           s_r1w[vb], s_off[vb], EPI_WARPS / 4);
-      // release the accumulator stage back to the MMA issuer
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty[acc]));
+      // (the accumulator stage is released to the MMA issuer inside, once its last chunk has been read)
+      if (STAGED) {
+        const int ewi = warp - 2;                     // index among the epilogue warps
+        epi_store_row_staged<MODE, HAS_R1>(p.e, taddr, half, EPI_WARPS / 4, p.block_n, n0, valid, row_base, rs, r1,
+                                           s_bias[vb], s_r1w[vb], s_off[vb], smem_u32(&bar_tmem_empty[acc]),
+                                           smem_raw + (smem_base - smem_u32(smem_raw)) + p.epi_off +
+                                               ewi * EPI_WARP_STAGE_BYTES,
+                                           s_rowbase + 32 * ewi);
+      } else {
+        epi_store_row<MODE, HAS_R1, OUT_F32>(p.e, taddr, half, p.block_n, n0, valid, m_glob, row_base, rs, r1, s_bias[vb],
+                                             s_r1w[vb], s_off[vb], EPI_WARPS / 4, smem_u32(&bar_tmem_empty[acc]));
+      }
     }
   }
 
@@ -352,26 +364,36 @@ int igemm_tcgen05(const ccvpe_igemm_desc& d, cudaStream_t st, const TcOutPad* ou
   p.c0 = d.c0;
   p.c1 = d.c1;
   p.taps = d.kh * d.kw;
-  // shallow-K layers are HBM / issue bound, not tensor bound: keep their tiles <= 128 columns so that two CTAs fit an SM
-  const int max_n = (p.taps * (d.c0 + d.c1) <= 256) ? 128 : TC_MAX_N;
-  const int n_tiles_n = (d.N + max_n - 1) / max_n;
-  int block_n = ((d.N + n_tiles_n - 1) / n_tiles_n + 15) / 16 * 16;
-  p.n_tiles_n = n_tiles_n;
-  p.block_n = block_n;
+  // shallow-K layers are HBM / issue bound, not tensor bound: their tiles stay <= 128 columns so that two CTAs (two
+  // producers / MMA issuers, 16 epilogue warps) fit an SM -- the LIGHT configuration, whose bf16 rows leave through the
+  // per-warp staging tiles; everything else gets one HEAVY CTA per SM with all of its shared memory as pipeline stages.
   const int kw_max = (d.c1 && p.kw1 > p.kw0) ? p.kw1 : p.kw0;
   p.a_bytes = TC_BM * kw_max * 2;                                   // multiple of 1024 for every kw
-  const int stage_bytes = p.a_bytes + (block_n * kw_max * 2 + 1023) / 1024 * 1024;
+  const bool shallow = p.taps * (d.c0 + d.c1) <= 256;
+  const bool staged_out = d.out_dtype == CCVPE_BF16 && d.out_mode != 2;
+  const int light_budget = 104 * 1024 - (staged_out ? TC_EPI_WARPS * EPI_WARP_STAGE_BYTES : 0);
+  int n_tiles_n = 0, block_n = 0, stage_bytes = 0;
+  auto plan = [&](int max_n) {
+    n_tiles_n = (d.N + max_n - 1) / max_n;
+    block_n = ((d.N + n_tiles_n - 1) / n_tiles_n + 15) / 16 * 16;
+    stage_bytes = p.a_bytes + (block_n * kw_max * 2 + 1023) / 1024 * 1024;   // A + B tile of the widest K block in use
+    p.tmem_cols = 32;
+    while (p.tmem_cols < 2 * block_n) p.tmem_cols <<= 1;
+    return p.tmem_cols <= 256 && light_budget / stage_bytes >= 3;
+  };
+  bool light = plan(shallow ? 128 : TC_MAX_N);
+  if (!light && shallow) {            // wide K blocks: narrower N tiles keep three pipeline stages within the light budget
+    light = plan(64);
+    if (!light) plan(128);
+  }
+  p.n_tiles_n = n_tiles_n;
+  p.block_n = block_n;
   p.stage_bytes = stage_bytes;
-  p.tmem_cols = 32;
-  while (p.tmem_cols < 2 * block_n) p.tmem_cols <<= 1;
-  // narrow tiles (<= 128 accumulator columns): small CTAs, two per SM; wide tiles: one fat CTA per SM
-  int light_ctas = 0;                       // CTAs per SM in the light configuration (0 = heavy)
-  // (three CTAs would need <= 112 registers/thread: measured slower, the epilogue spills)
-  if (p.tmem_cols <= 256 && (104 * 1024) / stage_bytes >= 3) light_ctas = 2;
-  const bool light = light_ctas > 0;
-  int stages = (light_ctas == 3 ? 68 * 1024 : (light_ctas == 2 ? 104 * 1024 : TC_SMEM_BUDGET)) / stage_bytes;
+  int stages = (light ? light_budget : TC_SMEM_BUDGET) / stage_bytes;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   p.stages = stages;
+  p.epi_off = stages * stage_bytes;
+  const bool staged = light && staged_out;
   const int64_t ktot = (int64_t)p.taps * (p.kpad0 + p.kpad1);
 
   int rc;
@@ -464,27 +486,27 @@ int igemm_tcgen05(const ccvpe_igemm_desc& d, cudaStream_t st, const TcOutPad* ou
     p.pad_w = d.Wout; p.pad_h = d.Hout; p.pad_wp = out_pad->Wp; p.pad_hp = out_pad->Hp; p.pad_lo = out_pad->lo;
   }
 
-  const int smem = stages * stage_bytes + 1024;
-  const int max_grid = (light ? light_ctas : 1) * sm_count();
+  const int smem = stages * stage_bytes + (staged ? (TC_EPI_WARPS * EPI_WARP_STAGE_BYTES) : 0) + 1024;
+  const int max_grid = (light ? 2 : 1) * sm_count();
   const int grid = p.total_tiles < max_grid ? p.total_tiles : max_grid;
   cudaError_t attr_err = cudaSuccess;
 #define CCVPE_LAUNCH_IGEMM(MODE, R1, F32)                                                                              \
   do {                                                                                                                 \
-    static thread_local bool attr4 = false, attr8 = false;                                                             \
+    static thread_local bool attr_l = false, attr_h = false;                                                           \
     if (light) {                                                                                                       \
-      if (!attr4) {                                                                                                    \
-        attr_err = cudaFuncSetAttribute(igemm_tcgen05_kernel<4, MODE, R1, F32>,                                        \
+      if (!attr_l) {                                                                                                   \
+        attr_err = cudaFuncSetAttribute(igemm_tcgen05_kernel<true, MODE, R1, F32>,                                     \
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8192);               \
-        attr4 = true;                                                                                                  \
+        attr_l = true;                                                                                                 \
       }                                                                                                                \
-      igemm_tcgen05_kernel<4, MODE, R1, F32><<<grid, 64 + 32 * 4, smem, st>>>(p);                                       \
+      igemm_tcgen05_kernel<true, MODE, R1, F32><<<grid, 64 + 32 * TC_EPI_WARPS, smem, st>>>(p);                         \
     } else {                                                                                                           \
-      if (!attr8) {                                                                                                    \
-        attr_err = cudaFuncSetAttribute(igemm_tcgen05_kernel<8, MODE, R1, F32>,                                        \
+      if (!attr_h) {                                                                                                   \
+        attr_err = cudaFuncSetAttribute(igemm_tcgen05_kernel<false, MODE, R1, F32>,                                    \
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8192);               \
-        attr8 = true;                                                                                                  \
+        attr_h = true;                                                                                                 \
       }                                                                                                                \
-      igemm_tcgen05_kernel<8, MODE, R1, F32><<<grid, 64 + 32 * 8, smem, st>>>(p);                                       \
+      igemm_tcgen05_kernel<false, MODE, R1, F32><<<grid, 64 + 32 * TC_EPI_WARPS, smem, st>>>(p);                        \
     }                                                                                                                  \
   } while (0)
   if (epi_variant(p.e) == 6) {

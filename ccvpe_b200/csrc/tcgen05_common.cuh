@@ -13,7 +13,8 @@ namespace ccvpe {
 
 constexpr int TC_BM = 128;          // pixels per tile (UMMA M)
 constexpr int TC_MAX_N = 256;       // widest accumulator tile (TMEM columns per stage)
-constexpr int TC_EPI_THREADS = 256; // 8 epilogue warps
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_EPI_THREADS = 32 * TC_EPI_WARPS;
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -183,10 +184,14 @@ __device__ __forceinline__ float tanh_approx(float x) {
 // offset) and ONE 16-byte store -- the host guarantees 8-column groups never straddle N / a quadrant and 16-byte alignment
 // (tc_epilogue_supported).  The epilogue, not the tensor pipe, bounds the shallow-K layers, so its instruction count is
 // what is being minimised here.  row_base = epi_row_base() of the row (m_glob itself is only used by the planar mode).
+// release_bar (an mbarrier address, or 0): arrived on by lane 0 as soon as the last TMEM chunk of the row is in registers,
+// so the MMA issuer gets the accumulator stage back before the stores have drained.
 template <int MODE, bool HAS_R1, bool OUT_F32>
 __device__ __forceinline__ void epi_store_row(const EpiParams& e, uint32_t taddr, int half, int block_n, int n0,
                                               bool valid, int m_glob, int64_t row_base, float rs, float r1,
-                                              const float* s_bias, const float* s_r1w, const int* s_off, int halves) {
+                                              const float* s_bias, const float* s_r1w, const int* s_off, int halves,
+                                              uint32_t release_bar = 0) {
+  const int lane = threadIdx.x & 31;
   const int N = e.N;
   const int ncols = min(block_n, N - n0);               // accumulator columns of this tile that exist
   const float lower = e.relu ? 0.f : -INFINITY;          // branch-free ReLU
@@ -249,20 +254,116 @@ __device__ __forceinline__ void epi_store_row(const EpiParams& e, uint32_t taddr
     }
   };
 
+  // the accumulator stage goes back to the MMA issuer as soon as its last chunk is in registers
+  auto release = [&]() {
+    if (release_bar) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(release_bar);
+    }
+  };
+
   // TMEM -> registers, double buffered: the load of the next chunk is in flight while this one is processed
   uint32_t va[32], vb2[32];
   const int cfirst = half * 32, cstep = 32 * halves;
   if (cfirst < block_n) tmem_ld32(taddr + (uint32_t)cfirst, va);
+  else release();
   for (int c0 = cfirst; c0 < block_n; c0 += 2 * cstep) {
     tmem_ld_wait();
     const bool more1 = (c0 + cstep < block_n);
     if (more1) tmem_ld32(taddr + (uint32_t)(c0 + cstep), vb2);
+    else release();
     process(va, c0);
     if (more1) {
       tmem_ld_wait();
       if (c0 + 2 * cstep < block_n) tmem_ld32(taddr + (uint32_t)(c0 + 2 * cstep), va);
+      else release();
       process(vb2, c0 + cstep);
     }
+  }
+}
+
+// Staged variant for the HBM-bound (shallow-K) layers, bf16 outputs only.  32 threads each storing their own row touch 32
+// different 128-byte lines per instruction, which caps a row-per-thread epilogue at ~2.4 TB/s on B200
+// (scripts/store_probe.cu).  Here every 32-column chunk (64 bytes per row) goes through a per-warp shared-memory tile
+// instead (row pitch 80 bytes = an odd number of 16-byte units: the row-per-thread writes are bank-conflict free) and is
+// copied out with 4 lanes per row / 8 rows per instruction, so consecutive pixels leave as contiguous runs (6 TB/s in the
+// same probe).  Rows outside the problem are computed like the others and dropped at the copy (no divergent math).
+// `stage` / `s_rowbase`: THIS WARP's 32 x 80-byte tile and 32 row offsets.  Single-buffered TMEM loads keep the register
+// count low enough for 16 epilogue warps per SM, which is what hides the instruction latencies of this code.
+constexpr int EPI_CHUNK_PITCH = 80;
+constexpr int EPI_WARP_STAGE_BYTES = 32 * EPI_CHUNK_PITCH;
+
+template <int MODE, bool HAS_R1>
+__device__ __forceinline__ void epi_store_row_staged(const EpiParams& e, uint32_t taddr, int half, int halves, int block_n,
+                                                     int n0, bool valid, int64_t row_base, float rs, float r1,
+                                                     const float* s_bias, const float* s_r1w, const int* s_off,
+                                                     uint32_t release_bar, uint8_t* stage, int64_t* s_rowbase) {
+  const int lane = threadIdx.x & 31;
+  const int ncols = min(block_n, e.N - n0);
+  const float lower = e.relu ? 0.f : -INFINITY;
+  if (MODE == 3) rs *= 0.5f;
+  s_rowbase[lane] = valid ? row_base : -1;
+  uint8_t* my = stage + lane * EPI_CHUNK_PITCH;
+  __nv_bfloat16* out = static_cast<__nv_bfloat16*>(e.out);
+  const int cstep = 32 * halves;
+  const int fr = lane >> 2, fc = lane & 3;          // copy-out role: row within a group of 8, 16-byte unit within the chunk
+  const uint8_t* src = stage + fr * EPI_CHUNK_PITCH + fc * 16;
+  auto release = [&]() {
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(release_bar);
+  };
+  int c0 = half * 32;
+  if (c0 >= ncols) release();
+  for (; c0 < ncols; c0 += cstep) {
+    uint32_t v[32];
+    tmem_ld32(taddr + (uint32_t)c0, v);
+    tmem_ld_wait();
+    if (c0 + cstep >= ncols) release();             // that was this warp's last chunk of the accumulator stage
+#pragma unroll
+    for (int g8 = 0; g8 < 4; ++g8) {
+      const int cl = c0 + g8 * 8;
+      if (cl >= ncols) break;
+      const float4 b0 = *reinterpret_cast<const float4*>(&s_bias[cl]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&s_bias[cl + 4]);
+      float y[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      if (HAS_R1) {
+        const float4 w0 = *reinterpret_cast<const float4*>(&s_r1w[cl]);
+        const float4 w1 = *reinterpret_cast<const float4*>(&s_r1w[cl + 4]);
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] = fmaf(r1, wv[j], y[j]);
+      }
+      if (MODE == 3) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float h = fmaf(__uint_as_float(v[g8 * 8 + j]), rs, y[j]);
+          y[j] = fmaf(h, tanh_approx(h), h);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] = fmaxf(fmaf(__uint_as_float(v[g8 * 8 + j]), rs, y[j]), lower);
+      }
+      __nv_bfloat162 q0 = __floats2bfloat162_rn(y[0], y[1]), q1 = __floats2bfloat162_rn(y[2], y[3]);
+      __nv_bfloat162 q2 = __floats2bfloat162_rn(y[4], y[5]), q3 = __floats2bfloat162_rn(y[6], y[7]);
+      uint4 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&q0);
+      pk.y = *reinterpret_cast<uint32_t*>(&q1);
+      pk.z = *reinterpret_cast<uint32_t*>(&q2);
+      pk.w = *reinterpret_cast<uint32_t*>(&q3);
+      *reinterpret_cast<uint4*>(my + g8 * 16) = pk;
+    }
+    __syncwarp();
+    const bool unit_ok = fc < ((min(32, ncols - c0)) >> 3);
+    const int goff = unit_ok ? s_off[(c0 >> 3) + fc] : 0;
+#pragma unroll
+    for (int pass = 0; pass < 4; ++pass) {
+      const int64_t rb = s_rowbase[pass * 8 + fr];
+      const uint4 val = *reinterpret_cast<const uint4*>(src + pass * 8 * EPI_CHUNK_PITCH);
+      if (unit_ok && rb >= 0) *reinterpret_cast<uint4*>(out + (rb + goff)) = val;
+    }
+    __syncwarp();
   }
 }
 
