@@ -21,7 +21,7 @@ EXPORTED_SYMBOLS = (
     "ccvpe_grd_descriptor", "ccvpe_grd_descriptors", "ccvpe_igemm", "ccvpe_igemm_plan", "ccvpe_match_scratch_elems", "ccvpe_match_level",
     "ccvpe_softmax_scratch_elems", "ccvpe_softmax_heatmap", "ccvpe_ori_normalize",
     "ccvpe_pose_scratch_bytes", "ccvpe_pose_decode", "ccvpe_bias_silu_nhwc", "ccvpe_dwconv_bias_silu_nhwc",
-    "ccvpe_pointwise_silu_nhwc",
+    "ccvpe_pointwise_silu_nhwc", "ccvpe_stem_conv_silu_nhwc",
 )
 
 
@@ -110,6 +110,9 @@ def load() -> C.CDLL:
     lib.ccvpe_pointwise_silu_nhwc.restype = C.c_int
     lib.ccvpe_pointwise_silu_nhwc.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                               C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.ccvpe_stem_conv_silu_nhwc.restype = C.c_int
+    lib.ccvpe_stem_conv_silu_nhwc.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                              C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     if lib.ccvpe_abi_version() != 1:
         raise CcvpeError("libccvpe_b200.so ABI version mismatch")
     _lib = lib
@@ -292,3 +295,21 @@ def pointwise_silu_nhwc(x: torch.Tensor, w_nk: torch.Tensor, bias: Optional[torc
         raise CcvpeError("pointwise_silu_nhwc: bias must be fp32")
     _check(load().ccvpe_pointwise_silu_nhwc(_ptr(x), B, H, W, K, K, _ptr(w_nk), _ptr(bias), N, _ptr(out), pad_lo, pad_hi,
                                             _stream()), "ccvpe_pointwise_silu_nhwc")
+
+
+def stem_conv_silu_nhwc(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, out: torch.Tensor, in_pad_lo: int,
+                        in_pad_hi: int, out_pad_lo: int, out_pad_hi: int, circular: bool):
+    """x: contiguous fp32 NCHW [B,3,H,W]; w fp32 [27, CO] ordered (ci, ky, kx); bias fp32 [CO];
+    out: contiguous bf16 [B, Ho+lo+hi, Wo+lo+hi, CO], Ho = (H+in_lo+in_hi-3)//2+1 (interior + wrap columns are written)."""
+    _require_cuda(x, w, bias, out)
+    B, Cin, H, W = x.shape
+    CO = w.shape[1]
+    if Cin != 3 or x.dtype != torch.float32 or not x.is_contiguous() or w.dtype != torch.float32 or bias.dtype != torch.float32:
+        raise CcvpeError("stem_conv_silu_nhwc: x must be contiguous fp32 [B,3,H,W], w / bias fp32")
+    Ho, Wo = (H + in_pad_lo + in_pad_hi - 3) // 2 + 1, (W + in_pad_lo + in_pad_hi - 3) // 2 + 1
+    want = (B, Ho + out_pad_lo + out_pad_hi, Wo + out_pad_lo + out_pad_hi, CO)
+    if tuple(out.shape) != want or out.dtype != torch.bfloat16 or not out.is_contiguous():
+        raise CcvpeError(f"stem_conv_silu_nhwc: out must be contiguous bf16 {want}, got {tuple(out.shape)}")
+    _check(load().ccvpe_stem_conv_silu_nhwc(_ptr(x), B, H, W, _ptr(w.contiguous()), _ptr(bias), CO, _ptr(out), in_pad_lo,
+                                            in_pad_hi, out_pad_lo, out_pad_hi, 1 if circular else 0, _stream()),
+           "ccvpe_stem_conv_silu_nhwc")

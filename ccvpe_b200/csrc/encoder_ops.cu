@@ -232,9 +232,122 @@ dwconv_bias_silu_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_sb, int64
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Encoder stem: 3x3 stride-2 convolution over the fp32 NCHW image (3 channels, TensorFlow-"same" zero padding, optionally
+// circular along the width for panoramas) + folded-BN bias + SiLU, written as bf16 channels-last into the interior of the
+// first depthwise convolution's padded input image (wrap columns included for the circular encoder).  Replaces: dtype /
+// layout conversion of the image, two F.pad copies, cuDNN's conv + its own padding pass, and the bias/SiLU pass.
+// One thread = two horizontally adjacent output pixels x all CO output channels (weights broadcast from shared memory).
+// ---------------------------------------------------------------------------------------------------------------------
+template <int CO, bool CIRC>
+__global__ void __launch_bounds__(128)
+stem_conv_silu_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                      __nv_bfloat16* __restrict__ out, int H, int W, int Ho, int Wo, int in_lo, int out_lo, int Hp, int Wp) {
+  __shared__ __align__(16) float s_w[27 * CO];
+  __shared__ __align__(16) float s_b[CO];
+  for (int i = threadIdx.x; i < 27 * CO; i += blockDim.x) s_w[i] = w[i];
+  for (int i = threadIdx.x; i < CO; i += blockDim.x) s_b[i] = bias[i];
+  __syncthreads();
+  const int pw = blockIdx.x * blockDim.x + threadIdx.x;      // pair index along the output row
+  const int wo0 = 2 * pw;
+  if (wo0 >= Wo) return;
+  const int ho = blockIdx.y, b = blockIdx.z;
+  float acc[2][CO];
+#pragma unroll
+  for (int c = 0; c < CO; ++c) acc[0][c] = acc[1][c] = s_b[c];
+  const float* xb = x + (int64_t)b * 3 * H * W;
+#pragma unroll 1
+  for (int ci = 0; ci < 3; ++ci) {
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int ih = 2 * ho + ky - in_lo;
+      float in[5];
+#pragma unroll
+      for (int ix = 0; ix < 5; ++ix) {
+        int iw = 2 * wo0 + ix - in_lo;
+        bool ok = ih >= 0 && ih < H;
+        if (CIRC) iw = iw < 0 ? iw + W : (iw >= W ? iw - W : iw);
+        else ok = ok && iw >= 0 && iw < W;
+        in[ix] = ok ? __ldg(xb + ((int64_t)ci * H + ih) * W + iw) : 0.f;
+      }
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const float* wt = s_w + ((ci * 3 + ky) * 3 + kx) * CO;
+#pragma unroll
+        for (int c = 0; c < CO; c += 4) {
+          const float4 wv = *reinterpret_cast<const float4*>(wt + c);
+          acc[0][c] = fmaf(in[kx], wv.x, acc[0][c]);
+          acc[0][c + 1] = fmaf(in[kx], wv.y, acc[0][c + 1]);
+          acc[0][c + 2] = fmaf(in[kx], wv.z, acc[0][c + 2]);
+          acc[0][c + 3] = fmaf(in[kx], wv.w, acc[0][c + 3]);
+          acc[1][c] = fmaf(in[kx + 2], wv.x, acc[1][c]);
+          acc[1][c + 1] = fmaf(in[kx + 2], wv.y, acc[1][c + 1]);
+          acc[1][c + 2] = fmaf(in[kx + 2], wv.z, acc[1][c + 2]);
+          acc[1][c + 3] = fmaf(in[kx + 2], wv.w, acc[1][c + 3]);
+        }
+      }
+    }
+  }
+  __nv_bfloat16* orow = out + ((int64_t)b * Hp + ho + out_lo) * Wp * CO;
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int wo = wo0 + t;
+    if (wo >= Wo) break;
+    uint4 q[CO / 8];
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(q);
+#pragma unroll
+    for (int c = 0; c < CO; c += 2) {
+      const float a0 = acc[t][c], a1 = acc[t][c + 1];
+      h[c >> 1] = __floats2bfloat162_rn(__fdividef(a0, 1.f + __expf(-a0)), __fdividef(a1, 1.f + __expf(-a1)));
+    }
+    uint4* dst = reinterpret_cast<uint4*>(orow + (int64_t)(wo + out_lo) * CO);
+#pragma unroll
+    for (int i = 0; i < CO / 8; ++i) dst[i] = q[i];
+    if (CIRC) {   // wrap columns of the circularly padded image: [0, out_lo) <- last columns, [out_lo + Wo, Wp) <- first ones
+      const int hi = Wp - out_lo - Wo;
+      if (wo >= Wo - out_lo) {
+        uint4* d2 = reinterpret_cast<uint4*>(orow + (int64_t)(wo - (Wo - out_lo)) * CO);
+#pragma unroll
+        for (int i = 0; i < CO / 8; ++i) d2[i] = q[i];
+      }
+      if (wo < hi) {
+        uint4* d2 = reinterpret_cast<uint4*>(orow + (int64_t)(out_lo + Wo + wo) * CO);
+#pragma unroll
+        for (int i = 0; i < CO / 8; ++i) d2[i] = q[i];
+      }
+    }
+  }
+}
+
 int igemm_tcgen05(const ccvpe_igemm_desc& d, cudaStream_t st, const TcOutPad* out_pad);  // igemm_tcgen05.cu
 
 }  // namespace ccvpe
+
+extern "C" int ccvpe_stem_conv_silu_nhwc(const float* x, int B, int H, int W, const float* w, const float* bias, int CO,
+                                         void* out, int in_pad_lo, int in_pad_hi, int out_pad_lo, int out_pad_hi,
+                                         int circular, void* stream) {
+  using namespace ccvpe;
+  CCVPE_REQUIRE(x && w && bias && out, "ccvpe_stem_conv_silu_nhwc: null pointer");
+  CCVPE_REQUIRE(B > 0 && H >= 3 && W >= 3 && B <= 65535, "ccvpe_stem_conv_silu_nhwc: bad shape B=%d H=%d W=%d", B, H, W);
+  CCVPE_REQUIRE(CO == 32, "ccvpe_stem_conv_silu_nhwc: CO=%d unsupported (EfficientNet-B0 stem has 32 channels)", CO);
+  CCVPE_REQUIRE(in_pad_lo >= 0 && in_pad_lo <= 2 && in_pad_hi >= 0 && in_pad_hi <= 2 && out_pad_lo >= 0 && out_pad_hi >= 0,
+                "ccvpe_stem_conv_silu_nhwc: bad padding");
+  CCVPE_REQUIRE(aligned16(out), "ccvpe_stem_conv_silu_nhwc: out must be 16-byte aligned");
+  const int Ho = (H + in_pad_lo + in_pad_hi - 3) / 2 + 1, Wo = (W + in_pad_lo + in_pad_hi - 3) / 2 + 1;
+  CCVPE_REQUIRE(Ho <= 65535, "ccvpe_stem_conv_silu_nhwc: image too tall");
+  CCVPE_REQUIRE(!circular || (out_pad_lo <= Wo && out_pad_hi <= Wo), "ccvpe_stem_conv_silu_nhwc: wrap wider than the image");
+  const int Hp = Ho + out_pad_lo + out_pad_hi, Wp = Wo + out_pad_lo + out_pad_hi;
+  const int pairs = (Wo + 1) / 2;
+  const dim3 grid((pairs + 127) / 128, Ho, B);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (circular)
+    stem_conv_silu_kernel<32, true><<<grid, 128, 0, st>>>(x, w, bias, (__nv_bfloat16*)out, H, W, Ho, Wo, in_pad_lo, out_pad_lo, Hp, Wp);
+  else
+    stem_conv_silu_kernel<32, false><<<grid, 128, 0, st>>>(x, w, bias, (__nv_bfloat16*)out, H, W, Ho, Wo, in_pad_lo, out_pad_lo, Hp, Wp);
+  CCVPE_LAUNCH_CHECK("stem_conv_silu_kernel");
+  return CCVPE_OK;
+}
 
 extern "C" int ccvpe_pointwise_silu_nhwc(const void* x, int B, int H, int W, int K, int ldx, const void* w_nk,
                                          const float* bias, int N, void* out, int pad_lo, int pad_hi, void* stream) {

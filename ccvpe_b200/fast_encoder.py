@@ -56,6 +56,9 @@ class FastEncoder:
         self.stem_w = cast(w).contiguous(memory_format=torch.channels_last)
         self.stem_b = cast(b)
         self.stem_pad = (enc._conv_stem._pad_lo, enc._conv_stem._pad_hi)
+        # fp32 operands of libccvpe_b200's fused stem kernel: weights [27, 32] ordered (ci, ky, kx)
+        self.stem_w_taps = w.permute(1, 2, 3, 0).reshape(27, -1).to(device=dev, dtype=torch.float32).contiguous()
+        self.stem_b_f32 = b.to(device=dev, dtype=torch.float32).contiguous()
         self.blocks: List[_Block] = []
         # The projection bias (folded BN shift) of every block is a constant per-channel vector.  Instead of adding it
         # (a broadcast pass per block) it is carried as a "pending" constant: folded into the next expand GEMM's bias
@@ -150,20 +153,36 @@ class FastEncoder:
     def extract(self, x: torch.Tensor, keep_blocks: bool):
         """x: [B,3,H,W] (any format).  Returns (head features NCHW-logical/channels-last, [16 block outputs] or [])."""
         dt = self.dtype
-        x = x.to(dt).contiguous(memory_format=torch.channels_last)
         lo, hi = self.stem_pad
-        if self.circular:
-            x = F.pad(F.pad(x, (lo, hi, 0, 0), mode="circular"), (0, 0, lo, hi))     # 3-channel input: negligible
+        fused_dw = x.is_cuda and dt == torch.bfloat16      # libccvpe_b200's kernels (stem, expand, depthwise) vs torch ops
+        stem_padded = None
+        if fused_dw and self.stem_w_taps.shape[1] == 32 and x.shape[1] == 3 and not self.blocks[0].has_expand:
+            # stem conv + bias + SiLU straight from the fp32 NCHW image into block 0's padded depthwise input
+            o0 = self.blocks[0]
+            B, _c, H, W = x.shape
+            Ho, Wo = (H + lo + hi - 3) // 2 + 1, (W + lo + hi - 3) // 2 + 1
+            buf = self._padded(B, 32, Ho, Wo, o0.pad_lo, o0.pad_hi, "dw")
+            cabi.stem_conv_silu_nhwc(x.float().contiguous(), self.stem_w_taps, self.stem_b_f32, buf, lo, hi, o0.pad_lo,
+                                     o0.pad_hi, self.circular)
+            stem_padded = buf.permute(0, 3, 1, 2)
+            pre = pre_bias = None
         else:
-            x = F.pad(x, (lo, hi, lo, hi))
-        pre = F.conv2d(x, self.stem_w, None, stride=2).permute(0, 2, 3, 1)          # NHWC, before bias + SiLU
-        pre_bias = self.stem_b
+            x = x.to(dt).contiguous(memory_format=torch.channels_last)
+            if self.circular:
+                x = F.pad(F.pad(x, (lo, hi, 0, 0), mode="circular"), (0, 0, lo, hi))     # 3-channel input: negligible
+            else:
+                x = F.pad(x, (lo, hi, lo, hi))
+            pre = F.conv2d(x, self.stem_w, None, stride=2).permute(0, 2, 3, 1)          # NHWC, before bias + SiLU
+            pre_bias = self.stem_b
         cur = None                                                                   # activated NHWC tensor
         outs: List[torch.Tensor] = []
-        fused_dw = x.is_cuda and dt == torch.bfloat16      # libccvpe_b200's depthwise conv + bias + SiLU + SE-sum kernel
         for o in self.blocks:
             dw_pad = (o.pad_lo, o.pad_hi) if (self.circular or o.stride == 2 or fused_dw) else None
-            if pre is not None and not o.has_expand and not o.residual:
+            if stem_padded is not None:
+                block_in = None
+                mid_in_plain, mid_in_padded = None, stem_padded
+                stem_padded = None
+            elif pre is not None and not o.has_expand and not o.residual:
                 # block 0: the stem's pending bias + SiLU is applied straight into the depthwise conv's input
                 plain, padded, _unused = self._act(pre, pre_bias, pad=dw_pad)
                 block_in = None

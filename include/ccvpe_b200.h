@@ -174,6 +174,18 @@ int ccvpe_dwconv_bias_silu_nhwc(const void* x, int64_t x_sb, int64_t x_sh, int64
                                 const void* w, const void* bias, void* y, int B, int C, int K, int S,
                                 float* chan_sum, void* stream);
 
+/* Encoder stem (reference efficientnet_pytorch/model.py:296-297 in eval mode, BN folded; circular variant: the reference's
+ * models.py circular-padding patch of the ground encoder): 3x3 stride-2 conv over the fp32 NCHW image with the reference's
+ * static "same" padding (in_pad_lo / in_pad_hi zero rows and columns before / after the image; circular != 0 wraps the
+ * width instead of zero-filling it), + bias + SiLU:
+ *   out[b, ho + out_pad_lo, wo + out_pad_lo, co] = SiLU(bias[co] + sum_{ci,ky,kx} x[b,ci,2ho+ky-in_pad_lo,2wo+kx-in_pad_lo] * w[(ci,ky,kx), co])
+ * x: fp32 [B,3,H,W]; w: fp32 [27][CO] ordered (ci, ky, kx); bias fp32 [CO]; CO == 32;
+ * out: bf16 [B, Ho+out_pad_lo+out_pad_hi, Wo+out_pad_lo+out_pad_hi, CO], Ho = (H+in_pad_lo+in_pad_hi-3)/2+1 (Wo alike); the interior is
+ * written, and for circular != 0 also the wrap columns (the zero rows above / below are left untouched). */
+int ccvpe_stem_conv_silu_nhwc(const float* x, int B, int H, int W, const float* w, const float* bias, int CO,
+                              void* out, int in_pad_lo, int in_pad_hi, int out_pad_lo, int out_pad_hi, int circular,
+                              void* stream);
+
 /* Pointwise (1x1) convolution + bias + SiLU over channels-last bf16 pixels on the tcgen05 pipeline -- the MBConv expand
  * step and the encoder head (reference efficientnet_pytorch/model.py:100-106, 312-314 in eval mode, BN folded):
  *   out[b, h + pad_lo, w + pad_lo, n] = SiLU(sum_k x[(b,h,w), k] * w_nk[n, k] + bias[n])

@@ -498,3 +498,31 @@ def test_pointwise_silu_nhwc(cuda_device, B, H, W, K, N, lo, hi):
     border = out.clone()
     border[:, lo:lo + H, lo:lo + W, :] = 7.0
     assert bool((border == 7.0).all())
+
+
+@pytest.mark.parametrize("B,H,W,circ,olo,ohi", [(2, 64, 96, False, 1, 1), (2, 40, 72, True, 1, 1), (1, 31, 45, False, 0, 2),
+                                               (3, 16, 20, True, 2, 1)])
+def test_stem_conv_silu_nhwc(cuda_device, B, H, W, circ, olo, ohi):
+    """fused stem (3x3 s2 conv from the fp32 NCHW image + bias + SiLU -> padded bf16 NHWC, wrap columns) vs torch."""
+    g = _gen(17)
+    dev = cuda_device
+    x = torch.randn(B, 3, H, W, generator=g)
+    w = torch.randn(32, 3, 3, 3, generator=g) * 0.3
+    bias = torch.randn(32, generator=g)
+    lo, hi = 0, 1                                              # the reference's static "same" padding of a k3 s2 conv
+    xp = F.pad(F.pad(x, (lo, hi, 0, 0), mode="circular"), (0, 0, lo, hi)) if circ else F.pad(x, (lo, hi, lo, hi))
+    ref = F.silu(F.conv2d(xp, w, bias, stride=2)).permute(0, 2, 3, 1)            # [B,Ho,Wo,32]
+    Ho, Wo = ref.shape[1], ref.shape[2]
+    out = torch.zeros(B, Ho + olo + ohi, Wo + olo + ohi, 32, device=dev, dtype=torch.bfloat16)
+    cabi.stem_conv_silu_nhwc(x.to(dev), w.permute(1, 2, 3, 0).reshape(27, 32).contiguous().to(dev), bias.to(dev), out,
+                             lo, hi, olo, ohi, circ)
+    torch.cuda.synchronize()
+    got = out.float().cpu()
+    assert rel_err(got[:, olo:olo + Ho, olo:olo + Wo, :], ref) < 1e-2
+    assert bool((got[:, :olo] == 0).all()) and bool((got[:, olo + Ho:] == 0).all())          # zero rows untouched
+    if circ:
+        if olo:
+            assert torch.equal(got[:, olo:olo + Ho, :olo], got[:, olo:olo + Ho, Wo:Wo + olo])
+        assert torch.equal(got[:, olo:olo + Ho, olo + Wo:], got[:, olo:olo + Ho, olo:olo + ohi])
+    else:
+        assert bool((got[:, :, :olo] == 0).all()) and bool((got[:, :, olo + Wo:] == 0).all())
