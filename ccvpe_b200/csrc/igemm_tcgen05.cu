@@ -33,6 +33,7 @@ struct TcParams {
   int out_stride[4], extent[4];
   int pad_w, pad_h, pad_wp, pad_hp, pad_lo;   // MODE 3 only: rows are written into the interior of a padded image
   int epi_off;                                // byte offset of the epilogue staging tile behind the pipeline stages
+  int w_resident, w_off, w_blk;               // weights loaded once per CTA: offset of / bytes per K-block B tile
   EpiParams e;
 };
 
@@ -50,6 +51,7 @@ igemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
   __shared__ __align__(8) uint64_t bar_empty[TC_MAX_STAGES];
   __shared__ __align__(8) uint64_t bar_tmem_full[2];
   __shared__ __align__(8) uint64_t bar_tmem_empty[2];
+  __shared__ __align__(8) uint64_t bar_weights;
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(16) float s_bias[2][TC_MAX_N];
   __shared__ __align__(16) float s_r1w[2][TC_MAX_N];
@@ -70,6 +72,7 @@ igemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
       mbar_init(smem_u32(&bar_tmem_full[a]), 1);
       mbar_init(smem_u32(&bar_tmem_empty[a]), EPI_WARPS);
     }
+    mbar_init(smem_u32(&bar_weights), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0 && lane == 0) {
@@ -90,15 +93,45 @@ igemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  // Tile schedule.  Streaming mode: CTA c takes tiles c, c + grid, ... of the (m tile, n tile) grid, n fastest.  Resident
+  // mode (weights of ONE N tile stay in shared memory): CTA c owns N tile c % n_tiles_n and walks the m tiles
+  // c / n_tiles_n, + grid / n_tiles_n, ...  Either way `tile` below runs t0, t0 + tstep, ... < tend.
+  const bool res = p.w_resident != 0;
+  const int cta_nt = res ? (int)blockIdx.x % p.n_tiles_n : 0;
+  const int t0 = res ? (int)blockIdx.x / p.n_tiles_n : (int)blockIdx.x;
+  const int tstep = res ? (int)gridDim.x / p.n_tiles_n : (int)gridDim.x;
+  const int tend = res ? p.total_tiles / p.n_tiles_n : p.total_tiles;
+  const bool fixed_n = res || p.n_tiles_n == 1;     // the N tile never changes within this CTA
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp converged, single-lane issue via elect_one) =====================
     {
+      if (res && t0 < tend) {
+        // this CTA's N tile of the weight matrix stays in shared memory: one K-block B tile per (tap, source, block).
+        // Re-fetching it per tile would make every CTA hammer the same few L2 lines all the time.
+        if (elect_one()) {
+          const uint32_t bw = smem_u32(&bar_weights);
+          uint32_t bytes = 0;
+          for (int tap = 0; tap < p.taps; ++tap)
+            bytes += (uint32_t)(p.block_n * 2 * (p.nb0 * p.kw0 + p.nb1 * p.kw1));
+          mbar_arrive_expect_tx(bw, bytes);
+          int kb = 0;
+          for (int tap = 0; tap < p.taps; ++tap)
+            for (int src = 0; src < 2; ++src) {
+              const int nb = src ? p.nb1 : p.nb0, kw = src ? p.kw1 : p.kw0;
+              const int kbase = tap * (p.kpad0 + p.kpad1) + (src ? p.kpad0 : 0);
+              for (int cb = 0; cb < nb; ++cb, ++kb)
+                tma_load_2d(smem_base + p.w_off + kb * p.w_blk, src ? &p.tm_b1 : &p.tm_b0, bw, kbase + cb * kw,
+                            cta_nt * p.block_n);
+            }
+        }
+        __syncwarp();
+      }
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        int mt = tile / p.n_tiles_n;
-        const int nt = tile - mt * p.n_tiles_n;
+      for (int tile = t0; tile < tend; tile += tstep) {
+        int mt = fixed_n ? tile : tile / p.n_tiles_n;
+        const int nt = fixed_n ? cta_nt : tile - mt * p.n_tiles_n;
         int base[4];
 #pragma unroll
         for (int d = 0; d < 4; ++d) {
@@ -115,7 +148,7 @@ igemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
             const CUtensorMap* tm = src ? &p.tm_a1 : &p.tm_a0;
             const CUtensorMap* tmb = src ? &p.tm_b1 : &p.tm_b0;
             const int kbase = tap * (p.kpad0 + p.kpad1) + (src ? p.kpad0 : 0);   // column of this source in W[n][.]
-            const uint32_t tx = (uint32_t)((TC_BM + p.block_n) * kw * 2);
+            const uint32_t tx = (uint32_t)((TC_BM + (p.w_resident ? 0 : p.block_n)) * kw * 2);
             for (int cb = 0; cb < nb; ++cb) {
               mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
               if (elect_one()) {
@@ -126,7 +159,7 @@ igemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
                 if (p.a_rank == 2) tma_load_2d(a_dst, tm, full, cb * kw, c1);
                 else if (p.a_rank == 4) tma_load_4d(a_dst, tm, full, cb * kw, c1, c2, c3);
                 else tma_load_5d(a_dst, tm, full, cb * kw, c1, c2, c3, c4);
-                tma_load_2d(a_dst + p.a_bytes, tmb, full, kbase + cb * kw, n0);
+                if (!p.w_resident) tma_load_2d(a_dst + p.a_bytes, tmb, full, kbase + cb * kw, n0);
               }
               __syncwarp();
               if (++stage == p.stages) {
@@ -152,16 +185,22 @@ igemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
       const int tail0 = (p.c0 - (p.nb0 - 1) * p.kw0 + 15) >> 4, tail1 = p.nb1 ? (p.c1 - (p.nb1 - 1) * p.kw1 + 15) >> 4 : 0;
       const uint32_t lo_base = ((smem_base & 0x3FFFFu) >> 4) | (1u << 16);
       const uint32_t lo_stage = (uint32_t)stage_bytes >> 4, lo_b = (uint32_t)p.a_bytes >> 4;
+      const uint32_t lo_w = ((((smem_base + (uint32_t)p.w_off) & 0x3FFFFu) >> 4) | (1u << 16)), lo_wblk = (uint32_t)p.w_blk >> 4;
+      if (res && t0 < tend) {
+        mbar_wait(smem_u32(&bar_weights), 0);
+        tc_fence_after();
+      }
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      for (int tile = t0; tile < tend; tile += tstep, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
         mbar_wait(smem_u32(&bar_tmem_empty[acc]), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.block_n);
         uint32_t accumulate = 0;
+        uint32_t b_res = lo_w;                     // resident B tile of the next K block
         for (int tap = 0; tap < p.taps; ++tap) {
 #pragma unroll 1
           for (int src = 0; src < 2; ++src) {
@@ -175,7 +214,8 @@ igemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
               tc_fence_after();
               const uint32_t a_lo = lo_base + (uint32_t)stage * lo_stage;
               const uint64_t adesc = ((uint64_t)hi << 32) | a_lo;
-              const uint64_t bdesc = ((uint64_t)hi << 32) | (a_lo + lo_b);
+              const uint64_t bdesc = ((uint64_t)hi << 32) | (p.w_resident ? b_res : a_lo + lo_b);
+              b_res += lo_wblk;
               if (elect_one()) {
                 // k-th MMA: advance 16 bf16 = 32 bytes inside the swizzle row (+2 in the 16-byte address field)
                 umma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);
@@ -203,7 +243,6 @@ igemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
     const int half = (warp - 2) >> 2;                 // which interleaved set of 32-column chunks
     const int row = ew * 32 + lane;
     const int et = threadIdx.x - 64;                  // index within the epilogue group
-    const bool fixed_n = (p.n_tiles_n == 1);
     const bool has_r1 = (p.e.row_r1 != nullptr), has_rs = (p.e.row_scale != nullptr);
     // row -> output pixel of a tile
     // (shifts and masks only: this runs per tile in every epilogue thread)
@@ -234,25 +273,25 @@ igemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
       row_base = epi_row_base<MODE>(p.e, m_out);
     };
 
-    if (fixed_n) epi_stage_vectors(p.e, s_bias[0], s_r1w[0], s_off[0], 0, p.block_n, et, EPI_THREADS);
+    if (fixed_n) epi_stage_vectors(p.e, s_bias[0], s_r1w[0], s_off[0], cta_nt * p.block_n, p.block_n, et, EPI_THREADS);
     int m_glob, m_next = 0;
     int64_t row_base, base_next = 0;
     bool valid, valid_next = false;
     float rs = 1.f, r1 = 0.f, rs_next = 1.f, r1_next = 0.f;
-    if ((int)blockIdx.x < p.total_tiles) {
-      locate(blockIdx.x, m_next, valid_next, base_next);
+    if (t0 < tend) {
+      locate(t0, m_next, valid_next, base_next);
       if (valid_next) {
         if (has_rs) rs_next = __ldg(p.e.row_scale + m_next);
         if (has_r1) r1_next = __ldg(p.e.row_r1 + m_next);
       }
     }
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = t0; tile < tend; tile += tstep, ++it) {
       m_glob = m_next; valid = valid_next; rs = rs_next; r1 = r1_next; row_base = base_next;
       {  // prefetch the per-row scalars of the next tile: their latency hides behind this tile's epilogue
-        const int nxt = tile + gridDim.x;
+        const int nxt = tile + tstep;
         rs_next = 1.f; r1_next = 0.f; valid_next = false;
-        if (nxt < p.total_tiles) {
+        if (nxt < tend) {
           locate(nxt, m_next, valid_next, base_next);
           if (valid_next) {
             if (has_rs) rs_next = __ldg(p.e.row_scale + m_next);
@@ -260,7 +299,7 @@ igemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
           }
         }
       }
-      const int n0 = fixed_n ? 0 : (tile % p.n_tiles_n) * p.block_n;
+      const int n0 = (fixed_n ? cta_nt : tile % p.n_tiles_n) * p.block_n;
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       const int vb = fixed_n ? 0 : acc;
@@ -372,14 +411,21 @@ int igemm_tcgen05(const ccvpe_igemm_desc& d, cudaStream_t st, const TcOutPad* ou
   const bool shallow = p.taps * (d.c0 + d.c1) <= 256;
   const bool staged_out = d.out_dtype == CCVPE_BF16 && d.out_mode != 2;
   const int light_budget = 104 * 1024 - (staged_out ? TC_EPI_WARPS * EPI_WARP_STAGE_BYTES : 0);
-  int n_tiles_n = 0, block_n = 0, stage_bytes = 0;
+  int n_tiles_n = 0, block_n = 0, stage_bytes = 0, w_bytes = 0;
+  const int nkb_total = p.taps * (p.nb0 + p.nb1);
   auto plan = [&](int max_n) {
     n_tiles_n = (d.N + max_n - 1) / max_n;
     block_n = ((d.N + n_tiles_n - 1) / n_tiles_n + 15) / 16 * 16;
-    stage_bytes = p.a_bytes + (block_n * kw_max * 2 + 1023) / 1024 * 1024;   // A + B tile of the widest K block in use
+    const int b_blk = (block_n * kw_max * 2 + 1023) / 1024 * 1024;           // B tile of the widest K block in use
     p.tmem_cols = 32;
     while (p.tmem_cols < 2 * block_n) p.tmem_cols <<= 1;
-    return p.tmem_cols <= 256 && light_budget / stage_bytes >= 3;
+    // an N tile whose weights fit next to >= 4 A stages stays resident in its CTAs (loaded once per CTA)
+    p.w_resident = (p.tmem_cols <= 256 && nkb_total * b_blk <= 48 * 1024 &&
+                    (light_budget - nkb_total * b_blk) / p.a_bytes >= 4) ? 1 : 0;
+    p.w_blk = b_blk;
+    w_bytes = p.w_resident ? nkb_total * b_blk : 0;
+    stage_bytes = p.a_bytes + (p.w_resident ? 0 : b_blk);
+    return p.tmem_cols <= 256 && (light_budget - w_bytes) / stage_bytes >= 3;
   };
   bool light = plan(shallow ? 128 : TC_MAX_N);
   if (!light && shallow) {            // wide K blocks: narrower N tiles keep three pipeline stages within the light budget
@@ -389,10 +435,16 @@ int igemm_tcgen05(const ccvpe_igemm_desc& d, cudaStream_t st, const TcOutPad* ou
   p.n_tiles_n = n_tiles_n;
   p.block_n = block_n;
   p.stage_bytes = stage_bytes;
-  int stages = (light ? light_budget : TC_SMEM_BUDGET) / stage_bytes;
+  if (!light && p.w_resident) {   // (cannot happen with the thresholds above; keep the two modes consistent anyway)
+    p.w_resident = 0;
+    w_bytes = 0;
+    stage_bytes = p.a_bytes + p.w_blk;
+  }
+  int stages = (light ? light_budget - w_bytes : TC_SMEM_BUDGET) / stage_bytes;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   p.stages = stages;
-  p.epi_off = stages * stage_bytes;
+  p.w_off = stages * stage_bytes;
+  p.epi_off = p.w_off + w_bytes;
   const bool staged = light && staged_out;
   const int64_t ktot = (int64_t)p.taps * (p.kpad0 + p.kpad1);
 
@@ -486,9 +538,15 @@ int igemm_tcgen05(const ccvpe_igemm_desc& d, cudaStream_t st, const TcOutPad* ou
     p.pad_w = d.Wout; p.pad_h = d.Hout; p.pad_wp = out_pad->Wp; p.pad_hp = out_pad->Hp; p.pad_lo = out_pad->lo;
   }
 
-  const int smem = stages * stage_bytes + (staged ? (TC_EPI_WARPS * EPI_WARP_STAGE_BYTES) : 0) + 1024;
+  const int smem = stages * stage_bytes + w_bytes + (staged ? (TC_EPI_WARPS * EPI_WARP_STAGE_BYTES) : 0) + 1024;
   const int max_grid = (light ? 2 : 1) * sm_count();
-  const int grid = p.total_tiles < max_grid ? p.total_tiles : max_grid;
+  int grid = p.total_tiles < max_grid ? p.total_tiles : max_grid;
+  if (p.w_resident) {   // whole groups of n_tiles_n CTAs, one per N tile
+    int groups = max_grid / n_tiles_n;
+    if (groups > m_tiles) groups = m_tiles;
+    if (groups < 1) groups = 1;
+    grid = groups * n_tiles_n;
+  }
   cudaError_t attr_err = cudaSuccess;
 #define CCVPE_LAUNCH_IGEMM(MODE, R1, F32)                                                                              \
   do {                                                                                                                 \
