@@ -7,6 +7,7 @@
 // the TensorFlow-"same" / circular padding of the following depthwise conv costs no extra copy); the channel sums feed
 // the squeeze-excite gate, so the separate mean pass over the 6x-expanded activation disappears as well.
 // HBM-bound: one read + one write of the tensor, 16-byte accesses.
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -122,82 +123,147 @@ extern "C" int ccvpe_bias_silu_nhwc(const void* x, const void* bias, void* y, in
 // ---------------------------------------------------------------------------------------------------------------------
 namespace ccvpe {
 
-template <int K, int S>
-__global__ void __launch_bounds__(256)
+// packed fp32x2 helpers: Blackwell's FFMA2 does two fp32 FMAs per issued instruction, and a bf16x2 word widens to an
+// fp32 pair with one shift and one mask -- the loop below is issue-bound, so instruction count is what matters
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t bf16x2_to_f32x2(uint32_t v) {
+  return pack_f32x2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+}
+__device__ __forceinline__ float dw_tanh(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
+// V = channels per thread (8: 16-byte vectors; 4: 8-byte vectors -- half the registers, twice the resident warps, which
+// is what the latency-bound 5x5 layers need).
+template <int V> struct DwVec;
+template <> struct DwVec<8> { using type = uint4; };
+template <> struct DwVec<4> { using type = uint2; };
+template <int V>
+__device__ __forceinline__ void dw_widen(const typename DwVec<V>::type& q, uint64_t (&f)[V / 2]);
+template <>
+__device__ __forceinline__ void dw_widen<8>(const uint4& q, uint64_t (&f)[4]) {
+  f[0] = bf16x2_to_f32x2(q.x);
+  f[1] = bf16x2_to_f32x2(q.y);
+  f[2] = bf16x2_to_f32x2(q.z);
+  f[3] = bf16x2_to_f32x2(q.w);
+}
+template <>
+__device__ __forceinline__ void dw_widen<4>(const uint2& q, uint64_t (&f)[2]) {
+  f[0] = bf16x2_to_f32x2(q.x);
+  f[1] = bf16x2_to_f32x2(q.y);
+}
+
+template <int K, int S, int V>
+__global__ void __launch_bounds__(256, V == 8 ? 2 : 3)
 dwconv_bias_silu_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_sb, int64_t x_sh, int64_t x_sw,
                         const __nv_bfloat16* __restrict__ w, const __nv_bfloat16* __restrict__ bias,
-                        __nv_bfloat16* __restrict__ y, int Ho, int Wo, int C, int strips_per_block,
+                        __nv_bfloat16* __restrict__ y, int Ho, int Wo, int C, int CG, int strips_per_block,
                         float* __restrict__ chan_sum) {
+  using vec_t = typename DwVec<V>::type;
+  constexpr int P = V / 2;                           // fp32x2 pairs per thread
   constexpr int TW = 4;                              // outputs per thread along W
   constexpr int IW = (TW - 1) * S + K;               // input columns a strip touches
-  extern __shared__ __align__(16) float s_sum[];     // [C] channel sums, then the bf16 weights [K*K][C]
-  __nv_bfloat16* s_w = reinterpret_cast<__nv_bfloat16*>(s_sum + C);
-  const int G = C >> 3;
-  const int lanes = blockDim.x / G;
-  const int cg = threadIdx.x % G, pl = threadIdx.x / G;
+  // A block owns one image (blockIdx.y), one chunk of CG V-channel groups (blockIdx.z) and a range of strips
+  // (blockIdx.x): wide low-resolution layers are split over channels so that every block still has a whole image's worth
+  // of pixels to amortise its weight load over.
+  extern __shared__ __align__(16) float s_sum[];     // [CG*V] channel sums, then the chunk's fp32 weights [K*K][CG*V]
+  const int CC = CG * V;                             // channels of a full chunk
+  float* s_w = s_sum + CC;
+  const int G = C / V;
+  const int g0 = blockIdx.z * CG;                    // first channel group of this chunk
+  const int gn = min(CG, G - g0);                    // groups actually present in it
+  const int lanes = blockDim.x / CG;
+  const int cl = threadIdx.x % CG, pl = threadIdx.x / CG;
+  const int cg = g0 + cl;
+  const bool active = pl < lanes && cl < gn;
   const int b = blockIdx.y;
-  for (int i = threadIdx.x; i < (K * K * C) / 8; i += blockDim.x)
-    reinterpret_cast<uint4*>(s_w)[i] = __ldg(reinterpret_cast<const uint4*>(w) + i);
+  {  // weight prologue: 4 channels per item, four independent loads in flight per thread (it is pure latency otherwise,
+     // and the blocks of a wave all sit in it at the same time)
+    const int q4 = gn * V / 4, n_items = K * K * q4;
+#pragma unroll 1
+    for (int i0 = threadIdx.x; i0 < n_items; i0 += 4 * blockDim.x) {
+      uint2 v[4];
+      int dst[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * blockDim.x;
+        const int ii = i < n_items ? i : 0;
+        const int tap = ii / q4, c4 = ii - tap * q4;
+        v[u] = __ldg(reinterpret_cast<const uint2*>(w + (int64_t)tap * C + g0 * V) + c4);
+        dst[u] = i < n_items ? tap * CC + c4 * 4 : -1;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (dst[u] >= 0)
+          *reinterpret_cast<float4*>(s_w + dst[u]) =
+              make_float4(__uint_as_float(v[u].x << 16), __uint_as_float(v[u].x & 0xffff0000u),
+                          __uint_as_float(v[u].y << 16), __uint_as_float(v[u].y & 0xffff0000u));
+    }
+  }
   const int strips_row = (Wo + TW - 1) / TW;
   const int n_strips = Ho * strips_row;
   const int s_lo = blockIdx.x * strips_per_block;
   const int s_hi = min(n_strips, s_lo + strips_per_block);
-  for (int c = threadIdx.x; c < C; c += blockDim.x) s_sum[c] = 0.f;
+  for (int c = threadIdx.x; c < CC; c += blockDim.x) s_sum[c] = 0.f;
   __syncthreads();
-  float csum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  if (pl < lanes) {
-    float bv[8];
-    {
-      const uint4 q = *reinterpret_cast<const uint4*>(bias + cg * 8);
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+  float csum[V];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = __bfloat1622float2(h[j]);
-        bv[2 * j] = f.x;
-        bv[2 * j + 1] = f.y;
-      }
-    }
-    const __nv_bfloat16* xb = x + (int64_t)b * x_sb + cg * 8;
-    __nv_bfloat16* yb = y + (int64_t)b * Ho * Wo * C + cg * 8;
+  for (int j = 0; j < V; ++j) csum[j] = 0.f;
+  if (active) {
+    uint64_t bv[P];
+    dw_widen<V>(*reinterpret_cast<const vec_t*>(bias + cg * V), bv);
+    const __nv_bfloat16* xb = x + (int64_t)b * x_sb + cg * V;
+    __nv_bfloat16* yb = y + (int64_t)b * Ho * Wo * C + cg * V;
+    const float* wt = s_w + cl * V;
+    // columns beyond the padded buffer can only feed outputs >= Wo (never stored): clamp them to stay in bounds
+    const int iw_max = (Wo - 1) * S + K - 1;
+    const int sw = (int)x_sw;                         // (32-bit offsets: one IMAD.WIDE per load address)
     for (int sidx = s_lo + pl; sidx < s_hi; sidx += lanes) {
       const int ho = sidx / strips_row;
       const int wo0 = (sidx - ho * strips_row) * TW;
-      float acc[TW][8];
+      uint64_t acc[TW][P];
 #pragma unroll
       for (int t = 0; t < TW; ++t)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[t][j] = bv[j];
-      // columns beyond the padded buffer can only feed outputs >= Wo (never stored): clamp them to stay in bounds
-      const int iw_max = (Wo - 1) * S + K - 1;
+        for (int j = 0; j < P; ++j) acc[t][j] = bv[j];
+      const int ix_max = iw_max - wo0 * S;            // >= IW - 1 except on the right-most strip of a row
+      const __nv_bfloat16* xrow = xb + (int64_t)(ho * S) * x_sh + (int64_t)(wo0 * S) * x_sw;
 #pragma unroll 1
-      for (int ky = 0; ky < K; ++ky) {                // not unrolled: bounds the register footprint
-        const __nv_bfloat16* xrow = xb + (int64_t)(ho * S + ky) * x_sh;
-        uint4 xin[IW];                                // the row segment this strip needs, still packed bf16
+      for (int ky = 0; ky < K; ++ky, xrow += x_sh) {  // not unrolled: bounds the register footprint
+        vec_t xin[IW];                                // the row segment this strip needs, still packed bf16
 #pragma unroll
-        for (int ix = 0; ix < IW; ++ix) {
-          const int iw = min(wo0 * S + ix, iw_max);
-          xin[ix] = __ldg(reinterpret_cast<const uint4*>(xrow + (int64_t)iw * x_sw));
-        }
+        for (int ix = 0; ix < IW; ++ix)
+          xin[ix] = __ldg(reinterpret_cast<const vec_t*>(xrow + min(ix, ix_max) * sw));
+        uint64_t xf[IW][P];                           // widened lazily: at most TW columns are live at a time
 #pragma unroll
         for (int kx = 0; kx < K; ++kx) {
-          const uint4 wq = *reinterpret_cast<const uint4*>(s_w + ((ky * K + kx) * C + cg * 8));   // one weight vector per tap
-          const __nv_bfloat162* wh = reinterpret_cast<const __nv_bfloat162*>(&wq);
-          float wf[8];
+          uint64_t wv[P];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 f = __bfloat1622float2(wh[j]);
-            wf[2 * j] = f.x;
-            wf[2 * j + 1] = f.y;
+          for (int j = 0; j < P; j += 2) {
+            const float4 wq = *reinterpret_cast<const float4*>(wt + (ky * K + kx) * CC + 2 * j);
+            wv[j] = pack_f32x2(wq.x, wq.y);
+            wv[j + 1] = pack_f32x2(wq.z, wq.w);
           }
 #pragma unroll
           for (int t = 0; t < TW; ++t) {
-            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&xin[t * S + kx]);
+            const int ix = t * S + kx;
+            if (t == TW - 1 || kx < S) dw_widen<V>(xin[ix], xf[ix]);   // first use of this input column
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 f = __bfloat1622float2(h[j]);
-              acc[t][2 * j] = fmaf(f.x, wf[2 * j], acc[t][2 * j]);
-              acc[t][2 * j + 1] = fmaf(f.y, wf[2 * j + 1], acc[t][2 * j + 1]);
-            }
+            for (int j = 0; j < P; ++j) acc[t][j] = ffma2(xf[ix][j], wv[j], acc[t][j]);
           }
         }
       }
@@ -205,33 +271,35 @@ dwconv_bias_silu_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_sb, int64
       for (int t = 0; t < TW; ++t) {
         const int wo = wo0 + t;
         if (wo < Wo) {
-          uint4 q;
+          vec_t q;
           __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float a0 = acc[t][2 * j], a1 = acc[t][2 * j + 1];
-            a0 = __fdividef(a0, 1.f + __expf(-a0));
-            a1 = __fdividef(a1, 1.f + __expf(-a1));
+          for (int j = 0; j < P; ++j) {
+            float a0, a1;
+            unpack_f32x2(acc[t][j], a0, a1);
+            a0 *= 0.5f;                               // SiLU(a) = a * sigmoid(a) = h + h * tanh(h), h = a / 2: one MUFU
+            a1 *= 0.5f;
+            a0 = fmaf(a0, dw_tanh(a0), a0);
+            a1 = fmaf(a1, dw_tanh(a1), a1);
             h[j] = __floats2bfloat162_rn(a0, a1);
             const float2 r = __bfloat1622float2(h[j]);
             csum[2 * j] += r.x;
             csum[2 * j + 1] += r.y;
           }
-          *reinterpret_cast<uint4*>(yb + ((int64_t)ho * Wo + wo) * C) = q;
+          *reinterpret_cast<vec_t*>(yb + ((int64_t)ho * Wo + wo) * C) = q;
         }
       }
     }
   }
   if (chan_sum) {
-    if (pl < lanes) {
+    if (active) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(&s_sum[cg * 8 + j], csum[j]);
+      for (int j = 0; j < V; ++j) atomicAdd(&s_sum[cl * V + j], csum[j]);
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(chan_sum + (int64_t)b * C + c, s_sum[c]);
+    for (int c = threadIdx.x; c < gn * V; c += blockDim.x) atomicAdd(chan_sum + (int64_t)b * C + g0 * V + c, s_sum[c]);
   }
 }
-
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Encoder stem: 3x3 stride-2 convolution over the fp32 NCHW image (3 channels, TensorFlow-"same" zero padding, optionally
@@ -380,34 +448,61 @@ extern "C" int ccvpe_dwconv_bias_silu_nhwc(const void* x, int64_t x_sb, int64_t 
   CCVPE_REQUIRE((K == 3 || K == 5) && (S == 1 || S == 2) && Hp >= K && Wp >= K, "ccvpe_dwconv_bias_silu_nhwc: K=%d S=%d Hp=%d Wp=%d unsupported", K, S, Hp, Wp);
   CCVPE_REQUIRE(aligned16(x) && aligned16(w) && aligned16(bias) && aligned16(y), "ccvpe_dwconv_bias_silu_nhwc: pointers must be 16-byte aligned");
   CCVPE_REQUIRE(x_sb % 8 == 0 && x_sh % 8 == 0 && x_sw % 8 == 0, "ccvpe_dwconv_bias_silu_nhwc: input strides must be multiples of 8");
+  CCVPE_REQUIRE(x_sw > 0 && x_sw * 16 < (1LL << 31), "ccvpe_dwconv_bias_silu_nhwc: pixel stride out of range");
   const int Ho = (Hp - K) / S + 1, Wo = (Wp - K) / S + 1;
-  const int G = C / 8, lanes = 256 / G;
+  // V = channels per thread
+  static const int force_v = getenv("CCVPE_DW_V") ? atoi(getenv("CCVPE_DW_V")) : 0;
+  const int V = force_v ? force_v : 8;   // (measured: 4 channels per thread gains nothing, the loop is issue-bound)
+  const int G = C / V;
+  // channel chunking: up to 256 channels a block takes them all; wider layers are cut into chunks of CG groups, CG the
+  // largest divisor of G giving 64..128 channels (else 128 with a partial last chunk), which multiplies the number of
+  // blocks on the low-resolution layers and keeps a block's weight tile small
+  int CG = G;
+  if (C > 256) {
+    CG = 128 / V;
+    for (int c = 128 / V; c >= 64 / V; --c)
+      if (G % c == 0) {
+        CG = c;
+        break;
+      }
+  }
+  const int chunks = (G + CG - 1) / CG;
+  const int lanes = 256 / CG;
   const int64_t n_strips = (int64_t)Ho * ((Wo + 3) / 4);
-  int blocks_x = (int)((8LL * sm_count() + B - 1) / B);
+  int blocks_x = (int)((8LL * sm_count() + (int64_t)B * chunks - 1) / ((int64_t)B * chunks));
   int64_t spb = (n_strips + blocks_x - 1) / blocks_x;
   spb = (spb + lanes - 1) / lanes * lanes;
   if (spb < lanes) spb = lanes;
   blocks_x = (int)((n_strips + spb - 1) / spb);
-  const dim3 grid(blocks_x, B);
-  const size_t sm = C * sizeof(float) + (size_t)K * K * C * 2;
+  CCVPE_REQUIRE(chunks <= 65535 && B <= 65535, "ccvpe_dwconv_bias_silu_nhwc: grid too large");
+  const dim3 grid(blocks_x, B, chunks);
+  const size_t sm = (size_t)CG * V * sizeof(float) * (1 + K * K);
   CCVPE_REQUIRE(sm <= 96 * 1024, "ccvpe_dwconv_bias_silu_nhwc: K*K*C too large for shared memory");
   static thread_local bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(dwconv_bias_silu_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    cudaFuncSetAttribute(dwconv_bias_silu_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    cudaFuncSetAttribute(dwconv_bias_silu_kernel<5, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    cudaFuncSetAttribute(dwconv_bias_silu_kernel<5, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+#define CCVPE_DW_ATTR(KK, SS, VV) \
+  cudaFuncSetAttribute(dwconv_bias_silu_kernel<KK, SS, VV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)
+    CCVPE_DW_ATTR(3, 1, 8); CCVPE_DW_ATTR(3, 2, 8); CCVPE_DW_ATTR(5, 1, 8); CCVPE_DW_ATTR(5, 2, 8);
+    CCVPE_DW_ATTR(3, 1, 4); CCVPE_DW_ATTR(3, 2, 4); CCVPE_DW_ATTR(5, 1, 4); CCVPE_DW_ATTR(5, 2, 4);
+#undef CCVPE_DW_ATTR
     attr_set = true;
   }
   cudaStream_t st = (cudaStream_t)stream;
-#define CCVPE_DW(KK, SS)                                                                                              \
-  dwconv_bias_silu_kernel<KK, SS><<<grid, 256, sm, st>>>((const __nv_bfloat16*)x, x_sb, x_sh, x_sw,                   \
-                                                         (const __nv_bfloat16*)w, (const __nv_bfloat16*)bias,         \
-                                                         (__nv_bfloat16*)y, Ho, Wo, C, (int)spb, chan_sum)
-  if (K == 3 && S == 1) CCVPE_DW(3, 1);
-  else if (K == 3 && S == 2) CCVPE_DW(3, 2);
-  else if (K == 5 && S == 1) CCVPE_DW(5, 1);
-  else CCVPE_DW(5, 2);
+#define CCVPE_DW(KK, SS, VV)                                                                                          \
+  dwconv_bias_silu_kernel<KK, SS, VV><<<grid, 256, sm, st>>>((const __nv_bfloat16*)x, x_sb, x_sh, x_sw,               \
+                                                             (const __nv_bfloat16*)w, (const __nv_bfloat16*)bias,     \
+                                                             (__nv_bfloat16*)y, Ho, Wo, C, CG, (int)spb, chan_sum)
+  if (V == 8) {
+    if (K == 3 && S == 1) CCVPE_DW(3, 1, 8);
+    else if (K == 3 && S == 2) CCVPE_DW(3, 2, 8);
+    else if (K == 5 && S == 1) CCVPE_DW(5, 1, 8);
+    else CCVPE_DW(5, 2, 8);
+  } else {
+    if (K == 3 && S == 1) CCVPE_DW(3, 1, 4);
+    else if (K == 3 && S == 2) CCVPE_DW(3, 2, 4);
+    else if (K == 5 && S == 1) CCVPE_DW(5, 1, 4);
+    else CCVPE_DW(5, 2, 4);
+  }
 #undef CCVPE_DW
   CCVPE_LAUNCH_CHECK("dwconv_bias_silu_kernel");
   return CCVPE_OK;

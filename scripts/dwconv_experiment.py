@@ -1,0 +1,23 @@
+import os, sys, torch
+sys.path.insert(0, "/root/repo")
+from ccvpe_b200 import cabi
+dev = torch.device("cuda")
+flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+def timeit(fn):
+    for _ in range(3): fn()
+    torch.cuda.synchronize(); ms=[]
+    for _ in range(5):
+        flush.zero_(); e0,e1=torch.cuda.Event(enable_timing=True),torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize(); ms.append(e0.elapsed_time(e1))
+    return min(ms)
+for (B,H,W,C,K,S) in [(64,64,64,240,5,1),(64,32,32,672,5,1),(64,128,128,144,3,1)]:
+    lo=hi=(K-1)//2
+    buf = torch.randn(B, H+lo+hi, W+lo+hi, C, device=dev).to(torch.bfloat16)
+    wt = (torch.randn(K*K, C, device=dev)*0.3).to(torch.bfloat16); bias=torch.randn(C,device=dev).to(torch.bfloat16)
+    y = torch.empty(B,H,W,C,device=dev,dtype=torch.bfloat16); sums=torch.zeros(B,C,device=dev)
+    t_full = timeit(lambda: cabi.dwconv_bias_silu_nhwc(buf, wt, bias, y, K, S, sums))
+    same_row = buf[:, :1].expand(B, H+lo+hi, W+lo+hi, C)          # every input row is row 0 of the image: no vertical L2 re-reads
+    t_row = timeit(lambda: cabi.dwconv_bias_silu_nhwc(same_row, wt, bias, y, K, S, sums))
+    one_img = buf[:1].expand(B, H+lo+hi, W+lo+hi, C)             # all images alias image 0: input is L2 resident, same access pattern
+    t_img = timeit(lambda: cabi.dwconv_bias_silu_nhwc(one_img, wt, bias, y, K, S, sums))
+    print(f"C={C} k{K}: full {t_full:.3f} ms | same-row input {t_row:.3f} ms | single aliased image {t_img:.3f} ms")
