@@ -21,7 +21,7 @@ EXPORTED_SYMBOLS = (
     "ccvpe_grd_descriptor", "ccvpe_grd_descriptors", "ccvpe_igemm", "ccvpe_igemm_plan", "ccvpe_match_scratch_elems", "ccvpe_match_level",
     "ccvpe_softmax_scratch_elems", "ccvpe_softmax_heatmap", "ccvpe_ori_normalize",
     "ccvpe_pose_scratch_bytes", "ccvpe_pose_decode", "ccvpe_bias_silu_nhwc", "ccvpe_dwconv_bias_silu_nhwc",
-    "ccvpe_pointwise_silu_nhwc", "ccvpe_stem_conv_silu_nhwc",
+    "ccvpe_pointwise_silu_nhwc", "ccvpe_stem_conv_silu_nhwc", "ccvpe_se_gate_scale",
 )
 
 
@@ -113,6 +113,8 @@ def load() -> C.CDLL:
     lib.ccvpe_stem_conv_silu_nhwc.restype = C.c_int
     lib.ccvpe_stem_conv_silu_nhwc.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                               C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.ccvpe_se_gate_scale.restype = C.c_int
+    lib.ccvpe_se_gate_scale.argtypes = [C.c_void_p, C.c_float] + [C.c_void_p] * 6 + [C.c_int] * 4 + [C.c_void_p]
     if lib.ccvpe_abi_version() != 1:
         raise CcvpeError("libccvpe_b200.so ABI version mismatch")
     _lib = lib
@@ -313,3 +315,20 @@ def stem_conv_silu_nhwc(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, ou
     _check(load().ccvpe_stem_conv_silu_nhwc(_ptr(x), B, H, W, _ptr(w.contiguous()), _ptr(bias), CO, _ptr(out), in_pad_lo,
                                             in_pad_hi, out_pad_lo, out_pad_hi, 1 if circular else 0, _stream()),
            "ccvpe_stem_conv_silu_nhwc")
+
+
+def se_gate_scale(chan_sum: torch.Tensor, inv_hw: float, w_red: torch.Tensor, b_red: torch.Tensor, w_se: torch.Tensor,
+                  b_se: torch.Tensor, w_proj: torch.Tensor, wg: torch.Tensor):
+    """wg[b] = w_proj * diag(sigmoid(w_se SiLU(w_red mean_b + b_red) + b_se)), mean_b = chan_sum[b] * inv_hw.
+    chan_sum fp32 [B, mid]; weights / biases contiguous bf16; wg contiguous bf16 [B, cout, mid]."""
+    _require_cuda(chan_sum, w_red, b_red, w_se, b_se, w_proj, wg)
+    B, mid = chan_sum.shape
+    R, cout = w_red.shape[0], w_proj.shape[0]
+    for t in (w_red, b_red, w_se, b_se, w_proj, wg):
+        if t.dtype != torch.bfloat16 or not t.is_contiguous():
+            raise CcvpeError("se_gate_scale: weights, biases and wg must be contiguous bf16")
+    if chan_sum.dtype != torch.float32 or not chan_sum.is_contiguous() or tuple(wg.shape) != (B, cout, mid) \
+            or tuple(w_red.shape) != (R, mid) or tuple(w_se.shape) != (mid, R) or tuple(w_proj.shape) != (cout, mid):
+        raise CcvpeError("se_gate_scale: shape / dtype mismatch")
+    _check(load().ccvpe_se_gate_scale(_ptr(chan_sum), C.c_float(inv_hw), _ptr(w_red), _ptr(b_red), _ptr(w_se), _ptr(b_se),
+                                      _ptr(w_proj), _ptr(wg), B, mid, R, cout, _stream()), "ccvpe_se_gate_scale")

@@ -388,9 +388,96 @@ stem_conv_silu_kernel(const float* __restrict__ x, const float* __restrict__ w, 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Squeeze-excite gate folded into the projection weights, one launch per MBConv block:
+//     mean[b, m]   = chan_sum[b, m] * inv_hw
+//     h[b, r]      = SiLU(b_red[r] + sum_m w_red[r, m] * mean[b, m])
+//     g[b, m]      = sigmoid(b_se[m] + sum_r w_se[m, r] * h[b, r])
+//     wg[b, c, m]  = w_proj[c, m] * g[b, m]                (the B operand of the per-image projection GEMM)
+// Replaces seven small PyTorch launches per block (div, cast, two addmm, silu, sigmoid, mul).  fp32 math, bf16 in / out.
+// grid (B, row chunks): every block recomputes its image's gate (two tiny mat-vecs) and scales its rows of w_proj.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+se_gate_scale_kernel(const float* __restrict__ chan_sum, float inv_hw, const __nv_bfloat16* __restrict__ w_red,
+                     const __nv_bfloat16* __restrict__ b_red, const __nv_bfloat16* __restrict__ w_se,
+                     const __nv_bfloat16* __restrict__ b_se, const __nv_bfloat16* __restrict__ w_proj,
+                     __nv_bfloat16* __restrict__ wg, int mid, int R, int cout, int rows_per_block) {
+  extern __shared__ __align__(16) float s_se[];      // mean[mid] (later g[mid]), h[R]
+  float* s_mean = s_se;
+  float* s_h = s_se + mid;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int m = tid; m < mid; m += blockDim.x) s_mean[m] = chan_sum[(int64_t)b * mid + m] * inv_hw;
+  __syncthreads();
+  for (int r = warp; r < R; r += 8) {                 // one warp per reduced channel, 8 bf16 per lane per step
+    const __nv_bfloat16* wr = w_red + (int64_t)r * mid;
+    float acc = 0.f;
+    for (int m0 = lane * 8; m0 < mid; m0 += 256) {
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(wr + m0));
+      const __nv_bfloat162* hq = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(hq[j]);
+        acc = fmaf(f.x, s_mean[m0 + 2 * j], acc);
+        acc = fmaf(f.y, s_mean[m0 + 2 * j + 1], acc);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      const float v = acc + __bfloat162float(b_red[r]);
+      s_h[r] = __fdividef(v, 1.f + __expf(-v));
+    }
+  }
+  __syncthreads();
+  for (int m = tid; m < mid; m += blockDim.x) {       // gate: one channel per thread, R (<= 48) terms
+    const __nv_bfloat16* ws = w_se + (int64_t)m * R;
+    float acc = __bfloat162float(b_se[m]);
+    for (int r = 0; r < R; ++r) acc = fmaf(__bfloat162float(ws[r]), s_h[r], acc);
+    s_mean[m] = __fdividef(1.f, 1.f + __expf(-acc));  // (each thread overwrites only the means it owns)
+  }
+  __syncthreads();
+  const int c_lo = blockIdx.y * rows_per_block, c_hi = min(cout, c_lo + rows_per_block);
+  const int vec_per_row = mid >> 3;
+  const int total = (c_hi - c_lo) * vec_per_row;
+  const uint4* src = reinterpret_cast<const uint4*>(w_proj + (int64_t)c_lo * mid);
+  uint4* dst = reinterpret_cast<uint4*>(wg + ((int64_t)b * cout + c_lo) * mid);
+  for (int i = tid; i < total; i += blockDim.x) {
+    const int m0 = (i % vec_per_row) * 8;
+    uint4 q = __ldg(src + i);
+    __nv_bfloat162* hq = reinterpret_cast<__nv_bfloat162*>(&q);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __bfloat1622float2(hq[j]);
+      hq[j] = __floats2bfloat162_rn(f.x * s_mean[m0 + 2 * j], f.y * s_mean[m0 + 2 * j + 1]);
+    }
+    dst[i] = q;
+  }
+}
+
 int igemm_tcgen05(const ccvpe_igemm_desc& d, cudaStream_t st, const TcOutPad* out_pad);  // igemm_tcgen05.cu
 
 }  // namespace ccvpe
+
+extern "C" int ccvpe_se_gate_scale(const float* chan_sum, float inv_hw, const void* w_red, const void* b_red,
+                                   const void* w_se, const void* b_se, const void* w_proj, void* wg, int B, int mid,
+                                   int R, int cout, void* stream) {
+  using namespace ccvpe;
+  CCVPE_REQUIRE(chan_sum && w_red && b_red && w_se && b_se && w_proj && wg, "ccvpe_se_gate_scale: null pointer");
+  CCVPE_REQUIRE(B > 0 && B <= 65535 * 32 && mid > 0 && mid % 8 == 0 && R > 0 && cout > 0,
+                "ccvpe_se_gate_scale: bad shape B=%d mid=%d R=%d cout=%d", B, mid, R, cout);
+  CCVPE_REQUIRE(aligned16(w_red) && aligned16(w_proj) && aligned16(wg), "ccvpe_se_gate_scale: pointers must be 16-byte aligned");
+  int rows = 65536 / mid;
+  if (rows < 8) rows = 8;
+  if (rows > cout) rows = cout;
+  const dim3 grid(B, (cout + rows - 1) / rows);
+  const size_t sm = (size_t)(mid + R) * sizeof(float);
+  CCVPE_REQUIRE(sm <= 48 * 1024, "ccvpe_se_gate_scale: mid too large");
+  se_gate_scale_kernel<<<grid, 256, sm, (cudaStream_t)stream>>>(
+      chan_sum, inv_hw, (const __nv_bfloat16*)w_red, (const __nv_bfloat16*)b_red, (const __nv_bfloat16*)w_se,
+      (const __nv_bfloat16*)b_se, (const __nv_bfloat16*)w_proj, (__nv_bfloat16*)wg, mid, R, cout, rows);
+  CCVPE_LAUNCH_CHECK("se_gate_scale_kernel");
+  return CCVPE_OK;
+}
 
 extern "C" int ccvpe_stem_conv_silu_nhwc(const float* x, int B, int H, int W, const float* w, const float* bias, int CO,
                                          void* out, int in_pad_lo, int in_pad_hi, int out_pad_lo, int out_pad_hi,

@@ -100,6 +100,7 @@ class FastEncoder:
         self.head_w_nk = cabi.pad_k_blocks(self.head_w)
         self.head_b_f32 = b.to(device=dev, dtype=torch.float32).contiguous()
         self._buffers: Dict[tuple, torch.Tensor] = {}
+        self._mid_total = sum(o.mid for o in self.blocks)
         self.keep = set(range(len(self.blocks)))        # block outputs materialised by extract_features_multiscale
 
     # -- padded staging buffers (borders zeroed once, interior rewritten on every use) ---------------------------
@@ -176,6 +177,9 @@ class FastEncoder:
             pre_bias = self.stem_b
         cur = None                                                                   # activated NHWC tensor
         outs: List[torch.Tensor] = []
+        # squeeze-excite channel sums of all blocks: one zero fill per forward instead of one per block
+        sums_ws = torch.zeros(x.shape[0] * self._mid_total, dtype=torch.float32, device=x.device) if fused_dw else None
+        sums_off = 0
         for o in self.blocks:
             dw_pad = (o.pad_lo, o.pad_hi) if (self.circular or o.stride == 2 or fused_dw) else None
             if stem_padded is not None:
@@ -220,7 +224,8 @@ class FastEncoder:
                 Bp, Hp, Wp, _ = xp.shape
                 Ho, Wo = (Hp - o.kernel) // o.stride + 1, (Wp - o.kernel) // o.stride + 1
                 d = torch.empty((Bp, Ho, Wo, o.mid), dtype=dt, device=xp.device)
-                sums = torch.zeros((Bp, o.mid), dtype=torch.float32, device=xp.device)
+                sums = sums_ws[sums_off:sums_off + Bp * o.mid].view(Bp, o.mid)
+                sums_off += Bp * o.mid
                 cabi.dwconv_bias_silu_nhwc(xp, o.w_dw_taps, o.b_dw, d, o.kernel, o.stride, sums)
             else:
                 if mid_in_padded is not None:
@@ -231,9 +236,13 @@ class FastEncoder:
                 d, _unused, sums = self._act(d.permute(0, 2, 3, 1), o.b_dw, want_sum=True)  # [B,Ho,Wo,mid] + SE squeeze
             Bo, Ho, Wo, _ = d.shape
             # squeeze-excite gate folded into the projection weights
-            sq = (sums / float(Ho * Wo)).to(dt)                                      # [B, mid]
-            g = torch.sigmoid(F.linear(F.silu(F.linear(sq, o.w_red, o.b_red)), o.w_se, o.b_se))   # [B, mid]
-            wg = o.w_proj.unsqueeze(0) * g.unsqueeze(1)                              # [B, cout, mid]
+            if fused_dw:
+                wg = torch.empty((Bo, o.cout, o.mid), dtype=dt, device=d.device)
+                cabi.se_gate_scale(sums, 1.0 / float(Ho * Wo), o.w_red, o.b_red, o.w_se, o.b_se, o.w_proj, wg)
+            else:
+                sq = (sums / float(Ho * Wo)).to(dt)                                  # [B, mid]
+                g = torch.sigmoid(F.linear(F.silu(F.linear(sq, o.w_red, o.b_red)), o.w_se, o.b_se))   # [B, mid]
+                wg = o.w_proj.unsqueeze(0) * g.unsqueeze(1)                          # [B, cout, mid]
             dm = d.reshape(Bo, Ho * Wo, o.mid)
             if o.residual:                                                           # residual add = beta 1 of the GEMM
                 y = torch.baddbmm(block_in.reshape(Bo, Ho * Wo, o.cout), dm, wg.transpose(1, 2))

@@ -186,6 +186,14 @@ int ccvpe_stem_conv_silu_nhwc(const float* x, int B, int H, int W, const float* 
                               void* out, int in_pad_lo, int in_pad_hi, int out_pad_lo, int out_pad_hi, int circular,
                               void* stream);
 
+/* Squeeze-excite gate folded into the projection weights (reference efficientnet_pytorch/model.py:113-121 in eval mode):
+ *   mean = chan_sum * inv_hw;  h = SiLU(w_red mean + b_red);  g = sigmoid(w_se h + b_se);  wg[b] = w_proj * diag(g[b])
+ * chan_sum fp32 [B, mid] (from ccvpe_dwconv_bias_silu_nhwc); w_red bf16 [R, mid]; b_red bf16 [R]; w_se bf16 [mid, R];
+ * b_se bf16 [mid]; w_proj bf16 [cout, mid]; wg bf16 [B, cout, mid] = the per-image B operand of the projection GEMM
+ * (W (g . x) == (W diag(g)) x, so the broadcast multiply over the expanded activation never happens).  mid % 8 == 0. */
+int ccvpe_se_gate_scale(const float* chan_sum, float inv_hw, const void* w_red, const void* b_red, const void* w_se,
+                        const void* b_se, const void* w_proj, void* wg, int B, int mid, int R, int cout, void* stream);
+
 /* Pointwise (1x1) convolution + bias + SiLU over channels-last bf16 pixels on the tcgen05 pipeline -- the MBConv expand
  * step and the encoder head (reference efficientnet_pytorch/model.py:100-106, 312-314 in eval mode, BN folded):
  *   out[b, h + pad_lo, w + pad_lo, n] = SiLU(sum_k x[(b,h,w), k] * w_nk[n, k] + bias[n])

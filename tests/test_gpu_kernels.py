@@ -526,3 +526,25 @@ def test_stem_conv_silu_nhwc(cuda_device, B, H, W, circ, olo, ohi):
         assert torch.equal(got[:, olo:olo + Ho, olo + Wo:], got[:, olo:olo + Ho, olo:olo + ohi])
     else:
         assert bool((got[:, :, :olo] == 0).all()) and bool((got[:, :, olo + Wo:] == 0).all())
+
+
+@pytest.mark.parametrize("B,mid,R,cout", [(3, 96, 4, 24), (2, 1152, 48, 320), (5, 240, 10, 80), (1, 32, 8, 16)])
+def test_se_gate_scale(cuda_device, B, mid, R, cout):
+    """fused squeeze-excite gate + projection-weight scaling vs torch (fp32 math on bf16 parameters)."""
+    g = _gen(18)
+    dev = cuda_device
+    hw = 77
+    sums = torch.randn(B, mid, generator=g) * hw * 0.5
+    w_red = (torch.randn(R, mid, generator=g) / math.sqrt(mid)).to(torch.bfloat16)
+    b_red = torch.randn(R, generator=g).to(torch.bfloat16)
+    w_se = (torch.randn(mid, R, generator=g) / math.sqrt(R)).to(torch.bfloat16)
+    b_se = torch.randn(mid, generator=g).to(torch.bfloat16)
+    w_proj = torch.randn(cout, mid, generator=g).to(torch.bfloat16)
+    mean = sums / hw
+    h = F.silu(mean @ w_red.float().t() + b_red.float())
+    gate = torch.sigmoid(h @ w_se.float().t() + b_se.float())
+    ref = w_proj.float().unsqueeze(0) * gate.unsqueeze(1)
+    wg = torch.empty(B, cout, mid, device=dev, dtype=torch.bfloat16)
+    cabi.se_gate_scale(sums.to(dev), 1.0 / hw, w_red.to(dev), b_red.to(dev), w_se.to(dev), b_se.to(dev), w_proj.to(dev), wg)
+    torch.cuda.synchronize()
+    assert rel_err(wg.float(), ref) < 1e-2
