@@ -319,8 +319,9 @@ def stem_conv_silu_nhwc(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, ou
 
 def se_gate_scale(chan_sum: torch.Tensor, inv_hw: float, w_red: torch.Tensor, b_red: torch.Tensor, w_se: torch.Tensor,
                   b_se: torch.Tensor, w_proj: torch.Tensor, wg: torch.Tensor):
-    """wg[b] = w_proj * diag(sigmoid(w_se SiLU(w_red mean_b + b_red) + b_se)), mean_b = chan_sum[b] * inv_hw.
-    chan_sum fp32 [B, mid]; weights / biases contiguous bf16; wg contiguous bf16 [B, cout, mid]."""
+    """wg[b] = w_proj * diag(sigmoid(w_se^T SiLU(w_red mean_b + b_red) + b_se)), mean_b = chan_sum[b] * inv_hw.
+    chan_sum fp32 [B, mid]; w_red [R, mid]; w_se [R, mid] (the excite weights transposed); contiguous bf16;
+    wg contiguous bf16 [B, cout, mid]."""
     _require_cuda(chan_sum, w_red, b_red, w_se, b_se, w_proj, wg)
     B, mid = chan_sum.shape
     R, cout = w_red.shape[0], w_proj.shape[0]
@@ -328,7 +329,7 @@ def se_gate_scale(chan_sum: torch.Tensor, inv_hw: float, w_red: torch.Tensor, b_
         if t.dtype != torch.bfloat16 or not t.is_contiguous():
             raise CcvpeError("se_gate_scale: weights, biases and wg must be contiguous bf16")
     if chan_sum.dtype != torch.float32 or not chan_sum.is_contiguous() or tuple(wg.shape) != (B, cout, mid) \
-            or tuple(w_red.shape) != (R, mid) or tuple(w_se.shape) != (mid, R) or tuple(w_proj.shape) != (cout, mid):
+            or tuple(w_red.shape) != (R, mid) or tuple(w_se.shape) != (R, mid) or tuple(w_proj.shape) != (cout, mid):
         raise CcvpeError("se_gate_scale: shape / dtype mismatch")
     _check(load().ccvpe_se_gate_scale(_ptr(chan_sum), C.c_float(inv_hw), _ptr(w_red), _ptr(b_red), _ptr(w_se), _ptr(b_se),
                                       _ptr(w_proj), _ptr(wg), B, mid, R, cout, _stream()), "ccvpe_se_gate_scale")

@@ -40,7 +40,9 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm,
       : "memory");
 }
 
-template <int MODE, bool HAS_R1, bool OUT_F32>
+// STAGE_OUT: bf16 rows leave through per-warp staging tiles (tiles of >= 32 columns; for 16-column tiles the direct
+// 32-byte stores measure faster, and compiling both paths into one kernel spills).
+template <int MODE, bool HAS_R1, bool OUT_F32, bool STAGE_OUT>
 __global__ void __launch_bounds__(RING_THREADS, 3) conv_ring_tcgen05_kernel(const __grid_constant__ RingParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[RING_MAX_DEPTH];
@@ -52,6 +54,10 @@ __global__ void __launch_bounds__(RING_THREADS, 3) conv_ring_tcgen05_kernel(cons
   __shared__ __align__(16) float s_bias[TC_MAX_N];
   __shared__ __align__(16) float s_r1w[TC_MAX_N];
   __shared__ int s_off[TC_MAX_N / 8];
+  // bf16 rows leave through per-warp staging tiles (coalesced copy-out, see epi_store_row_staged)
+  constexpr bool STAGED = STAGE_OUT && !OUT_F32 && MODE != 2;
+  __shared__ __align__(16) uint8_t s_stage[STAGED ? 4 * EPI_WARP_STAGE_BYTES : 16];
+  __shared__ int64_t s_rowbase[STAGED ? TC_BM : 1];
   __shared__ __align__(16) uint4 s_blk[4];   // per K block: descriptor offsets (16-byte units) for the MMA issuer
 
   const int warp = threadIdx.x >> 5;
@@ -284,11 +290,14 @@ __global__ void __launch_bounds__(RING_THREADS, 3) conv_ring_tcgen05_kernel(cons
         mbar_wait(smem_u32(&bar_tmem_full[acc]), acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * p.block_n);
-        epi_store_row<MODE, HAS_R1, OUT_F32>(p.e, taddr, 0, p.block_n, 0, true, m_glob, epi_row_base<MODE>(p.e, m_glob),
-                                             rs, r1, s_bias, s_r1w, s_off, 1);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty[acc]));
+        if (STAGED) {
+          epi_store_row_staged<MODE, HAS_R1>(p.e, taddr, 0, 1, p.block_n, 0, true, epi_row_base<MODE>(p.e, m_glob), rs, r1,
+                                             s_bias, s_r1w, s_off, smem_u32(&bar_tmem_empty[acc]),
+                                             s_stage + ew * EPI_WARP_STAGE_BYTES, s_rowbase + 32 * ew);
+        } else {
+          epi_store_row<MODE, HAS_R1, OUT_F32>(p.e, taddr, 0, p.block_n, 0, true, m_glob, epi_row_base<MODE>(p.e, m_glob),
+                                               rs, r1, s_bias, s_r1w, s_off, 1, smem_u32(&bar_tmem_empty[acc]));
+        }
       }
     }
   }
@@ -303,6 +312,10 @@ __global__ void __launch_bounds__(RING_THREADS, 3) conv_ring_tcgen05_kernel(cons
 
 // ---- host side ---------------------------------------------------------------------------------------------------
 static int round1k(int v) { return (v + 1023) / 1024 * 1024; }
+
+static bool ring_stages_output(const ccvpe_igemm_desc& d) {
+  return d.out_dtype == CCVPE_BF16 && d.out_mode != 2 && d.N >= 32;
+}
 
 static bool ring_plan(const ccvpe_igemm_desc& d, RingParams* p) {
   if (d.dtype != CCVPE_BF16 || !d.w_nk) return false;
@@ -335,10 +348,12 @@ static bool ring_plan(const ccvpe_igemm_desc& d, RingParams* p) {
   p->depth = depth > RING_MAX_DEPTH ? RING_MAX_DEPTH : depth;
   // prefer a shallower ring if that lets two CTAs (two MMA issuers, two producers, eight epilogue warps) share an SM:
   // the narrow levels are bound by single-thread issue latency, not by pipeline depth
+  // static shared memory + alignment slack of one CTA (the bf16 variants carry the epilogue staging tiles)
+  const int static_bytes = ring_stages_output(d) ? 15 * 1024 : 4096;
   bool placed = false;
   for (int ctas = 3; ctas >= 2 && !placed; --ctas) {
     for (int dd = p->depth; dd >= 4; --dd) {
-      if (ctas * (9 * p->w_tap_bytes + dd * p->row_bytes + 4096) <= 224 * 1024) {
+      if (ctas * (9 * p->w_tap_bytes + dd * p->row_bytes + static_bytes) <= 224 * 1024) {
         p->depth = dd;
         placed = true;
         break;
@@ -395,12 +410,17 @@ int conv_ring_tcgen05(const ccvpe_igemm_desc& d, cudaStream_t st) {
   do {                                                                                                           \
     static thread_local bool attr = false;                                                                       \
     if (!attr) {                                                                                                 \
-      attr_err = cudaFuncSetAttribute(conv_ring_tcgen05_kernel<MODE, R1, F32>,                                   \
+      attr_err = cudaFuncSetAttribute(conv_ring_tcgen05_kernel<MODE, R1, F32, false>,                            \
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, RING_SMEM_BUDGET + 2048);     \
+      if (!(F32) && MODE != 2 && attr_err == cudaSuccess)                                                        \
+        attr_err = cudaFuncSetAttribute(conv_ring_tcgen05_kernel<MODE, R1, F32, !(F32) && MODE != 2>,            \
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, RING_SMEM_BUDGET + 2048);   \
       attr = true;                                                                                               \
     }                                                                                                            \
-    conv_ring_tcgen05_kernel<MODE, R1, F32><<<grid, RING_THREADS, smem, st>>>(p);                                 \
+    if (stage_out) conv_ring_tcgen05_kernel<MODE, R1, F32, !(F32) && MODE != 2><<<grid, RING_THREADS, smem, st>>>(p); \
+    else conv_ring_tcgen05_kernel<MODE, R1, F32, false><<<grid, RING_THREADS, smem, st>>>(p);                     \
   } while (0)
+  const bool stage_out = ring_stages_output(d);
   CCVPE_EPI_SWITCH(epi_variant(p.e), CCVPE_LAUNCH_RING)
 #undef CCVPE_LAUNCH_RING
   if (attr_err != cudaSuccess) return fail(CCVPE_ERR_CUDA, "cudaFuncSetAttribute(ring): %s", cudaGetErrorString(attr_err));

@@ -392,14 +392,14 @@ stem_conv_silu_kernel(const float* __restrict__ x, const float* __restrict__ w, 
 // Squeeze-excite gate folded into the projection weights, one launch per MBConv block:
 //     mean[b, m]   = chan_sum[b, m] * inv_hw
 //     h[b, r]      = SiLU(b_red[r] + sum_m w_red[r, m] * mean[b, m])
-//     g[b, m]      = sigmoid(b_se[m] + sum_r w_se[m, r] * h[b, r])
+//     g[b, m]      = sigmoid(b_se[m] + sum_r w_se_t[r, m] * h[b, r])      (w_se_t = transposed excite weights)
 //     wg[b, c, m]  = w_proj[c, m] * g[b, m]                (the B operand of the per-image projection GEMM)
 // Replaces seven small PyTorch launches per block (div, cast, two addmm, silu, sigmoid, mul).  fp32 math, bf16 in / out.
 // grid (B, row chunks): every block recomputes its image's gate (two tiny mat-vecs) and scales its rows of w_proj.
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 se_gate_scale_kernel(const float* __restrict__ chan_sum, float inv_hw, const __nv_bfloat16* __restrict__ w_red,
-                     const __nv_bfloat16* __restrict__ b_red, const __nv_bfloat16* __restrict__ w_se,
+                     const __nv_bfloat16* __restrict__ b_red, const __nv_bfloat16* __restrict__ w_se_t,
                      const __nv_bfloat16* __restrict__ b_se, const __nv_bfloat16* __restrict__ w_proj,
                      __nv_bfloat16* __restrict__ wg, int mid, int R, int cout, int rows_per_block) {
   extern __shared__ __align__(16) float s_se[];      // mean[mid] (later g[mid]), h[R]
@@ -429,10 +429,9 @@ se_gate_scale_kernel(const float* __restrict__ chan_sum, float inv_hw, const __n
     }
   }
   __syncthreads();
-  for (int m = tid; m < mid; m += blockDim.x) {       // gate: one channel per thread, R (<= 48) terms
-    const __nv_bfloat16* ws = w_se + (int64_t)m * R;
+  for (int m = tid; m < mid; m += blockDim.x) {       // gate: one channel per thread, R (<= 48) terms, coalesced over m
     float acc = __bfloat162float(b_se[m]);
-    for (int r = 0; r < R; ++r) acc = fmaf(__bfloat162float(ws[r]), s_h[r], acc);
+    for (int r = 0; r < R; ++r) acc = fmaf(__bfloat162float(w_se_t[(int64_t)r * mid + m]), s_h[r], acc);
     s_mean[m] = __fdividef(1.f, 1.f + __expf(-acc));  // (each thread overwrites only the means it owns)
   }
   __syncthreads();

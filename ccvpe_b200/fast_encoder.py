@@ -43,7 +43,7 @@ def _fold(conv: torch.nn.Conv2d, bn: torch.nn.BatchNorm2d) -> Tuple[torch.Tensor
 class _Block:
     __slots__ = ("has_expand", "residual", "stride", "kernel", "pad_lo", "pad_hi", "w_exp", "b_exp", "w_exp_nk",
                  "b_exp_f32", "w_dw", "b_dw",
-                 "w_red", "b_red", "w_se", "b_se", "w_proj", "b_proj", "mid", "cout", "w_dw_taps")
+                 "w_red", "b_red", "w_se", "w_se_t", "b_se", "w_proj", "b_proj", "mid", "cout", "w_dw_taps")
 
 
 class FastEncoder:
@@ -89,6 +89,7 @@ class FastEncoder:
             o.w_dw_taps = cast(w.reshape(o.mid, -1).t())                             # [k*k, mid] for the fused kernel
             o.w_red, o.b_red = cast(blk._se_reduce.weight.detach().flatten(1)), cast(blk._se_reduce.bias.detach())
             o.w_se, o.b_se = cast(blk._se_expand.weight.detach().flatten(1)), cast(blk._se_expand.bias.detach())
+            o.w_se_t = o.w_se.t().contiguous()                                       # [R, mid] for the fused gate kernel
             w, b = _fold(blk._project_conv, blk._bn2)
             pending = b + (pending if (o.residual and pending is not None) else 0.0)
             o.w_proj, o.b_proj = cast(w.flatten(1)), cast(pending)                   # [cout, mid]; b_proj = pending AFTER this block
@@ -238,7 +239,7 @@ class FastEncoder:
             # squeeze-excite gate folded into the projection weights
             if fused_dw:
                 wg = torch.empty((Bo, o.cout, o.mid), dtype=dt, device=d.device)
-                cabi.se_gate_scale(sums, 1.0 / float(Ho * Wo), o.w_red, o.b_red, o.w_se, o.b_se, o.w_proj, wg)
+                cabi.se_gate_scale(sums, 1.0 / float(Ho * Wo), o.w_red, o.b_red, o.w_se_t, o.b_se, o.w_proj, wg)
             else:
                 sq = (sums / float(Ho * Wo)).to(dt)                                  # [B, mid]
                 g = torch.sigmoid(F.linear(F.silu(F.linear(sq, o.w_red, o.b_red)), o.w_se, o.b_se))   # [B, mid]

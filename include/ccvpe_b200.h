@@ -188,8 +188,8 @@ int ccvpe_stem_conv_silu_nhwc(const float* x, int B, int H, int W, const float* 
 
 /* Squeeze-excite gate folded into the projection weights (reference efficientnet_pytorch/model.py:113-121 in eval mode):
  *   mean = chan_sum * inv_hw;  h = SiLU(w_red mean + b_red);  g = sigmoid(w_se h + b_se);  wg[b] = w_proj * diag(g[b])
- * chan_sum fp32 [B, mid] (from ccvpe_dwconv_bias_silu_nhwc); w_red bf16 [R, mid]; b_red bf16 [R]; w_se bf16 [mid, R];
- * b_se bf16 [mid]; w_proj bf16 [cout, mid]; wg bf16 [B, cout, mid] = the per-image B operand of the projection GEMM
+ * chan_sum fp32 [B, mid] (from ccvpe_dwconv_bias_silu_nhwc); w_red bf16 [R, mid]; b_red bf16 [R]; w_se bf16 [R, mid]
+ * (the excite weights TRANSPOSED, so the gate mat-vec reads them coalesced); b_se bf16 [mid]; w_proj bf16 [cout, mid]; wg bf16 [B, cout, mid] = the per-image B operand of the projection GEMM
  * (W (g . x) == (W diag(g)) x, so the broadcast multiply over the expanded activation never happens).  mid % 8 == 0. */
 int ccvpe_se_gate_scale(const float* chan_sum, float inv_hw, const void* w_red, const void* b_red, const void* w_se,
                         const void* b_se, const void* w_proj, void* wg, int B, int mid, int R, int cout, void* stream);

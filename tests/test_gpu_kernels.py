@@ -545,6 +545,7 @@ def test_se_gate_scale(cuda_device, B, mid, R, cout):
     gate = torch.sigmoid(h @ w_se.float().t() + b_se.float())
     ref = w_proj.float().unsqueeze(0) * gate.unsqueeze(1)
     wg = torch.empty(B, cout, mid, device=dev, dtype=torch.bfloat16)
-    cabi.se_gate_scale(sums.to(dev), 1.0 / hw, w_red.to(dev), b_red.to(dev), w_se.to(dev), b_se.to(dev), w_proj.to(dev), wg)
+    cabi.se_gate_scale(sums.to(dev), 1.0 / hw, w_red.to(dev), b_red.to(dev), w_se.t().contiguous().to(dev), b_se.to(dev),
+                       w_proj.to(dev), wg)
     torch.cuda.synchronize()
     assert rel_err(wg.float(), ref) < 1e-2
