@@ -22,6 +22,7 @@ EXPORTED_SYMBOLS = (
     "ccvpe_softmax_scratch_elems", "ccvpe_softmax_heatmap", "ccvpe_ori_normalize",
     "ccvpe_pose_scratch_bytes", "ccvpe_pose_decode", "ccvpe_bias_silu_nhwc", "ccvpe_dwconv_bias_silu_nhwc",
     "ccvpe_pointwise_silu_nhwc", "ccvpe_stem_conv_silu_nhwc", "ccvpe_se_gate_scale",
+    "ccvpe_wrap_columns_nhwc",
 )
 
 
@@ -115,6 +116,8 @@ def load() -> C.CDLL:
                                               C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.ccvpe_se_gate_scale.restype = C.c_int
     lib.ccvpe_se_gate_scale.argtypes = [C.c_void_p, C.c_float] + [C.c_void_p] * 6 + [C.c_int] * 4 + [C.c_void_p]
+    lib.ccvpe_wrap_columns_nhwc.restype = C.c_int
+    lib.ccvpe_wrap_columns_nhwc.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     if lib.ccvpe_abi_version() != 1:
         raise CcvpeError("libccvpe_b200.so ABI version mismatch")
     _lib = lib
@@ -333,3 +336,12 @@ def se_gate_scale(chan_sum: torch.Tensor, inv_hw: float, w_red: torch.Tensor, b_
         raise CcvpeError("se_gate_scale: shape / dtype mismatch")
     _check(load().ccvpe_se_gate_scale(_ptr(chan_sum), C.c_float(inv_hw), _ptr(w_red), _ptr(b_red), _ptr(w_se), _ptr(b_se),
                                       _ptr(w_proj), _ptr(wg), B, mid, R, cout, _stream()), "ccvpe_se_gate_scale")
+
+
+def wrap_columns_nhwc(buf: torch.Tensor, H: int, W: int, pad_lo: int, pad_hi: int):
+    """Circular width padding inside a contiguous padded NHWC bf16 image [B, H+lo+hi, W+lo+hi, C] (interior already written)."""
+    _require_cuda(buf)
+    B, Hp, Wp, Cc = buf.shape
+    if buf.dtype != torch.bfloat16 or not buf.is_contiguous() or Hp != H + pad_lo + pad_hi or Wp != W + pad_lo + pad_hi:
+        raise CcvpeError("wrap_columns_nhwc: buf must be contiguous bf16 [B, H+lo+hi, W+lo+hi, C]")
+    _check(load().ccvpe_wrap_columns_nhwc(_ptr(buf), B, H, W, Cc, pad_lo, pad_hi, _stream()), "ccvpe_wrap_columns_nhwc")

@@ -453,9 +453,45 @@ se_gate_scale_kernel(const float* __restrict__ chan_sum, float inv_hw, const __n
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Circular width padding of a padded channels-last image [B, Hp, Wp, C] whose interior (rows lo .. lo+H-1, columns
+// lo .. lo+W-1) has been written: columns [0, lo) <- interior columns [W - lo, W), columns [lo + W, Wp) <- interior
+// columns [0, hi).  One launch instead of two strided tensor copies per depthwise conv of the panorama encoder.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+wrap_columns_kernel(__nv_bfloat16* __restrict__ buf, int H, int W, int C, int lo, int hi, int Hp, int Wp, int64_t total) {
+  const int vec = C >> 3;                                     // 16-byte vectors per pixel
+  const int per_row = (lo + hi) * vec;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / per_row;                          // (b, h) of an interior row
+    const int r = (int)(i - row * per_row);
+    const int col = r / vec, v = r - col * vec;               // wrap column index 0 .. lo+hi-1
+    const int b = (int)(row / H), h = (int)(row - (int64_t)b * H);
+    const int dst_col = col < lo ? col : W + col;             // left wraps, then right wraps (padded coordinates)
+    const int src_col = col < lo ? W + col : col;             // = dst_col +- W
+    uint4* base = reinterpret_cast<uint4*>(buf + (((int64_t)b * Hp + h + lo) * Wp) * C);
+    base[(int64_t)dst_col * vec + v] = base[(int64_t)src_col * vec + v];
+  }
+}
+
 int igemm_tcgen05(const ccvpe_igemm_desc& d, cudaStream_t st, const TcOutPad* out_pad);  // igemm_tcgen05.cu
 
 }  // namespace ccvpe
+
+extern "C" int ccvpe_wrap_columns_nhwc(void* buf, int B, int H, int W, int C, int pad_lo, int pad_hi, void* stream) {
+  using namespace ccvpe;
+  CCVPE_REQUIRE(buf && aligned16(buf), "ccvpe_wrap_columns_nhwc: buf must be a 16-byte aligned pointer");
+  CCVPE_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "ccvpe_wrap_columns_nhwc: bad shape");
+  CCVPE_REQUIRE(pad_lo >= 0 && pad_hi >= 0 && pad_lo <= W && pad_hi <= W, "ccvpe_wrap_columns_nhwc: wrap wider than the image");
+  if (pad_lo + pad_hi == 0) return CCVPE_OK;
+  const int Hp = H + pad_lo + pad_hi, Wp = W + pad_lo + pad_hi;
+  const int64_t total = (int64_t)B * H * (pad_lo + pad_hi) * (C / 8);
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 8LL * sm_count()) blocks = 8LL * sm_count();
+  wrap_columns_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)buf, H, W, C, pad_lo, pad_hi, Hp, Wp, total);
+  CCVPE_LAUNCH_CHECK("wrap_columns_kernel");
+  return CCVPE_OK;
+}
 
 extern "C" int ccvpe_se_gate_scale(const float* chan_sum, float inv_hw, const void* w_red, const void* b_red,
                                    const void* w_se, const void* b_se, const void* w_proj, void* wg, int B, int mid,

@@ -115,6 +115,9 @@ class FastEncoder:
 
     def _wrap_columns(self, buf, H, W, lo, hi):
         """Circular width padding: copy the wrap-around columns inside the padded buffer (vertical borders stay zero)."""
+        if buf.is_cuda and buf.dtype == torch.bfloat16 and buf.is_contiguous():
+            cabi.wrap_columns_nhwc(buf, H, W, lo, hi)
+            return
         if lo:
             buf[:, lo:lo + H, :lo, :] = buf[:, lo:lo + H, W:W + lo, :]
         if hi:

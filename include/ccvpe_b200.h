@@ -186,6 +186,12 @@ int ccvpe_stem_conv_silu_nhwc(const float* x, int B, int H, int W, const float* 
                               void* out, int in_pad_lo, int in_pad_hi, int out_pad_lo, int out_pad_hi, int circular,
                               void* stream);
 
+/* Circular width padding of a padded channels-last bf16 image [B, H+lo+hi, W+lo+hi, C] (pad the same on both axes, as
+ * the depthwise convs use it) whose interior is already written: the lo left / hi right padding columns of the interior
+ * rows receive the wrapped-around interior columns (the reference's circular-padding patch of the ground encoder,
+ * models.py: F.pad(..., mode='circular') along the width).  The zero rows above / below are left untouched.  C % 8 == 0. */
+int ccvpe_wrap_columns_nhwc(void* buf, int B, int H, int W, int C, int pad_lo, int pad_hi, void* stream);
+
 /* Squeeze-excite gate folded into the projection weights (reference efficientnet_pytorch/model.py:113-121 in eval mode):
  *   mean = chan_sum * inv_hw;  h = SiLU(w_red mean + b_red);  g = sigmoid(w_se h + b_se);  wg[b] = w_proj * diag(g[b])
  * chan_sum fp32 [B, mid] (from ccvpe_dwconv_bias_silu_nhwc); w_red bf16 [R, mid]; b_red bf16 [R]; w_se bf16 [R, mid]

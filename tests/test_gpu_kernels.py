@@ -549,3 +549,19 @@ def test_se_gate_scale(cuda_device, B, mid, R, cout):
                        w_proj.to(dev), wg)
     torch.cuda.synchronize()
     assert rel_err(wg.float(), ref) < 1e-2
+
+
+@pytest.mark.parametrize("B,H,W,C,lo,hi", [(2, 9, 20, 96, 1, 1), (1, 5, 7, 32, 2, 2), (3, 4, 16, 240, 0, 1), (2, 6, 5, 8, 1, 2)])
+def test_wrap_columns_nhwc(cuda_device, B, H, W, C, lo, hi):
+    g = _gen(19)
+    buf = torch.zeros(B, H + lo + hi, W + lo + hi, C, dtype=torch.bfloat16)
+    buf[:, lo:lo + H, lo:lo + W, :] = torch.randn(B, H, W, C, generator=g).to(torch.bfloat16)
+    ref = buf.clone()
+    if lo:
+        ref[:, lo:lo + H, :lo, :] = ref[:, lo:lo + H, W:W + lo, :]
+    if hi:
+        ref[:, lo:lo + H, lo + W:, :] = ref[:, lo:lo + H, lo:lo + hi, :]
+    dbuf = buf.to(cuda_device)
+    cabi.wrap_columns_nhwc(dbuf, H, W, lo, hi)
+    torch.cuda.synchronize()
+    assert torch.equal(dbuf.cpu(), ref)
