@@ -251,10 +251,16 @@ def run_ours(args):
         barrier()
         w0 = time.time()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ncu_range = bool(os.environ.get("CCVPE_NCU_RANGE"))     # `ncu --profile-from-start off`: capture exactly these steps
+        if ncu_range:
+            torch.cuda.profiler.start()
         ev0.record()
         for _ in range(args.steps):
             step_resident()
         ev1.record()
+        if ncu_range:
+            torch.cuda.synchronize()
+            torch.cuda.profiler.stop()
         barrier()
         sampler.window(w0, time.time())
         launches = cabi.launch_count()

@@ -1,5 +1,5 @@
-"""Summarise an ncu launch list (gpu__time_duration per launch) of `bench.py`: kernel shares of ONE resident step
-(the launches between the last two pose_finish_kernel launches before the e2e phase).  Development / profiles tool."""
+"""Summarise an ncu launch list (gpu__time_duration per launch) of `bench.py`: kernel shares of the timed resident
+step(s), captured with `CCVPE_NCU_RANGE=1 ncu --profile-from-start off ...` (scripts/gpu_round.sh).  Profiles tool."""
 import collections
 import csv
 import sys
@@ -16,11 +16,9 @@ for r in data:
         launches.append((r[kn], float(r[mv].replace(",", "")) / 1e3))   # us
     except ValueError:
         pass
-ends = [i for i, (n, _) in enumerate(launches) if "pose_finish_kernel" in n]
-# bench order: warm-up steps, 1 timed resident step, then e2e steps; take the step that ends at the 4th pose_finish
-step_idx = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-lo, hi_ = ends[step_idx - 1] + 1, ends[step_idx] + 1
-step = launches[lo:hi_]
+# the list is captured with `ncu --profile-from-start off` around bench.py's timed resident step(s)
+# (CCVPE_NCU_RANGE=1), so every launch in it belongs to the timed region
+step = launches
 agg = collections.defaultdict(lambda: [0, 0.0])
 for n, us in step:
     key = n.split("(")[0].replace("void ", "")[:80]
