@@ -209,9 +209,9 @@ dwconv_bias_silu_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_sb, int64
 #pragma unroll
       for (int u = 0; u < 4; ++u)
         if (dst[u] >= 0)
-          *reinterpret_cast<float4*>(s_w + dst[u]) =
-              make_float4(__uint_as_float(v[u].x << 16), __uint_as_float(v[u].x & 0xffff0000u),
-                          __uint_as_float(v[u].y << 16), __uint_as_float(v[u].y & 0xffff0000u));
+          *reinterpret_cast<float4*>(s_w + dst[u]) =          // (pre-halved: the accumulator is h = a / 2 of the SiLU form)
+              make_float4(0.5f * __uint_as_float(v[u].x << 16), 0.5f * __uint_as_float(v[u].x & 0xffff0000u),
+                          0.5f * __uint_as_float(v[u].y << 16), 0.5f * __uint_as_float(v[u].y & 0xffff0000u));
     }
   }
   const int strips_row = (Wo + TW - 1) / TW;
@@ -226,6 +226,12 @@ dwconv_bias_silu_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_sb, int64
   if (active) {
     uint64_t bv[P];
     dw_widen<V>(*reinterpret_cast<const vec_t*>(bias + cg * V), bv);
+#pragma unroll
+    for (int j = 0; j < P; ++j) {                       // bias pre-halved like the weights
+      float lo, hi;
+      unpack_f32x2(bv[j], lo, hi);
+      bv[j] = pack_f32x2(0.5f * lo, 0.5f * hi);
+    }
     const __nv_bfloat16* xb = x + (int64_t)b * x_sb + cg * V;
     __nv_bfloat16* yb = y + (int64_t)b * Ho * Wo * C + cg * V;
     const float* wt = s_w + cl * V;
@@ -277,9 +283,7 @@ dwconv_bias_silu_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_sb, int64
           for (int j = 0; j < P; ++j) {
             float a0, a1;
             unpack_f32x2(acc[t][j], a0, a1);
-            a0 *= 0.5f;                               // SiLU(a) = a * sigmoid(a) = h + h * tanh(h), h = a / 2: one MUFU
-            a1 *= 0.5f;
-            a0 = fmaf(a0, dw_tanh(a0), a0);
+            a0 = fmaf(a0, dw_tanh(a0), a0);           // SiLU(a) = a * sigmoid(a) = h + h * tanh(h), h = a / 2: one MUFU
             a1 = fmaf(a1, dw_tanh(a1), a1);
             h[j] = __floats2bfloat162_rn(a0, a1);
             const float2 r = __bfloat1622float2(h[j]);
@@ -321,23 +325,24 @@ stem_conv_silu_kernel(const float* __restrict__ x, const float* __restrict__ w, 
   const int wo0 = 2 * pw;
   if (wo0 >= Wo) return;
   const int ho = blockIdx.y, b = blockIdx.z;
-  float acc[2][CO];
+  uint64_t acc[2][CO / 2];                                    // packed fp32 pairs over the output channels (FFMA2)
 #pragma unroll
-  for (int c = 0; c < CO; ++c) acc[0][c] = acc[1][c] = s_b[c];
+  for (int c = 0; c < CO / 2; ++c) acc[0][c] = acc[1][c] = pack_f32x2(s_b[2 * c], s_b[2 * c + 1]);
   const float* xb = x + (int64_t)b * 3 * H * W;
 #pragma unroll 1
   for (int ci = 0; ci < 3; ++ci) {
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
       const int ih = 2 * ho + ky - in_lo;
-      float in[5];
+      uint64_t in[5];                                         // each input value broadcast into both halves of a pair
 #pragma unroll
       for (int ix = 0; ix < 5; ++ix) {
         int iw = 2 * wo0 + ix - in_lo;
         bool ok = ih >= 0 && ih < H;
         if (CIRC) iw = iw < 0 ? iw + W : (iw >= W ? iw - W : iw);
         else ok = ok && iw >= 0 && iw < W;
-        in[ix] = ok ? __ldg(xb + ((int64_t)ci * H + ih) * W + iw) : 0.f;
+        const float v = ok ? __ldg(xb + ((int64_t)ci * H + ih) * W + iw) : 0.f;
+        in[ix] = pack_f32x2(v, v);
       }
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
@@ -345,14 +350,11 @@ stem_conv_silu_kernel(const float* __restrict__ x, const float* __restrict__ w, 
 #pragma unroll
         for (int c = 0; c < CO; c += 4) {
           const float4 wv = *reinterpret_cast<const float4*>(wt + c);
-          acc[0][c] = fmaf(in[kx], wv.x, acc[0][c]);
-          acc[0][c + 1] = fmaf(in[kx], wv.y, acc[0][c + 1]);
-          acc[0][c + 2] = fmaf(in[kx], wv.z, acc[0][c + 2]);
-          acc[0][c + 3] = fmaf(in[kx], wv.w, acc[0][c + 3]);
-          acc[1][c] = fmaf(in[kx + 2], wv.x, acc[1][c]);
-          acc[1][c + 1] = fmaf(in[kx + 2], wv.y, acc[1][c + 1]);
-          acc[1][c + 2] = fmaf(in[kx + 2], wv.z, acc[1][c + 2]);
-          acc[1][c + 3] = fmaf(in[kx + 2], wv.w, acc[1][c + 3]);
+          const uint64_t w01 = pack_f32x2(wv.x, wv.y), w23 = pack_f32x2(wv.z, wv.w);
+          acc[0][c / 2] = ffma2(in[kx], w01, acc[0][c / 2]);
+          acc[0][c / 2 + 1] = ffma2(in[kx], w23, acc[0][c / 2 + 1]);
+          acc[1][c / 2] = ffma2(in[kx + 2], w01, acc[1][c / 2]);
+          acc[1][c / 2 + 1] = ffma2(in[kx + 2], w23, acc[1][c / 2 + 1]);
         }
       }
     }
@@ -366,8 +368,11 @@ stem_conv_silu_kernel(const float* __restrict__ x, const float* __restrict__ w, 
     __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(q);
 #pragma unroll
     for (int c = 0; c < CO; c += 2) {
-      const float a0 = acc[t][c], a1 = acc[t][c + 1];
-      h[c >> 1] = __floats2bfloat162_rn(__fdividef(a0, 1.f + __expf(-a0)), __fdividef(a1, 1.f + __expf(-a1)));
+      float a0, a1;
+      unpack_f32x2(acc[t][c >> 1], a0, a1);
+      a0 *= 0.5f;                                              // SiLU(a) = h + h * tanh(h), h = a / 2
+      a1 *= 0.5f;
+      h[c >> 1] = __floats2bfloat162_rn(fmaf(a0, dw_tanh(a0), a0), fmaf(a1, dw_tanh(a1), a1));
     }
     uint4* dst = reinterpret_cast<uint4*>(orow + (int64_t)(wo + out_lo) * CO);
 #pragma unroll
