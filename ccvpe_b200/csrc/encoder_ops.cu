@@ -402,7 +402,7 @@ stem_conv_silu_kernel(const float* __restrict__ x, const float* __restrict__ w, 
 // Replaces seven small PyTorch launches per block (div, cast, two addmm, silu, sigmoid, mul).  fp32 math, bf16 in / out.
 // grid (B, row chunks): every block recomputes its image's gate (two tiny mat-vecs) and scales its rows of w_proj.
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 se_gate_scale_kernel(const float* __restrict__ chan_sum, float inv_hw, const __nv_bfloat16* __restrict__ w_red,
                      const __nv_bfloat16* __restrict__ b_red, const __nv_bfloat16* __restrict__ w_se_t,
                      const __nv_bfloat16* __restrict__ b_se, const __nv_bfloat16* __restrict__ w_proj,
@@ -413,7 +413,8 @@ se_gate_scale_kernel(const float* __restrict__ chan_sum, float inv_hw, const __n
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int m = tid; m < mid; m += blockDim.x) s_mean[m] = chan_sum[(int64_t)b * mid + m] * inv_hw;
   __syncthreads();
-  for (int r = warp; r < R; r += 8) {                 // one warp per reduced channel, 8 bf16 per lane per step
+  const int n_warps = blockDim.x >> 5;
+  for (int r = warp; r < R; r += n_warps) {           // one warp per reduced channel, 8 bf16 per lane per step
     const __nv_bfloat16* wr = w_red + (int64_t)r * mid;
     float acc = 0.f;
     for (int m0 = lane * 8; m0 < mid; m0 += 256) {
@@ -436,7 +437,8 @@ se_gate_scale_kernel(const float* __restrict__ chan_sum, float inv_hw, const __n
   __syncthreads();
   for (int m = tid; m < mid; m += blockDim.x) {       // gate: one channel per thread, R (<= 48) terms, coalesced over m
     float acc = __bfloat162float(b_se[m]);
-    for (int r = 0; r < R; ++r) acc = fmaf(__bfloat162float(w_se_t[(int64_t)r * mid + m]), s_h[r], acc);
+#pragma unroll 8
+    for (int r = 0; r < R; ++r) acc = fmaf(__bfloat162float(__ldg(w_se_t + (int64_t)r * mid + m)), s_h[r], acc);
     s_mean[m] = __fdividef(1.f, 1.f + __expf(-acc));  // (each thread overwrites only the means it owns)
   }
   __syncthreads();
@@ -506,13 +508,13 @@ extern "C" int ccvpe_se_gate_scale(const float* chan_sum, float inv_hw, const vo
   CCVPE_REQUIRE(B > 0 && B <= 65535 * 32 && mid > 0 && mid % 8 == 0 && R > 0 && cout > 0,
                 "ccvpe_se_gate_scale: bad shape B=%d mid=%d R=%d cout=%d", B, mid, R, cout);
   CCVPE_REQUIRE(aligned16(w_red) && aligned16(w_proj) && aligned16(wg), "ccvpe_se_gate_scale: pointers must be 16-byte aligned");
-  int rows = 65536 / mid;
+  int rows = 98304 / mid;
   if (rows < 8) rows = 8;
   if (rows > cout) rows = cout;
   const dim3 grid(B, (cout + rows - 1) / rows);
   const size_t sm = (size_t)(mid + R) * sizeof(float);
   CCVPE_REQUIRE(sm <= 48 * 1024, "ccvpe_se_gate_scale: mid too large");
-  se_gate_scale_kernel<<<grid, 256, sm, (cudaStream_t)stream>>>(
+  se_gate_scale_kernel<<<grid, 512, sm, (cudaStream_t)stream>>>(
       chan_sum, inv_hw, (const __nv_bfloat16*)w_red, (const __nv_bfloat16*)b_red, (const __nv_bfloat16*)w_se,
       (const __nv_bfloat16*)b_se, (const __nv_bfloat16*)w_proj, (__nv_bfloat16*)wg, mid, R, cout, rows);
   CCVPE_LAUNCH_CHECK("se_gate_scale_kernel");
