@@ -184,11 +184,21 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
-        # keep stdout to the one JSON line: NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # keep stdout to the one JSON line: NCCL prints its version banner to stdout when the first communicator is
+        # created (at NCCL_DEBUG=VERSION/WARN/INFO, whatever the box sets), so route fd 1 to stderr around the
+        # rendezvous and the first collective
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     def barrier():
         if dist is not None:
@@ -359,7 +369,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": d2h, "ms_per_step": round(ms_e2e / args.steps, 3),
                     "h2d_alone_ms": round(h2d_ms, 3), "h2d_gbs": round(h2d / h2d_ms / 1e6, 1),
                     "note": "fp32 host images; the H2D copy of step i+1 overlaps the kernels of step i"},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches) * world,      # libccvpe_b200 kernel launches in the timed region, all ranks
             "roofline": roofline, "kernels": kernels, "clocks": clocks,
         }
         if cpu is not None:
