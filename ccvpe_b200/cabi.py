@@ -152,12 +152,22 @@ def _require_cuda(*tensors):
                              % t.device.type)
 
 
+_replayed_launches = 0      # kernel launches executed through CUDA-graph replays (the C counter only sees direct launches)
+
+
 def launch_count() -> int:
-    return int(load().ccvpe_launch_count())
+    return int(load().ccvpe_launch_count()) + _replayed_launches
 
 
 def reset_launch_count():
+    global _replayed_launches
+    _replayed_launches = 0
     load().ccvpe_reset_launch_count()
+
+
+def add_replayed_launches(n: int):
+    global _replayed_launches
+    _replayed_launches += int(n)
 
 
 # ------------------------------------------------------------------------------------------------------------------

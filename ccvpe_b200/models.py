@@ -84,6 +84,7 @@ class _CVMBase(nn.Module):
         self._pipeline = [PostEncoderPipeline(self, spec, ori_noise)]   # in a list: not a sub-module, not in state_dict
         self._precision = "fp32"
         self._fast_encoders = [None]                                    # (signature, grd_enc_bf16, sat_enc_bf16)
+        self._graphs = [None]                                           # None = eager; dict = CUDA-graph cache
 
     # -- configuration ----------------------------------------------------------------------------------------
     @property
@@ -96,23 +97,57 @@ class _CVMBase(nn.Module):
         if precision not in ("fp32", "bf16"):
             raise ValueError("precision must be 'fp32' or 'bf16'")
         self._precision = precision
+        self._drop_graphs()
         return self
 
     def set_backend(self, backend: int):
         self.pipeline.backend = backend
+        self._drop_graphs()
         return self
+
+    def set_cuda_graph(self, enabled: bool = True):
+        """Serve `forward` from CUDA graphs (one per input shape/dtype): the ~200 kernel launches of a forward are
+        captured once and replayed with a single launch, which removes the host launch cost that dominates small
+        batches.  Semantics to know: the returned tensors are the graph's static output buffers -- they are overwritten
+        by the next `forward` call with the same shapes, so consume (or clone) them first; inputs are copied into
+        static device buffers.  Call it again (or load_state_dict / set_precision / .to) after changing weights: the
+        cache is dropped.  Eval mode only."""
+        self._graphs[0] = {} if enabled else None
+        return self
+
+    def _drop_graphs(self):
+        if self._graphs[0] is not None:
+            self._graphs[0] = {}
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self._drop_graphs()
+        return out
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        if "_graphs" in self.__dict__:
+            self._drop_graphs()
+        return out
+
+    def train(self, mode: bool = True):
+        out = super().train(mode)
+        if "_graphs" in self.__dict__:
+            self._drop_graphs()
+        return out
 
     def __deepcopy__(self, memo):
         cls = self.__class__
         new = cls.__new__(cls)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            if k in ("_pipeline", "_fast_encoders"):
+            if k in ("_pipeline", "_fast_encoders", "_graphs"):
                 continue
             setattr(new, k, copy.deepcopy(v, memo))
         new._pipeline = [PostEncoderPipeline(new, self.spec, self.pipeline.ori_noise)]
         new._pipeline[0].backend = self.pipeline.backend
         new._fast_encoders = [None]
+        new._graphs = [None if self._graphs[0] is None else {}]
         return new
 
     # -- encoders (PyTorch) -----------------------------------------------------------------------------------
@@ -152,8 +187,43 @@ class _CVMBase(nn.Module):
             raise cabi.CcvpeError("ccvpe_b200 models run on CUDA (sm_100a) only; there is no CPU fallback -- "
                                   "move the model and inputs to a B200")
         with torch.no_grad():
-            fg, fs, multi, dtype = self._encode(grd, sat)
-            return self.pipeline.run(fg, fs, multi, dtype)
+            if self._graphs[0] is not None and not self.training and self.pipeline.timer is None:
+                return self._forward_graphed(grd, sat)
+            return self._forward_eager(grd, sat)
+
+    def _forward_eager(self, grd, sat):
+        fg, fs, multi, dtype = self._encode(grd, sat)
+        return self.pipeline.run(fg, fs, multi, dtype)
+
+    def _forward_graphed(self, grd, sat):
+        key = (tuple(grd.shape), grd.dtype, tuple(sat.shape), sat.dtype, grd.device.index, self._precision)
+        entry = self._graphs[0].get(key)
+        if entry is None:
+            static_grd, static_sat = torch.empty_like(grd), torch.empty_like(sat)
+            static_grd.copy_(grd)
+            static_sat.copy_(sat)
+            # warm up on a side stream: weight caches, persistent staging buffers, cudaFuncSetAttribute, lazy handles
+            side = torch.cuda.Stream(device=grd.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self._forward_eager(static_grd, static_sat)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize(grd.device)
+            graph = torch.cuda.CUDAGraph()
+            n0 = cabi.launch_count()
+            with torch.cuda.graph(graph):
+                outs = self._forward_eager(static_grd, static_sat)
+            n_captured = cabi.launch_count() - n0
+            cabi.add_replayed_launches(-n_captured)          # captured, not executed: keep the executed-launch count honest
+            entry = (graph, static_grd, static_sat, outs, n_captured)
+            self._graphs[0][key] = entry
+        graph, static_grd, static_sat, outs, n_launches = entry
+        static_grd.copy_(grd)
+        static_sat.copy_(sat)
+        graph.replay()
+        cabi.add_replayed_launches(n_launches)
+        return outs
 
     # -- extras -----------------------------------------------------------------------------------------------
     @staticmethod
