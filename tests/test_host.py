@@ -69,3 +69,33 @@ def test_specs_match_reference_tables():
     assert specs.OXFORD.window_offset(1280, 224) == 528 and specs.OXFORD.window_len(40, 7) == 7   # models.py:1094
     assert specs.loc_roll_indices(specs.VIGOR, 72.0) == list(range(-4, 5))                          # models.py:489
     assert specs.loc_roll_indices(specs.KITTI, None) == list(range(16))
+
+
+def test_pad_k_blocks_layout_rule():
+    """w_nk K padding documented in include/ccvpe_b200.h: block width 16 if K <= 16, 32 if K < 64, else 64; zero filled."""
+    for K, padded in [(16, 16), (24, 32), (40, 64), (80, 128), (112, 128), (192, 192), (320, 320), (8, 16)]:
+        w = torch.arange(3 * K, dtype=torch.float32).reshape(3, K) + 1.0
+        out = cabi.pad_k_blocks(w)
+        assert out.dtype == torch.bfloat16 and tuple(out.shape) == (3, padded), (K, out.shape)
+        assert torch.equal(out[:, :K].float(), w.to(torch.bfloat16).float())
+        assert float(out[:, K:].abs().sum()) == 0.0
+
+
+def test_cuda_graph_cache_is_dropped_when_weights_change():
+    """set_cuda_graph keeps one graph per input signature; anything that can move or change weights must drop them."""
+    m = models.CVM_VIGOR("cpu", True).eval()
+    assert m._graphs[0] is None                                  # eager by default
+    m.set_cuda_graph(True)
+    m._graphs[0]["sentinel"] = object()
+    m.load_state_dict(m.state_dict())
+    assert m._graphs[0] == {}
+    m._graphs[0]["sentinel"] = object()
+    m.set_precision("bf16")
+    assert m._graphs[0] == {}
+    m._graphs[0]["sentinel"] = object()
+    m.float()
+    assert m._graphs[0] == {}
+    m.set_cuda_graph(False)
+    assert m._graphs[0] is None
+    with pytest.raises(cabi.CcvpeError):                         # still no CPU path, graph mode or not
+        m(torch.zeros(1, 3, 320, 640), torch.zeros(1, 3, 512, 512))
