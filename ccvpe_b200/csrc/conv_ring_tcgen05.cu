@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(RING_THREADS, 3) conv_ring_tcgen05_kernel(cons
   // bf16 rows leave through per-warp staging tiles (coalesced copy-out, see epi_store_row_staged)
   constexpr bool STAGED = STAGE_OUT && !OUT_F32 && MODE != 2;
   __shared__ __align__(16) uint8_t s_stage[STAGED ? 4 * EPI_WARP_STAGE_BYTES : 16];
-  __shared__ int64_t s_rowbase[STAGED ? TC_BM : 1];
+  __shared__ int32_t s_rowbase[STAGED ? TC_BM : 1];
   __shared__ __align__(16) uint4 s_blk[4];   // per K block: descriptor offsets (16-byte units) for the MMA issuer
 
   const int warp = threadIdx.x >> 5;

@@ -46,7 +46,7 @@ igemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
   // the light (two CTAs per SM) configuration runs the HBM-bound layers: its bf16 rows leave through per-warp staging tiles
   constexpr bool STAGED = LIGHT && !OUT_F32 && MODE != 2;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ int64_t s_rowbase[STAGED ? 32 * EPI_WARPS : 1];
+  __shared__ int32_t s_rowbase[STAGED ? 32 * EPI_WARPS : 1];
   __shared__ __align__(8) uint64_t bar_full[TC_MAX_STAGES];
   __shared__ __align__(8) uint64_t bar_empty[TC_MAX_STAGES];
   __shared__ __align__(8) uint64_t bar_tmem_full[2];

@@ -290,7 +290,7 @@ __device__ __forceinline__ void epi_store_row(const EpiParams& e, uint32_t taddr
 // instead (row pitch 80 bytes = an odd number of 16-byte units: the row-per-thread writes are bank-conflict free) and is
 // copied out with 4 lanes per row / 8 rows per instruction, so consecutive pixels leave as contiguous runs (6 TB/s in the
 // same probe).  Rows outside the problem are computed like the others and dropped at the copy (no divergent math).
-// `stage` / `s_rowbase`: THIS WARP's 32 x 80-byte tile and 32 row offsets.  Single-buffered TMEM loads keep the register
+// `stage` / `s_rowbase`: THIS WARP's 32 x 80-byte tile and 32 row offsets (16-byte units).  Single-buffered TMEM loads keep the register
 // count low enough for 16 epilogue warps per SM, which is what hides the instruction latencies of this code.
 constexpr int EPI_CHUNK_PITCH = 80;
 constexpr int EPI_WARP_STAGE_BYTES = 32 * EPI_CHUNK_PITCH;
@@ -299,14 +299,15 @@ template <int MODE, bool HAS_R1>
 __device__ __forceinline__ void epi_store_row_staged(const EpiParams& e, uint32_t taddr, int half, int halves, int block_n,
                                                      int n0, bool valid, int64_t row_base, float rs, float r1,
                                                      const float* s_bias, const float* s_r1w, const int* s_off,
-                                                     uint32_t release_bar, uint8_t* stage, int64_t* s_rowbase) {
+                                                     uint32_t release_bar, uint8_t* stage, int32_t* s_rowbase) {
   const int lane = threadIdx.x & 31;
   const int ncols = min(block_n, e.N - n0);
   const float lower = e.relu ? 0.f : -INFINITY;
   if (MODE == 3) rs *= 0.5f;
-  s_rowbase[lane] = valid ? row_base : -1;
+  // row offsets travel as 32-bit indices of 16-byte units (outputs < 32 GB, checked on the host): one IMAD.WIDE per store
+  s_rowbase[lane] = valid ? (int32_t)(row_base >> 3) : -1;
   uint8_t* my = stage + lane * EPI_CHUNK_PITCH;
-  __nv_bfloat16* out = static_cast<__nv_bfloat16*>(e.out);
+  uint4* out16 = static_cast<uint4*>(e.out);
   const int cstep = 32 * halves;
   const int fr = lane >> 2, fc = lane & 3;          // copy-out role: row within a group of 8, 16-byte unit within the chunk
   const uint8_t* src = stage + fr * EPI_CHUNK_PITCH + fc * 16;
@@ -322,10 +323,8 @@ __device__ __forceinline__ void epi_store_row_staged(const EpiParams& e, uint32_
     tmem_ld32(taddr + (uint32_t)c0, v);
     tmem_ld_wait();
     if (c0 + cstep >= ncols) release();             // that was this warp's last chunk of the accumulator stage
-#pragma unroll
-    for (int g8 = 0; g8 < 4; ++g8) {
+    auto group = [&](int g8) {                       // 8 columns: bias / rank-1 / scale / activation -> 16 staged bytes
       const int cl = c0 + g8 * 8;
-      if (cl >= ncols) break;
       const float4 b0 = *reinterpret_cast<const float4*>(&s_bias[cl]);
       const float4 b1 = *reinterpret_cast<const float4*>(&s_bias[cl + 4]);
       float y[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
@@ -354,15 +353,25 @@ __device__ __forceinline__ void epi_store_row_staged(const EpiParams& e, uint32_
       pk.z = *reinterpret_cast<uint32_t*>(&q2);
       pk.w = *reinterpret_cast<uint32_t*>(&q3);
       *reinterpret_cast<uint4*>(my + g8 * 16) = pk;
+    };
+    if (c0 + 32 <= ncols) {                           // full chunk: straight-line code
+      group(0);
+      group(1);
+      group(2);
+      group(3);
+    } else {
+#pragma unroll
+      for (int g8 = 0; g8 < 4; ++g8)
+        if (c0 + g8 * 8 < ncols) group(g8);
     }
     __syncwarp();
     const bool unit_ok = fc < ((min(32, ncols - c0)) >> 3);
-    const int goff = unit_ok ? s_off[(c0 >> 3) + fc] : 0;
+    const int goff = unit_ok ? (s_off[(c0 >> 3) + fc] >> 3) : 0;
 #pragma unroll
     for (int pass = 0; pass < 4; ++pass) {
-      const int64_t rb = s_rowbase[pass * 8 + fr];
+      const int32_t rb = s_rowbase[pass * 8 + fr];
       const uint4 val = *reinterpret_cast<const uint4*>(src + pass * 8 * EPI_CHUNK_PITCH);
-      if (unit_ok && rb >= 0) *reinterpret_cast<uint4*>(out + (rb + goff)) = val;
+      if (unit_ok && rb >= 0) out16[(uint32_t)(rb + goff)] = val;
     }
     __syncwarp();
   }
@@ -373,8 +382,10 @@ inline bool tc_epilogue_supported(const ccvpe_igemm_desc& d) {
   if (d.out_dtype != CCVPE_BF16) return true;
   if (d.out_mode == 2) return false;
   const int cout = d.out_mode == 1 ? d.N / 4 : d.N;
+  // (the staged epilogue addresses the output with 32-bit indices of 16-byte units: keep it below 16 GB, padding included)
+  const int64_t out_elems = (int64_t)(d.out_mode == 1 ? 4 : 1) * d.B * d.Hout * d.Wout * d.ldo;
   return (cout % 8 == 0) && (d.ldo % 8 == 0) && ((reinterpret_cast<uintptr_t>(d.out) & 15) == 0) &&
-         (d.out_mode != 1 || d.N % 4 == 0);
+         (d.out_mode != 1 || d.N % 4 == 0) && out_elems < (1LL << 33);
 }
 
 // Epilogue variant of a descriptor: 0 conv bf16 | 1 conv bf16 + rank-1 | 2 conv fp32 channels-last | 3 planar fp32 |
