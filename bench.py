@@ -408,6 +408,10 @@ def run_ours(args):
                        "backend": args.backend,
                        "cuda_graph": bool(use_graph), **({"cuda_graph_note": graph_note} if graph_note else {}),
                        "l2": "per-step working set (inputs %.0f MB + >1 GB activations) exceeds the 126 MB L2" % (h2d / 1e6)},
+            # the post-encoder path on its own (sum of the per-launch CUDA-event times of the
+            # libccvpe_b200 decoder kernels, encoders excluded)
+            "post_encoder": {"value": round(world * B * args.steps / (post_ms / 1e3), 1), "unit": "pairs/s",
+                             "ms_per_step": round(post_ms / args.steps, 3)},
             "e2e": {"value": round(e2e_value, 3), "unit": "pairs/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": round(ms_e2e / args.steps, 3),
                     "h2d_alone_ms": round(h2d_ms, 3), "h2d_gbs": round(h2d / h2d_ms / 1e6, 1),
