@@ -14,11 +14,13 @@ import torch
 from . import build as _build
 
 F32, BF16 = 0, 1
+ABI_VERSION = 2
+SE_SUM_SCALE = 1048576.0    # CCVPE_SE_SUM_SCALE: the squeeze-excite channel sums are int64 fixed point (order independent)
 BACKEND_AUTO, BACKEND_SIMT, BACKEND_TCGEN05 = 0, 1, 2
 
 EXPORTED_SYMBOLS = (
     "ccvpe_abi_version", "ccvpe_last_error", "ccvpe_launch_count", "ccvpe_reset_launch_count",
-    "ccvpe_grd_descriptor", "ccvpe_grd_descriptors", "ccvpe_igemm", "ccvpe_igemm_plan", "ccvpe_match_scratch_elems", "ccvpe_match_level",
+    "ccvpe_grd_descriptor", "ccvpe_grd_descriptors", "ccvpe_igemm", "ccvpe_igemm_plan", "ccvpe_match_scratch_elems", "ccvpe_match_plan", "ccvpe_match_level",
     "ccvpe_softmax_scratch_elems", "ccvpe_softmax_heatmap", "ccvpe_ori_normalize",
     "ccvpe_pose_scratch_bytes", "ccvpe_pose_decode", "ccvpe_bias_silu_nhwc", "ccvpe_dwconv_bias_silu_nhwc",
     "ccvpe_pointwise_silu_nhwc", "ccvpe_stem_conv_silu_nhwc", "ccvpe_se_gate_scale",
@@ -84,6 +86,8 @@ def load() -> C.CDLL:
     lib.ccvpe_igemm_plan.argtypes = [C.POINTER(IgemmDesc)]
     lib.ccvpe_match_scratch_elems.restype = C.c_int64
     lib.ccvpe_match_scratch_elems.argtypes = [C.c_int, C.c_int, C.c_int]
+    lib.ccvpe_match_plan.restype = C.c_int
+    lib.ccvpe_match_plan.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_int]
     lib.ccvpe_match_level.restype = C.c_int
     lib.ccvpe_match_level.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_int, C.c_uint32,
@@ -118,7 +122,7 @@ def load() -> C.CDLL:
     lib.ccvpe_se_gate_scale.argtypes = [C.c_void_p, C.c_float] + [C.c_void_p] * 6 + [C.c_int] * 4 + [C.c_void_p]
     lib.ccvpe_wrap_columns_nhwc.restype = C.c_int
     lib.ccvpe_wrap_columns_nhwc.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
-    if lib.ccvpe_abi_version() != 1:
+    if lib.ccvpe_abi_version() != ABI_VERSION:
         raise CcvpeError("libccvpe_b200.so ABI version mismatch")
     _lib = lib
     return lib
@@ -146,10 +150,27 @@ def _stream():
 
 
 def _require_cuda(*tensors):
+    """Every tensor must live on the CURRENT CUDA device: the library launches on the calling thread's current device and
+    on torch's current stream of that device (`_stream`).  The model-level entry points (`forward`, `decode_pose`, ...)
+    switch to their tensors' device themselves (`device_of`), so `model.to('cuda:1')` works whatever the current device
+    is; direct callers of this binding get a clear error instead of an illegal address."""
+    cur = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise CcvpeError("ccvpe_b200 kernels need CUDA tensors (got a %s tensor); there is no CPU fallback"
                              % t.device.type)
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            raise CcvpeError("tensor on cuda:%d but the current device is cuda:%d -- wrap the call in "
+                             "`with torch.cuda.device(tensor.device):`" % (t.device.index, cur))
+
+
+def device_of(t: torch.Tensor):
+    """Context manager making `t`'s device current (kernels, func attributes and the stream are per device)."""
+    return torch.cuda.device(t.device)
 
 
 _replayed_launches = 0      # kernel launches executed through CUDA-graph replays (the C counter only sees direct launches)
@@ -217,6 +238,20 @@ def match_scratch_elems(B: int, Cch: int, n_rolls: int) -> int:
     return int(load().ccvpe_match_scratch_elems(B, Cch, n_rolls))
 
 
+MATCH_KERNELS = ("match_level_simt_kernel", "match_tcgen05_kernel")
+
+
+def match_kernel_name(dtype: torch.dtype, Cch: int, L: int, offset: int, shifts: Sequence[int], ld_scores_cl: int,
+                      backend: int = BACKEND_AUTO) -> str:
+    """Which kernel `match_level` launches for this level (bench attribution / tests)."""
+    n = len(shifts)
+    arr = (C.c_int32 * n)(*[int(s) for s in shifts])
+    rc = load().ccvpe_match_plan(dtype_code(dtype), Cch, L, int(offset), arr, n, ld_scores_cl, backend)
+    if rc < 0:
+        _check(rc, "ccvpe_match_plan")
+    return MATCH_KERNELS[rc]
+
+
 def match_level(x: torch.Tensor, g: torch.Tensor, offset: int, shifts: Sequence[int], max_mask: int,
                 scores=None, scores_cl=None, max_out=None, inv_norm=None, xhat=None, scratch=None,
                 backend: int = BACKEND_AUTO):
@@ -263,9 +298,16 @@ def pose_decode(heatmap: torch.Tensor, ori: torch.Tensor, idx, rc, cs, angle, va
                                     _ptr(valid), _ptr(scratch), _stream()), "ccvpe_pose_decode")
 
 
+def _check_se_sum(chan_sum: Optional[torch.Tensor]):
+    if chan_sum is not None and (chan_sum.dtype != torch.int64 or not chan_sum.is_contiguous()):
+        raise CcvpeError("chan_sum must be a contiguous int64 tensor (fixed point, units of 1/SE_SUM_SCALE)")
+
+
 def bias_silu_nhwc(x: torch.Tensor, bias: Optional[torch.Tensor], y: torch.Tensor, chan_sum: Optional[torch.Tensor] = None):
-    """x contiguous NHWC bf16 [B,H,W,C]; y NHWC bf16 view with contiguous channels (any batch/row/pixel strides)."""
+    """x contiguous NHWC bf16 [B,H,W,C]; y NHWC bf16 view with contiguous channels (any batch/row/pixel strides);
+    chan_sum: int64 [B, C] fixed-point accumulator (units of 1/SE_SUM_SCALE), zeroed by the caller."""
     _require_cuda(x, bias, y, chan_sum)
+    _check_se_sum(chan_sum)
     B, H, W, Cc = x.shape
     if not x.is_contiguous() or y.stride(3) != 1 or tuple(y.shape) != tuple(x.shape):
         raise CcvpeError("bias_silu_nhwc: x must be contiguous NHWC and y an NHWC view of the same shape")
@@ -277,6 +319,7 @@ def dwconv_bias_silu_nhwc(x_pad: torch.Tensor, w: torch.Tensor, bias: torch.Tens
                           chan_sum: Optional[torch.Tensor] = None):
     """x_pad: pre-padded NHWC bf16 view [B,Hp,Wp,C] (channels contiguous); w bf16 [k*k, C]; y contiguous NHWC bf16."""
     _require_cuda(x_pad, w, bias, y, chan_sum)
+    _check_se_sum(chan_sum)
     B, Hp, Wp, Cc = x_pad.shape
     if x_pad.stride(3) != 1 or not y.is_contiguous():
         raise CcvpeError("dwconv_bias_silu_nhwc: channels must be contiguous and y contiguous")
@@ -333,7 +376,7 @@ def stem_conv_silu_nhwc(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, ou
 def se_gate_scale(chan_sum: torch.Tensor, inv_hw: float, w_red: torch.Tensor, b_red: torch.Tensor, w_se: torch.Tensor,
                   b_se: torch.Tensor, w_proj: torch.Tensor, wg: torch.Tensor):
     """wg[b] = w_proj * diag(sigmoid(w_se^T SiLU(w_red mean_b + b_red) + b_se)), mean_b = chan_sum[b] * inv_hw.
-    chan_sum fp32 [B, mid]; w_red [R, mid]; w_se [R, mid] (the excite weights transposed); contiguous bf16;
+    chan_sum int64 fixed point [B, mid]; w_red [R, mid]; w_se [R, mid] (the excite weights transposed); contiguous bf16;
     wg contiguous bf16 [B, cout, mid]."""
     _require_cuda(chan_sum, w_red, b_red, w_se, b_se, w_proj, wg)
     B, mid = chan_sum.shape
@@ -341,7 +384,7 @@ def se_gate_scale(chan_sum: torch.Tensor, inv_hw: float, w_red: torch.Tensor, b_
     for t in (w_red, b_red, w_se, b_se, w_proj, wg):
         if t.dtype != torch.bfloat16 or not t.is_contiguous():
             raise CcvpeError("se_gate_scale: weights, biases and wg must be contiguous bf16")
-    if chan_sum.dtype != torch.float32 or not chan_sum.is_contiguous() or tuple(wg.shape) != (B, cout, mid) \
+    if chan_sum.dtype != torch.int64 or not chan_sum.is_contiguous() or tuple(wg.shape) != (B, cout, mid) \
             or tuple(w_red.shape) != (R, mid) or tuple(w_se.shape) != (R, mid) or tuple(w_proj.shape) != (cout, mid):
         raise CcvpeError("se_gate_scale: shape / dtype mismatch")
     _check(load().ccvpe_se_gate_scale(_ptr(chan_sum), C.c_float(inv_hw), _ptr(w_red), _ptr(b_red), _ptr(w_se), _ptr(b_se),

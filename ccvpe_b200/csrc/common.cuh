@@ -52,6 +52,17 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 int sm_count();  // cached cudaDevAttrMultiProcessorCount of the current device (148 on B200)
 
+// cudaFuncSetAttribute is per (function, DEVICE): the launchers remember in a per-thread bit mask which devices a kernel's
+// attributes were already set on.  Returns true the first time it is called for the calling thread's current device.
+inline bool first_use_on_device(uint64_t& mask) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return true;
+  const uint64_t bit = 1ull << (dev & 63);
+  if (mask & bit) return false;
+  mask |= bit;
+  return true;
+}
+
 // ---- element access ----------------------------------------------------------------------------------------------
 template <typename T> __device__ __forceinline__ float to_float(T v);
 template <> __device__ __forceinline__ float to_float<float>(float v) { return v; }
@@ -77,6 +88,25 @@ __device__ __forceinline__ void store4(__nv_bfloat16* p, float4 v) {
   raw.x = *reinterpret_cast<uint32_t*>(&lo);
   raw.y = *reinterpret_cast<uint32_t*>(&hi);
   *reinterpret_cast<uint2*>(p) = raw;
+}
+
+// packed fp32x2 helpers: Blackwell's FFMA2 does two fp32 FMAs per issued instruction, and a bf16x2 word widens to an
+// fp32 pair with one shift and one mask
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t bf16x2_to_f32x2(uint32_t v) {
+  return pack_f32x2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

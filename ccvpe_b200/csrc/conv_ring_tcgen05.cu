@@ -408,14 +408,13 @@ int conv_ring_tcgen05(const ccvpe_igemm_desc& d, cudaStream_t st) {
   cudaError_t attr_err = cudaSuccess;
 #define CCVPE_LAUNCH_RING(MODE, R1, F32)                                                                         \
   do {                                                                                                           \
-    static thread_local bool attr = false;                                                                       \
-    if (!attr) {                                                                                                 \
+    static thread_local uint64_t attr = 0;                                                                       \
+    if (first_use_on_device(attr)) {                                                                             \
       attr_err = cudaFuncSetAttribute(conv_ring_tcgen05_kernel<MODE, R1, F32, false>,                            \
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, RING_SMEM_BUDGET + 2048);     \
       if (!(F32) && MODE != 2 && attr_err == cudaSuccess)                                                        \
         attr_err = cudaFuncSetAttribute(conv_ring_tcgen05_kernel<MODE, R1, F32, !(F32) && MODE != 2>,            \
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, RING_SMEM_BUDGET + 2048);   \
-      attr = true;                                                                                               \
     }                                                                                                            \
     if (stage_out) conv_ring_tcgen05_kernel<MODE, R1, F32, !(F32) && MODE != 2><<<grid, RING_THREADS, smem, st>>>(p); \
     else conv_ring_tcgen05_kernel<MODE, R1, F32, false><<<grid, RING_THREADS, smem, st>>>(p);                     \

@@ -14,11 +14,20 @@
 
 namespace ccvpe {
 
+// Squeeze-excite channel sums are accumulated in 64-bit FIXED POINT (2^-20 units): integer addition is associative, so the
+// result does not depend on the order in which threads and blocks arrive -- the bf16 path is bit-reproducible run to run
+// (eager or CUDA-graph replay).  Every thread's own partial is a plain fp32 sum over a fixed set of pixels.  Head room:
+// |sum| < 2^43 ~ 8.8e12, i.e. 65536 pixels of magnitude 1e8.
+constexpr float kSeFixedScale = 1048576.f;
+__device__ __forceinline__ unsigned long long se_fixed(float v) {
+  return (unsigned long long)__float2ll_rn(v * kSeFixedScale);
+}
+
 __global__ void __launch_bounds__(256)
 bias_silu_nhwc_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ bias,
                       __nv_bfloat16* __restrict__ y, int64_t y_sb, int64_t y_sh, int64_t y_sw, int H, int W, int C,
-                      int pix_per_block, float* __restrict__ chan_sum) {
-  extern __shared__ float s_sum[];                 // [C] per-block channel sums (only if chan_sum)
+                      int pix_per_block, long long* __restrict__ chan_sum) {
+  extern __shared__ unsigned long long s_sum[];    // [C] per-block channel sums, fixed point (only if chan_sum)
   const int G = C >> 3;                            // 8-channel groups per pixel
   const int lanes = blockDim.x / G;                // pixels processed concurrently by the block
   const int cg = threadIdx.x % G, pl = threadIdx.x / G;
@@ -27,7 +36,7 @@ bias_silu_nhwc_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* 
   const int p_lo = blockIdx.x * pix_per_block;
   const int p_hi = min(HW, p_lo + pix_per_block);
   if (chan_sum) {
-    for (int c = threadIdx.x; c < C; c += blockDim.x) s_sum[c] = 0.f;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) s_sum[c] = 0ull;
     __syncthreads();
   }
   float bv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -79,17 +88,18 @@ bias_silu_nhwc_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* 
   if (chan_sum) {
     if (pl < lanes) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(&s_sum[cg * 8 + j], acc[j]);
+      for (int j = 0; j < 8; ++j) atomicAdd(&s_sum[cg * 8 + j], se_fixed(acc[j]));
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(chan_sum + (int64_t)b * C + c, s_sum[c]);
+    for (int c = threadIdx.x; c < C; c += blockDim.x)
+      atomicAdd(reinterpret_cast<unsigned long long*>(chan_sum) + (int64_t)b * C + c, s_sum[c]);
   }
 }
 
 }  // namespace ccvpe
 
 extern "C" int ccvpe_bias_silu_nhwc(const void* x, const void* bias, void* y, int64_t y_sb, int64_t y_sh, int64_t y_sw,
-                                    int B, int H, int W, int C, float* chan_sum, void* stream) {
+                                    int B, int H, int W, int C, int64_t* chan_sum, void* stream) {
   using namespace ccvpe;
   CCVPE_REQUIRE(x && y, "ccvpe_bias_silu_nhwc: null pointer");
   CCVPE_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && C <= 2048, "ccvpe_bias_silu_nhwc: bad shape B=%d H=%d W=%d C=%d",
@@ -106,8 +116,8 @@ extern "C" int ccvpe_bias_silu_nhwc(const void* x, const void* bias, void* y, in
   ppb = (ppb + lanes - 1) / lanes * lanes;
   if (ppb < lanes) ppb = lanes;
   blocks_x = (int)((HW + ppb - 1) / ppb);
-  bias_silu_nhwc_kernel<<<dim3(blocks_x, B), 256, chan_sum ? C * sizeof(float) : 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x, (const __nv_bfloat16*)bias, (__nv_bfloat16*)y, y_sb, y_sh, y_sw, H, W, C, (int)ppb, chan_sum);
+  bias_silu_nhwc_kernel<<<dim3(blocks_x, B), 256, chan_sum ? C * sizeof(unsigned long long) : 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, (const __nv_bfloat16*)bias, (__nv_bfloat16*)y, y_sb, y_sh, y_sw, H, W, C, (int)ppb, reinterpret_cast<long long*>(chan_sum));
   CCVPE_LAUNCH_CHECK("bias_silu_nhwc_kernel");
   return CCVPE_OK;
 }
@@ -123,28 +133,11 @@ extern "C" int ccvpe_bias_silu_nhwc(const void* x, const void* bias, void* y, in
 // ---------------------------------------------------------------------------------------------------------------------
 namespace ccvpe {
 
-// packed fp32x2 helpers: Blackwell's FFMA2 does two fp32 FMAs per issued instruction, and a bf16x2 word widens to an
-// fp32 pair with one shift and one mask -- the loop below is issue-bound, so instruction count is what matters
-__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ uint64_t bf16x2_to_f32x2(uint32_t v) {
-  return pack_f32x2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
-}
+// (packed fp32x2 helpers -- FFMA2 -- live in common.cuh: the loop below is issue-bound, so instruction count is what matters)
 __device__ __forceinline__ float dw_tanh(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
-}
-__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
 }
 
 // V = channels per thread (8: 16-byte vectors; 4: 8-byte vectors -- half the registers, twice the resident warps, which
@@ -172,7 +165,7 @@ __global__ void __launch_bounds__(256, V == 8 ? 2 : 3)
 dwconv_bias_silu_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_sb, int64_t x_sh, int64_t x_sw,
                         const __nv_bfloat16* __restrict__ w, const __nv_bfloat16* __restrict__ bias,
                         __nv_bfloat16* __restrict__ y, int Ho, int Wo, int C, int CG, int strips_per_block,
-                        float* __restrict__ chan_sum) {
+                        long long* __restrict__ chan_sum) {
   using vec_t = typename DwVec<V>::type;
   constexpr int P = V / 2;                           // fp32x2 pairs per thread
   constexpr int TW = 4;                              // outputs per thread along W
@@ -180,9 +173,9 @@ dwconv_bias_silu_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_sb, int64
   // A block owns one image (blockIdx.y), one chunk of CG V-channel groups (blockIdx.z) and a range of strips
   // (blockIdx.x): wide low-resolution layers are split over channels so that every block still has a whole image's worth
   // of pixels to amortise its weight load over.
-  extern __shared__ __align__(16) float s_sum[];     // [CG*V] channel sums, then the chunk's fp32 weights [K*K][CG*V]
+  extern __shared__ __align__(16) unsigned long long s_sum[];   // [CG*V] fixed-point channel sums, then the chunk's fp32 weights [K*K][CG*V]
   const int CC = CG * V;                             // channels of a full chunk
-  float* s_w = s_sum + CC;
+  float* s_w = reinterpret_cast<float*>(s_sum + CC);
   const int G = C / V;
   const int g0 = blockIdx.z * CG;                    // first channel group of this chunk
   const int gn = min(CG, G - g0);                    // groups actually present in it
@@ -218,7 +211,7 @@ dwconv_bias_silu_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_sb, int64
   const int n_strips = Ho * strips_row;
   const int s_lo = blockIdx.x * strips_per_block;
   const int s_hi = min(n_strips, s_lo + strips_per_block);
-  for (int c = threadIdx.x; c < CC; c += blockDim.x) s_sum[c] = 0.f;
+  for (int c = threadIdx.x; c < CC; c += blockDim.x) s_sum[c] = 0ull;
   __syncthreads();
   float csum[V];
 #pragma unroll
@@ -298,10 +291,11 @@ dwconv_bias_silu_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_sb, int64
   if (chan_sum) {
     if (active) {
 #pragma unroll
-      for (int j = 0; j < V; ++j) atomicAdd(&s_sum[cl * V + j], csum[j]);
+      for (int j = 0; j < V; ++j) atomicAdd(&s_sum[cl * V + j], se_fixed(csum[j]));
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < gn * V; c += blockDim.x) atomicAdd(chan_sum + (int64_t)b * C + g0 * V + c, s_sum[c]);
+    for (int c = threadIdx.x; c < gn * V; c += blockDim.x)
+      atomicAdd(reinterpret_cast<unsigned long long*>(chan_sum) + (int64_t)b * C + g0 * V + c, s_sum[c]);
   }
 }
 
@@ -403,7 +397,7 @@ stem_conv_silu_kernel(const float* __restrict__ x, const float* __restrict__ w, 
 // grid (B, row chunks): every block recomputes its image's gate (two tiny mat-vecs) and scales its rows of w_proj.
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(512)
-se_gate_scale_kernel(const float* __restrict__ chan_sum, float inv_hw, const __nv_bfloat16* __restrict__ w_red,
+se_gate_scale_kernel(const long long* __restrict__ chan_sum, float inv_hw, const __nv_bfloat16* __restrict__ w_red,
                      const __nv_bfloat16* __restrict__ b_red, const __nv_bfloat16* __restrict__ w_se_t,
                      const __nv_bfloat16* __restrict__ b_se, const __nv_bfloat16* __restrict__ w_proj,
                      __nv_bfloat16* __restrict__ wg, int mid, int R, int cout, int rows_per_block) {
@@ -411,7 +405,7 @@ se_gate_scale_kernel(const float* __restrict__ chan_sum, float inv_hw, const __n
   float* s_mean = s_se;
   float* s_h = s_se + mid;
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int m = tid; m < mid; m += blockDim.x) s_mean[m] = chan_sum[(int64_t)b * mid + m] * inv_hw;
+  for (int m = tid; m < mid; m += blockDim.x) s_mean[m] = __ll2float_rn(chan_sum[(int64_t)b * mid + m]) * (inv_hw * (1.f / kSeFixedScale));
   __syncthreads();
   const int n_warps = blockDim.x >> 5;
   for (int r = warp; r < R; r += n_warps) {           // one warp per reduced channel, 8 bf16 per lane per step
@@ -500,7 +494,7 @@ extern "C" int ccvpe_wrap_columns_nhwc(void* buf, int B, int H, int W, int C, in
   return CCVPE_OK;
 }
 
-extern "C" int ccvpe_se_gate_scale(const float* chan_sum, float inv_hw, const void* w_red, const void* b_red,
+extern "C" int ccvpe_se_gate_scale(const int64_t* chan_sum, float inv_hw, const void* w_red, const void* b_red,
                                    const void* w_se, const void* b_se, const void* w_proj, void* wg, int B, int mid,
                                    int R, int cout, void* stream) {
   using namespace ccvpe;
@@ -515,7 +509,7 @@ extern "C" int ccvpe_se_gate_scale(const float* chan_sum, float inv_hw, const vo
   const size_t sm = (size_t)(mid + R) * sizeof(float);
   CCVPE_REQUIRE(sm <= 48 * 1024, "ccvpe_se_gate_scale: mid too large");
   se_gate_scale_kernel<<<grid, 512, sm, (cudaStream_t)stream>>>(
-      chan_sum, inv_hw, (const __nv_bfloat16*)w_red, (const __nv_bfloat16*)b_red, (const __nv_bfloat16*)w_se,
+      reinterpret_cast<const long long*>(chan_sum), inv_hw, (const __nv_bfloat16*)w_red, (const __nv_bfloat16*)b_red, (const __nv_bfloat16*)w_se,
       (const __nv_bfloat16*)b_se, (const __nv_bfloat16*)w_proj, (__nv_bfloat16*)wg, mid, R, cout, rows);
   CCVPE_LAUNCH_CHECK("se_gate_scale_kernel");
   return CCVPE_OK;
@@ -570,7 +564,7 @@ extern "C" int ccvpe_pointwise_silu_nhwc(const void* x, int B, int H, int W, int
 
 extern "C" int ccvpe_dwconv_bias_silu_nhwc(const void* x, int64_t x_sb, int64_t x_sh, int64_t x_sw, int Hp, int Wp,
                                            const void* w, const void* bias, void* y, int B, int C, int K, int S,
-                                           float* chan_sum, void* stream) {
+                                           int64_t* chan_sum, void* stream) {
   using namespace ccvpe;
   CCVPE_REQUIRE(x && w && bias && y, "ccvpe_dwconv_bias_silu_nhwc: null pointer");
   CCVPE_REQUIRE(B > 0 && C > 0 && C % 8 == 0 && C <= 2048, "ccvpe_dwconv_bias_silu_nhwc: bad shape B=%d C=%d", B, C);
@@ -605,22 +599,21 @@ extern "C" int ccvpe_dwconv_bias_silu_nhwc(const void* x, int64_t x_sb, int64_t 
   blocks_x = (int)((n_strips + spb - 1) / spb);
   CCVPE_REQUIRE(chunks <= 65535 && B <= 65535, "ccvpe_dwconv_bias_silu_nhwc: grid too large");
   const dim3 grid(blocks_x, B, chunks);
-  const size_t sm = (size_t)CG * V * sizeof(float) * (1 + K * K);
+  const size_t sm = (size_t)CG * V * (sizeof(unsigned long long) + sizeof(float) * K * K);
   CCVPE_REQUIRE(sm <= 96 * 1024, "ccvpe_dwconv_bias_silu_nhwc: K*K*C too large for shared memory");
-  static thread_local bool attr_set = false;
-  if (!attr_set) {
+  static thread_local uint64_t attr_set = 0;
+  if (first_use_on_device(attr_set)) {
 #define CCVPE_DW_ATTR(KK, SS, VV) \
   cudaFuncSetAttribute(dwconv_bias_silu_kernel<KK, SS, VV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)
     CCVPE_DW_ATTR(3, 1, 8); CCVPE_DW_ATTR(3, 2, 8); CCVPE_DW_ATTR(5, 1, 8); CCVPE_DW_ATTR(5, 2, 8);
     CCVPE_DW_ATTR(3, 1, 4); CCVPE_DW_ATTR(3, 2, 4); CCVPE_DW_ATTR(5, 1, 4); CCVPE_DW_ATTR(5, 2, 4);
 #undef CCVPE_DW_ATTR
-    attr_set = true;
   }
   cudaStream_t st = (cudaStream_t)stream;
 #define CCVPE_DW(KK, SS, VV)                                                                                          \
   dwconv_bias_silu_kernel<KK, SS, VV><<<grid, 256, sm, st>>>((const __nv_bfloat16*)x, x_sb, x_sh, x_sw,               \
                                                              (const __nv_bfloat16*)w, (const __nv_bfloat16*)bias,     \
-                                                             (__nv_bfloat16*)y, Ho, Wo, C, CG, (int)spb, chan_sum)
+                                                             (__nv_bfloat16*)y, Ho, Wo, C, CG, (int)spb, reinterpret_cast<long long*>(chan_sum))
   if (V == 8) {
     if (K == 3 && S == 1) CCVPE_DW(3, 1, 8);
     else if (K == 3 && S == 2) CCVPE_DW(3, 2, 8);

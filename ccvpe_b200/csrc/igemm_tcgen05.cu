@@ -550,19 +550,17 @@ int igemm_tcgen05(const ccvpe_igemm_desc& d, cudaStream_t st, const TcOutPad* ou
   cudaError_t attr_err = cudaSuccess;
 #define CCVPE_LAUNCH_IGEMM(MODE, R1, F32)                                                                              \
   do {                                                                                                                 \
-    static thread_local bool attr_l = false, attr_h = false;                                                           \
+    static thread_local uint64_t attr_l = 0, attr_h = 0;                                                               \
     if (light) {                                                                                                       \
-      if (!attr_l) {                                                                                                   \
+      if (first_use_on_device(attr_l)) {                                                                               \
         attr_err = cudaFuncSetAttribute(igemm_tcgen05_kernel<true, MODE, R1, F32>,                                     \
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8192);               \
-        attr_l = true;                                                                                                 \
       }                                                                                                                \
       igemm_tcgen05_kernel<true, MODE, R1, F32><<<grid, 64 + 32 * TC_EPI_WARPS, smem, st>>>(p);                         \
     } else {                                                                                                           \
-      if (!attr_h) {                                                                                                   \
+      if (first_use_on_device(attr_h)) {                                                                               \
         attr_err = cudaFuncSetAttribute(igemm_tcgen05_kernel<false, MODE, R1, F32>,                                    \
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8192);               \
-        attr_h = true;                                                                                                 \
       }                                                                                                                \
       igemm_tcgen05_kernel<false, MODE, R1, F32><<<grid, 64 + 32 * TC_EPI_WARPS, smem, st>>>(p);                        \
     }                                                                                                                  \

@@ -189,7 +189,8 @@ int launch_match_simt(const T* x, int B, int HW, int C, const float* G, const fl
   return check_launch("match_level_simt_kernel");
 }
 
-bool match_tcgen05_supported(int dtype, int C, int L, int n_rolls, int ld_scores_cl);   // match_tcgen05.cu
+bool match_tcgen05_supported(int dtype, int C, int L, int offset, const int32_t* shifts_host, int n_rolls,
+                             int ld_scores_cl);   // match_tcgen05.cu
 int match_tcgen05(const void* x, int B, int HW, int C, const float* g, int L, int offset, const int32_t* shifts_host,
                   int n_rolls, uint32_t max_mask, float* scores, void* scores_cl, int ld_scores_cl, float* max_out,
                   float* inv_norm, void* xhat, float* scratch, cudaStream_t st);
@@ -198,10 +199,19 @@ int match_tcgen05(const void* x, int B, int HW, int C, const float* g, int L, in
 
 extern "C" int64_t ccvpe_match_scratch_elems(int B, int C, int n_rolls) {
   // SIMT backend: G fp32 [B, R, C] + M [R, C] + gnorm [B], each region rounded up to 64 floats (256 B);
-  // tcgen05 backend: G bf16 [B, 32, C] (= B*16*C floats) + gnorm [B].  Sized for the larger of the two.
+  // tcgen05 backend: G bf16 [B, 32, C] (= B*16*C floats) + gnorm [B] + the window-membership table (<= 40 KB).
+  // Sized for the larger of the two.
   auto up = [](int64_t v) { return (v + 63) / 64 * 64; };
   const int r = n_rolls > 17 ? n_rolls : 17;
-  return up((int64_t)B * r * C) + up((int64_t)n_rolls * C) + up(B) + 256;
+  return up((int64_t)B * r * C) + up((int64_t)n_rolls * C) + up(B) + 256 + 10240 + 128;
+}
+
+extern "C" int ccvpe_match_plan(int dtype, int C, int L, int offset, const int32_t* shifts_host, int n_rolls,
+                                int ld_scores_cl, int backend) {
+  using namespace ccvpe;
+  CCVPE_REQUIRE(shifts_host && C > 0 && L > 0 && L <= C && n_rolls > 0 && n_rolls <= 24, "ccvpe_match_plan: bad argument");
+  if (backend == CCVPE_BACKEND_SIMT) return 0;
+  return match_tcgen05_supported(dtype, C, L, offset, shifts_host, n_rolls, ld_scores_cl) ? 1 : 0;
 }
 
 extern "C" int ccvpe_match_level(const void* x, int dtype, int B, int HW, int C, const float* g, int L, int offset,
@@ -218,9 +228,9 @@ extern "C" int ccvpe_match_level(const void* x, int dtype, int B, int HW, int C,
   CCVPE_REQUIRE(aligned16(x) && aligned16(scratch), "ccvpe_match_level: x/scratch must be 16-byte aligned");
   CCVPE_REQUIRE(!scores_cl || ld_scores_cl >= n_rolls, "ccvpe_match_level: ld_scores_cl=%d < n_rolls", ld_scores_cl);
   cudaStream_t st = (cudaStream_t)stream;
-  const bool tc_ok = match_tcgen05_supported(dtype, C, L, n_rolls, scores_cl ? ld_scores_cl : 0);
+  const bool tc_ok = match_tcgen05_supported(dtype, C, L, offset, shifts_host, n_rolls, scores_cl ? ld_scores_cl : 0);
   if (backend == CCVPE_BACKEND_TCGEN05 && !tc_ok)
-    return fail(CCVPE_ERR_UNSUPPORTED, "ccvpe_match_level: tcgen05 backend needs bf16, L == C, n_rolls <= 32");
+    return fail(CCVPE_ERR_UNSUPPORTED, "ccvpe_match_level: tcgen05 backend needs bf16, n_rolls <= 24 and a window table <= 40 KB");
   if ((backend == CCVPE_BACKEND_TCGEN05 || backend == CCVPE_BACKEND_AUTO) && tc_ok)
     return match_tcgen05(x, B, HW, C, g, L, offset, shifts_host, n_rolls, max_mask, scores, scores_cl, ld_scores_cl,
                          max_out, inv_norm, xhat, scratch, st);

@@ -284,8 +284,9 @@ class PostEncoderPipeline:
             x_in, g_in = x, g[l]
             # algorithmic traffic: read x once, write the score volume + max + 1/norm
             nbytes = x.numel() * x.element_size() + (R + 2) * B * H * W * 4
-            mk = "match_tcgen05_kernel" if (dtype == torch.bfloat16 and L == C and
-                                            self.backend != cabi.BACKEND_SIMT) else "match_level_simt_kernel"
+            mk = "match" if self.timer is None else cabi.match_kernel_name(
+                dtype, C, L, spec.window_offset(C, L), [i * stride for i in rolls], SCORES_CL_PAD if l == 0 else 0,
+                cabi.BACKEND_SIMT if self.backend == cabi.BACKEND_SIMT else cabi.BACKEND_AUTO)
             self._op(mk + ":match|l%d" % (l + 1), 2.0 * R * L * B * H * W, nbytes, lambda: cabi.match_level(
                 x_in, g_in, spec.window_offset(C, L), [i * stride for i in rolls], mask, scores=scores,
                 scores_cl=scores_cl if l == 0 else None, max_out=mx, inv_norm=inv,
@@ -349,5 +350,6 @@ def decode_pose(heatmap: torch.Tensor, ori: torch.Tensor) -> Dict[str, torch.Ten
                cs=torch.empty((B, 2), dtype=torch.float32, device=dev),
                angle=torch.empty(B, dtype=torch.float64, device=dev), valid=torch.empty(B, dtype=torch.uint8, device=dev))
     scratch = torch.empty(cabi.pose_scratch_bytes(B, H * W), dtype=torch.uint8, device=dev)
-    cabi.pose_decode(heatmap, ori, out["idx"], out["rc"], out["cs"], out["angle"], out["valid"], scratch)
+    with cabi.device_of(heatmap):
+        cabi.pose_decode(heatmap, ori, out["idx"], out["rc"], out["cs"], out["angle"], out["valid"], scratch)
     return out

@@ -139,8 +139,10 @@ class FastEncoder:
         sums = None
         if x_nhwc.is_cuda and x_nhwc.dtype == torch.bfloat16:
             if want_sum:
-                sums = torch.zeros((B, C), dtype=torch.float32, device=x_nhwc.device)
+                sums = torch.zeros((B, C), dtype=torch.int64, device=x_nhwc.device)
             cabi.bias_silu_nhwc(x_nhwc.contiguous(), bias, out, sums)
+            if want_sum:
+                sums = sums.double().div_(cabi.SE_SUM_SCALE).float()
         else:
             t = x_nhwc if bias is None else x_nhwc + bias
             torch.ops.aten.silu.out(t, out=out)
@@ -182,7 +184,7 @@ class FastEncoder:
         cur = None                                                                   # activated NHWC tensor
         outs: List[torch.Tensor] = []
         # squeeze-excite channel sums of all blocks: one zero fill per forward instead of one per block
-        sums_ws = torch.zeros(x.shape[0] * self._mid_total, dtype=torch.float32, device=x.device) if fused_dw else None
+        sums_ws = torch.zeros(x.shape[0] * self._mid_total, dtype=torch.int64, device=x.device) if fused_dw else None
         sums_off = 0
         for o in self.blocks:
             dw_pad = (o.pad_lo, o.pad_hi) if (self.circular or o.stride == 2 or fused_dw) else None

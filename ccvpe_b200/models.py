@@ -170,7 +170,8 @@ class _CVMBase(nn.Module):
             fs, multi = se.extract_features_multiscale(sat)
             return fg, fs, multi, torch.bfloat16
         # fp32 means fp32: cuDNN must not silently drop the encoders to TF32 (torch's default for convolutions)
-        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+        cudnn = torch.backends.cudnn           # (keep the caller's benchmark / deterministic choices)
+        with cudnn.flags(enabled=True, benchmark=cudnn.benchmark, deterministic=cudnn.deterministic, allow_tf32=False):
             fg = self.grd_efficientnet.extract_features(grd)                      # reference models.py:151
             fs, multi = self.sat_efficientnet.extract_features_multiscale(sat)    # reference models.py:166
         return fg, fs, multi, (torch.bfloat16 if self._precision == "bf16" else torch.float32)
@@ -186,7 +187,9 @@ class _CVMBase(nn.Module):
         if not (grd.is_cuda and sat.is_cuda):
             raise cabi.CcvpeError("ccvpe_b200 models run on CUDA (sm_100a) only; there is no CPU fallback -- "
                                   "move the model and inputs to a B200")
-        with torch.no_grad():
+        if sat.device != grd.device:
+            raise cabi.CcvpeError("grd (%s) and sat (%s) must be on the same device" % (grd.device, sat.device))
+        with torch.no_grad(), cabi.device_of(grd):     # kernels / stream / func attributes follow the tensors' device
             if self._graphs[0] is not None and not self.training and self.pipeline.timer is None:
                 return self._forward_graphed(grd, sat)
             return self._forward_eager(grd, sat)
@@ -245,7 +248,16 @@ class CVM_VIGOR(_CVMBase):
 class CVM_VIGOR_ori_prior(_CVMBase):
     """reference models.py:346 -- localisation sweeps only orientations within +-ori_noise (multiples of 18 deg)."""
 
+    #: the matching kernels sweep at most this many orientations per level (24 = +-198 deg; a prior wider than +-180 deg
+    #: sweeps orientations twice and carries no information)
+    MAX_ROLLS = 24
+
     def __init__(self, device, ori_noise, circular_padding=True):
+        n_rolls = 2 * int(float(ori_noise) / 18) + 1
+        if float(ori_noise) < 0 or n_rolls > self.MAX_ROLLS:
+            raise ValueError("CVM_VIGOR_ori_prior: ori_noise=%r sweeps %d orientations per level; this implementation "
+                             "supports 0 <= ori_noise < %d (at most %d orientations; +-180 deg already covers the full "
+                             "circle)" % (ori_noise, n_rolls, 18 * ((self.MAX_ROLLS - 1) // 2 + 1), self.MAX_ROLLS))
         super().__init__(VIGOR, device, circular_padding, ori_noise=float(ori_noise))
         self.ori_noise = ori_noise
 

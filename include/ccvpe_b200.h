@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define CCVPE_ABI_VERSION 1
+#define CCVPE_ABI_VERSION 2
 
 enum { CCVPE_F32 = 0, CCVPE_BF16 = 1 };
 
@@ -129,6 +129,10 @@ int ccvpe_igemm_plan(const ccvpe_igemm_desc* desc);
  * scratch: fp32, at least ccvpe_match_scratch_elems(B, C, n_rolls) elements.
  * ------------------------------------------------------------------------------------------------------------- */
 int64_t ccvpe_match_scratch_elems(int B, int C, int n_rolls);
+/* which kernel ccvpe_match_level would launch: 0 = match_level_simt_kernel (fp32 inputs, CCVPE_BACKEND_SIMT),
+ * 1 = match_tcgen05_kernel (bf16: full-circle and windowed levels); < 0 = error. */
+int ccvpe_match_plan(int dtype, int C, int L, int offset, const int32_t* shifts_host, int n_rolls, int ld_scores_cl,
+                     int backend);
 int ccvpe_match_level(const void* x, int dtype, int B, int HW, int C,
                       const float* g, int L, int offset, const int32_t* shifts_host, int n_rolls, uint32_t max_mask,
                       float* scores, void* scores_cl, int ld_scores_cl, float* max_out, float* inv_norm, void* xhat,
@@ -157,22 +161,26 @@ int ccvpe_pose_decode(const float* heatmap, const float* ori, int B, int H, int 
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Encoder glue (first step; the encoders themselves stay cuDNN/cuBLAS through PyTorch):
- *   y[b,h,w,c] = SiLU(x[b,h,w,c] + bias[c]);   chan_sum[b,c] += sum_{h,w} y[b,h,w,c]   (optional, fp32, caller zeroes it)
+ *   y[b,h,w,c] = SiLU(x[b,h,w,c] + bias[c]);   chan_sum[b,c] += sum_{h,w} y[b,h,w,c]   (optional, caller zeroes it)
+ * chan_sum is 64-bit FIXED POINT in units of 2^-20 (CCVPE_SE_SUM_SCALE): integer accumulation is order independent, so
+ * the squeeze-excite statistics -- and with them the whole bf16 path -- are bit-reproducible from run to run.
  * x: contiguous channels-last bf16 [B,H,W,C]; bias: bf16 [C] or NULL; y: bf16 with element strides (y_sb, y_sh, y_sw)
  * between images / rows / pixels (channels contiguous) -- e.g. the interior of a padded buffer.  C % 8 == 0.
  * Replaces x*sigmoid(x) after BN (reference efficientnet_pytorch/model.py:105-110) plus F.adaptive_avg_pool2d (:114).
  * ------------------------------------------------------------------------------------------------------------- */
+#define CCVPE_SE_SUM_SCALE 1048576.0
 int ccvpe_bias_silu_nhwc(const void* x, const void* bias, void* y, int64_t y_sb, int64_t y_sh, int64_t y_sw,
-                         int B, int H, int W, int C, float* chan_sum, void* stream);
+                         int B, int H, int W, int C, int64_t* chan_sum, void* stream);
 
 /* Depthwise KxK conv (K in {3,5}, stride S in {1,2}) over a PRE-PADDED channels-last bf16 buffer, fused with bias, SiLU
  * and the squeeze-excite channel sums (reference efficientnet_pytorch/model.py:108-114 in eval mode, BN folded):
  *   y[b,ho,wo,c] = SiLU(sum_{ky,kx} x[b, ho*S+ky, wo*S+kx, c] * w[ky,kx,c] + bias[c]);  chan_sum[b,c] += sum_{ho,wo} y
  * x: bf16, logical padded size [B,Hp,Wp,C] with element strides (x_sb, x_sh, x_sw), channels contiguous;
- * w: bf16 [K*K, C]; bias: bf16 [C]; y: contiguous bf16 [B,Ho,Wo,C], Ho=(Hp-K)/S+1, Wo=(Wp-K)/S+1; chan_sum fp32 or NULL. */
+ * w: bf16 [K*K, C]; bias: bf16 [C]; y: contiguous bf16 [B,Ho,Wo,C], Ho=(Hp-K)/S+1, Wo=(Wp-K)/S+1; chan_sum int64 fixed point
+ * (see ccvpe_bias_silu_nhwc) [B, C] or NULL. */
 int ccvpe_dwconv_bias_silu_nhwc(const void* x, int64_t x_sb, int64_t x_sh, int64_t x_sw, int Hp, int Wp,
                                 const void* w, const void* bias, void* y, int B, int C, int K, int S,
-                                float* chan_sum, void* stream);
+                                int64_t* chan_sum, void* stream);
 
 /* Encoder stem (reference efficientnet_pytorch/model.py:296-297 in eval mode, BN folded; circular variant: the reference's
  * models.py circular-padding patch of the ground encoder): 3x3 stride-2 conv over the fp32 NCHW image with the reference's
@@ -193,11 +201,11 @@ int ccvpe_stem_conv_silu_nhwc(const float* x, int B, int H, int W, const float* 
 int ccvpe_wrap_columns_nhwc(void* buf, int B, int H, int W, int C, int pad_lo, int pad_hi, void* stream);
 
 /* Squeeze-excite gate folded into the projection weights (reference efficientnet_pytorch/model.py:113-121 in eval mode):
- *   mean = chan_sum * inv_hw;  h = SiLU(w_red mean + b_red);  g = sigmoid(w_se h + b_se);  wg[b] = w_proj * diag(g[b])
- * chan_sum fp32 [B, mid] (from ccvpe_dwconv_bias_silu_nhwc); w_red bf16 [R, mid]; b_red bf16 [R]; w_se bf16 [R, mid]
+ *   mean = chan_sum / CCVPE_SE_SUM_SCALE * inv_hw;  h = SiLU(w_red mean + b_red);  g = sigmoid(w_se h + b_se);  wg[b] = w_proj * diag(g[b])
+ * chan_sum int64 fixed point [B, mid] (from ccvpe_dwconv_bias_silu_nhwc); w_red bf16 [R, mid]; b_red bf16 [R]; w_se bf16 [R, mid]
  * (the excite weights TRANSPOSED, so the gate mat-vec reads them coalesced); b_se bf16 [mid]; w_proj bf16 [cout, mid]; wg bf16 [B, cout, mid] = the per-image B operand of the projection GEMM
  * (W (g . x) == (W diag(g)) x, so the broadcast multiply over the expanded activation never happens).  mid % 8 == 0. */
-int ccvpe_se_gate_scale(const float* chan_sum, float inv_hw, const void* w_red, const void* b_red, const void* w_se,
+int ccvpe_se_gate_scale(const int64_t* chan_sum, float inv_hw, const void* w_red, const void* b_red, const void* w_se,
                         const void* b_se, const void* w_proj, void* wg, int B, int mid, int R, int cout, void* stream);
 
 /* Pointwise (1x1) convolution + bias + SiLU over channels-last bf16 pixels on the tcgen05 pipeline -- the MBConv expand

@@ -15,7 +15,7 @@ for (B, H, W, C, padded, sums) in [(64, 256, 256, 96, True, False), (64, 128, 12
         out = buf[:, :H, :W, :]
     else:
         out = torch.empty_like(x)
-    s = torch.zeros(B, C, device=dev) if sums else None
+    s = torch.zeros(B, C, device=dev, dtype=torch.int64) if sums else None
     for _ in range(3):
         cabi.bias_silu_nhwc(x, bias, out, s)
     torch.cuda.synchronize()

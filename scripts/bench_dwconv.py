@@ -35,7 +35,7 @@ for (B, H, W, C, K, S) in cases:
     bias = torch.randn(C, device=dev).to(torch.bfloat16)
     Ho, Wo = (H + lo + hi - K) // S + 1, (W + lo + hi - K) // S + 1
     y = torch.empty(B, Ho, Wo, C, device=dev, dtype=torch.bfloat16)
-    sums = torch.zeros(B, C, device=dev)
+    sums = torch.zeros(B, C, device=dev, dtype=torch.int64)
     t_fused = timeit(lambda: cabi.dwconv_bias_silu_nhwc(buf, wt, bias, y, K, S, sums))
     tot += t_fused
     nbytes = (buf.numel() + y.numel()) * 2

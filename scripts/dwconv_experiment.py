@@ -14,7 +14,7 @@ for (B,H,W,C,K,S) in [(64,64,64,240,5,1),(64,32,32,672,5,1),(64,128,128,144,3,1)
     lo=hi=(K-1)//2
     buf = torch.randn(B, H+lo+hi, W+lo+hi, C, device=dev).to(torch.bfloat16)
     wt = (torch.randn(K*K, C, device=dev)*0.3).to(torch.bfloat16); bias=torch.randn(C,device=dev).to(torch.bfloat16)
-    y = torch.empty(B,H,W,C,device=dev,dtype=torch.bfloat16); sums=torch.zeros(B,C,device=dev)
+    y = torch.empty(B,H,W,C,device=dev,dtype=torch.bfloat16); sums=torch.zeros(B,C,device=dev,dtype=torch.int64)
     t_full = timeit(lambda: cabi.dwconv_bias_silu_nhwc(buf, wt, bias, y, K, S, sums))
     same_row = buf[:, :1].expand(B, H+lo+hi, W+lo+hi, C)          # every input row is row 0 of the image: no vertical L2 re-reads
     t_row = timeit(lambda: cabi.dwconv_bias_silu_nhwc(same_row, wt, bias, y, K, S, sums))

@@ -166,6 +166,76 @@ def test_match_level(cuda_device, case, dtype, tol):
     assert torch.all(cl[..., R:] == 0)
 
 
+#: windowed levels on the tensor-core path: (name, B, C, L, H, rolls, stride, centred) -- every windowed MATCH_CASE plus the
+#: table granularities (one row per K block / per 8 channels / per channel) at full-size shapes
+MATCH_TC_WINDOWED = [c for c in MATCH_CASES if c[3] < c[2]] + [
+    ("kitti_l3",     2, 256,  128,  32, list(range(16)),       32,  False),   # unit = K block of 64? no: 32 -> per 8 channels
+    ("kitti_l4",     1, 128,  64,   64, list(range(16)),       16,  False),
+    ("kitti_l5",     2, 128,  32,   128, list(range(16)),      8,   False),
+    ("fov180_l1",    2, 1280, 640,  8,  list(range(-4, 5)),    64,  False),   # one table row per K block
+    ("fov180_l5",    1, 80,   40,   128, list(range(-4, 5)),   4,   False),   # per channel
+    ("fov108_l3",    2, 320,  96,   32, list(range(-4, 5)),    16,  False),
+    ("oxford_l2",    1, 640,  112,  16, list(range(20)),       32,  True),
+    ("oxford_l3",    2, 320,  56,   32, list(range(20)),       16,  True),    # per channel, 20 orientations
+    ("oxford_l5",    1, 80,   14,   128, list(range(20)),      4,   True),
+]
+
+
+@pytest.mark.parametrize("case", MATCH_TC_WINDOWED, ids=[c[0] for c in MATCH_TC_WINDOWED])
+def test_match_level_tcgen05_windowed(cuda_device, case):
+    """bf16 tensor-core correlation, windowed levels (L < C: limited FoV, KITTI, Oxford's centred window; reference
+    models.py:489-511, 788-920, 1087-1215) vs the oracle on the same bf16-rounded inputs.  Tolerance 1e-2 of max|ref|
+    (the ground descriptor is rounded to bf16 inside the kernel; windows as short as 7 channels)."""
+    name, B, C, L, H, rolls, stride, centred = case
+    g = _gen(13)
+    dev = cuda_device
+    x = torch.randn(B, C, H, H, generator=g)
+    gd = torch.randn(B, L, generator=g)
+    xr = x.to(torch.bfloat16).float()
+    ref = orc.match_level(xr, gd, rolls, stride, centred)
+    offset = int(C / 2 - L / 2) if centred else 0
+    R = len(rolls)
+    shifts = [i * stride for i in rolls]
+    assert cabi.match_kernel_name(torch.bfloat16, C, L, offset, shifts, 32) == "match_tcgen05_kernel"
+    x_cl = _cl(x, torch.bfloat16, dev)
+    scores = torch.empty(B, R, H, H, device=dev)
+    scores_cl = torch.full((B, H, H, 32), 7.0, device=dev, dtype=torch.bfloat16)
+    mx = torch.empty(B, H, H, device=dev)
+    inv = torch.empty(B, H, H, device=dev)
+    scratch = torch.empty(cabi.match_scratch_elems(B, C, R), device=dev)
+    mask = sum(1 << i for i in range(R) if i % 4 != 2)
+    cabi.match_level(x_cl, gd.to(dev), offset, shifts, mask, scores=scores, scores_cl=scores_cl,
+                     max_out=mx, inv_norm=inv, scratch=scratch, backend=cabi.BACKEND_TCGEN05)
+    torch.cuda.synchronize()
+    assert rel_err(scores, ref) < 1e-2, rel_err(scores, ref)
+    sel = [i for i in range(R) if i % 4 != 2]
+    assert rel_err(mx, ref[:, sel].max(dim=1)[0]) < 1e-2
+    assert rel_err(1.0 / inv, xr.norm(dim=1)) < 1e-4
+    cl = scores_cl.float()
+    assert rel_err(cl[..., :R].permute(0, 3, 1, 2), ref) < 2e-2
+    assert torch.all(cl[..., R:] == 0)
+
+
+def test_match_level_tcgen05_zero_window_is_nan(cuda_device):
+    """No epsilon in the cosine denominator on the tensor-core path either: an all-zero window gives NaN (models.py:196),
+    the other windows of the same pixel stay finite."""
+    dev = cuda_device
+    C, L = 64, 16
+    x = torch.randn(1, 8, 16, C, device=dev).to(torch.bfloat16)
+    x[0, 3, 5, 16:32] = 0                                    # window of roll 1 (channels 16..31) is all zero at one pixel
+    gd = torch.randn(1, L, device=dev)
+    scores = torch.empty(1, 4, 8, 16, device=dev)
+    mx = torch.empty(1, 8, 16, device=dev)
+    inv = torch.empty(1, 8, 16, device=dev)
+    scratch = torch.empty(cabi.match_scratch_elems(1, C, 4), device=dev)
+    cabi.match_level(x, gd, 0, [0, 16, 32, 48], 0b1101, scores=scores, max_out=mx, inv_norm=inv, scratch=scratch,
+                     backend=cabi.BACKEND_TCGEN05)
+    torch.cuda.synchronize()
+    assert torch.isnan(scores[0, 1, 3, 5]) and torch.isfinite(scores[0, [0, 2, 3], 3, 5]).all()
+    assert int(torch.isnan(scores).sum()) == 1
+    assert torch.isfinite(mx).all()                          # roll 1 is not in the max mask
+
+
 @pytest.mark.parametrize("B,C,H,R,stride", [(2, 1280, 8, 20, 64), (3, 640, 16, 20, 32), (2, 160, 64, 20, 8),
                                               (1, 80, 128, 20, 4), (2, 40, 256, 20, 2), (1, 320, 10, 21, 16),
                                               (2, 32, 64, 16, 8)])
@@ -399,8 +469,9 @@ def test_bias_silu_nhwc(cuda_device, B, H, W, C, with_bias, padded):
         out = buf[:, 1:1 + H, 1:1 + W, :]
     else:
         out = torch.empty_like(xd)
-    sums = torch.zeros(B, C, device=dev)
+    sums = torch.zeros(B, C, device=dev, dtype=torch.int64)
     cabi.bias_silu_nhwc(xd, bias.to(dev) if with_bias else None, out, sums)
+    sums = sums.double() / cabi.SE_SUM_SCALE
     torch.cuda.synchronize()
     assert rel_err(out.float(), ref) < 1e-2                                   # bf16 output rounding
     assert rel_err(sums, out.float().sum(dim=(1, 2))) < 1e-4                  # sums of what was stored
@@ -471,8 +542,12 @@ def test_dwconv_bias_silu_nhwc(cuda_device, B, H, W, C, K, S):
     buf[:, lo:lo + H, lo:lo + W, :] = x.to(dev)
     Ho, Wo = ref.shape[1], ref.shape[2]
     y = torch.empty(B, Ho, Wo, C, device=dev, dtype=torch.bfloat16)
-    sums = torch.zeros(B, C, device=dev)
+    sums = torch.zeros(B, C, device=dev, dtype=torch.int64)
     cabi.dwconv_bias_silu_nhwc(buf, w.reshape(C, K * K).t().contiguous().to(dev), bias.to(dev), y, K, S, sums)
+    again = torch.zeros_like(sums)
+    cabi.dwconv_bias_silu_nhwc(buf, w.reshape(C, K * K).t().contiguous().to(dev), bias.to(dev), y, K, S, again)
+    assert torch.equal(sums, again)                      # fixed-point accumulation: order independent, bit-reproducible
+    sums = sums.double() / cabi.SE_SUM_SCALE
     torch.cuda.synchronize()
     assert rel_err(y.float(), ref) < 1e-2
     assert rel_err(sums, y.float().sum(dim=(1, 2))) < 1e-4
@@ -534,7 +609,8 @@ def test_se_gate_scale(cuda_device, B, mid, R, cout):
     g = _gen(18)
     dev = cuda_device
     hw = 77
-    sums = torch.randn(B, mid, generator=g) * hw * 0.5
+    sums_fixed = (torch.randn(B, mid, generator=g) * hw * 0.5 * cabi.SE_SUM_SCALE).round().to(torch.int64)
+    sums = (sums_fixed.double() / cabi.SE_SUM_SCALE).float()
     w_red = (torch.randn(R, mid, generator=g) / math.sqrt(mid)).to(torch.bfloat16)
     b_red = torch.randn(R, generator=g).to(torch.bfloat16)
     w_se = (torch.randn(mid, R, generator=g) / math.sqrt(R)).to(torch.bfloat16)
@@ -545,7 +621,7 @@ def test_se_gate_scale(cuda_device, B, mid, R, cout):
     gate = torch.sigmoid(h @ w_se.float().t() + b_se.float())
     ref = w_proj.float().unsqueeze(0) * gate.unsqueeze(1)
     wg = torch.empty(B, cout, mid, device=dev, dtype=torch.bfloat16)
-    cabi.se_gate_scale(sums.to(dev), 1.0 / hw, w_red.to(dev), b_red.to(dev), w_se.t().contiguous().to(dev), b_se.to(dev),
+    cabi.se_gate_scale(sums_fixed.to(dev), 1.0 / hw, w_red.to(dev), b_red.to(dev), w_se.t().contiguous().to(dev), b_se.to(dev),
                        w_proj.to(dev), wg)
     torch.cuda.synchronize()
     assert rel_err(wg.float(), ref) < 1e-2

@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_cabi_library_loads_and_exports_every_declared_symbol():
     lib = cabi.load()
-    assert lib.ccvpe_abi_version() == 1
+    assert lib.ccvpe_abi_version() == cabi.ABI_VERSION
     header = open(os.path.join(ROOT, "include", "ccvpe_b200.h")).read()
     declared = set(re.findall(r"\b(ccvpe_[a-z0-9_]+)\s*\(", header))
     declared.discard("ccvpe_igemm_desc")
