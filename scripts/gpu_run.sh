@@ -1,0 +1,19 @@
+#!/bin/bash
+# usage: scripts/gpu_run.sh <tag> [what...]   -- runs on the GPU box (through gpurun); outputs under gpurun_out/<tag>_*
+tag=$1; shift
+what=${*:-"pytest smoke bench"}
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${tag}_smi.txt 2>&1
+for w in $what; do
+  case $w in
+    pytest) timeout 1500 python -m pytest tests -m gpu -q --timeout 900 -x > gpurun_out/${tag}_pytest_gpu.log 2>&1; tail -5 gpurun_out/${tag}_pytest_gpu.log;;
+    pytest_all) timeout 1500 python -m pytest tests -m gpu -q --timeout 900 > gpurun_out/${tag}_pytest_gpu.log 2>&1; tail -15 gpurun_out/${tag}_pytest_gpu.log;;
+    smoke) timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${tag}_smoke.log 2>&1; tail -3 gpurun_out/${tag}_smoke.log;;
+    bench) timeout 900 python bench.py --steps 10 --warmup 3 --layers gpurun_out/${tag}_layers.txt > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; tail -c 600 gpurun_out/${tag}_bench.json; tail -3 gpurun_out/${tag}_bench.err;;
+    bench_kitti|bench_fov180|bench_fov108|bench_oxford)
+      declare -A m=([bench_kitti]=kitti_b32 [bench_fov180]=vigor_prior72_fov180 [bench_fov108]=vigor_prior72_fov108 [bench_oxford]=oxford_b1)
+      k=${m[$w]}
+      timeout 900 python bench.py --workload $k --steps 10 --warmup 3 --layers gpurun_out/${tag}_layers_$k.txt > gpurun_out/${tag}_bench_$k.json 2> gpurun_out/${tag}_bench_$k.err; head -c 400 gpurun_out/${tag}_bench_$k.json; echo; tail -3 gpurun_out/${tag}_bench_$k.err;;
+    *) echo "unknown step $w";;
+  esac
+done
