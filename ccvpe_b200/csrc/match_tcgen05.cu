@@ -10,12 +10,13 @@
 // accumulate sum_c x^2, which gives both the cosine denominator and the 1/||x|| that F.normalize needs.  The same warps
 // run the epilogue: tcgen05.ld -> divide -> planar fp32 score stores (one pixel per lane: coalesced per orientation),
 // max over the selected orientations, 1/norm, and (bottleneck level only) the channels-last score copy and x-hat.
-// Windowed levels (L < C) need one denominator PER ORIENTATION: sum of x^2 over the channels of window i.  All windows of
-// a level start and end on multiples of u = gcd(C, L, window bases), so the norm warps accumulate
-//     wsq[i] += m[unit(c)][i] * x_c^2          m = 0/1 window-membership table, one row per UNIT of channels,
-// with the table in shared memory (rows read as broadcast LDS.128) and the R accumulators packed in fp32 pairs (FFMA2).
-// UNIT = a whole K block when u % kw == 0 (KITTI levels 1-3, FoV levels 1-2: one table row per K block, R/2 FFMA2 per 64
-// channels), 8 channels when u % 8 == 0, single channels otherwise (Oxford's levels 3-6, limited-FoV levels 5-6).
+// Windowed levels (L < C) need one denominator PER ORIENTATION: sum of x^2 over the channels of window i.  Every window is
+// a (circular) interval of channels, so its sum of squares is a difference of PREFIX sums: a norm thread walks its pixel's
+// channels in order keeping the running sum, and drops a snapshot into shared memory at each of the <= 2R distinct window
+// boundaries (positions are the same for every pixel: an 8-bit event mask per 16-byte chunk, tested on the uniform path;
+// chunks without a boundary -- almost all of them -- take the plain 8-FMA path).  The epilogue forms
+//     wsq[i] = P[end_i] - P[start_i]   (+ P[C] when the window wraps).
+// Cost over the full-circle kernel: one table byte per chunk and <= 2R stores per pixel, whatever the window granularity.
 // The correlation moves 2*R flops per loaded element (AI 8-20 flop/B in bf16) so the roofline that bounds it is HBM;
 // the tensor pipe is what keeps the arithmetic off the critical path.
 #include "tcgen05_common.cuh"
@@ -30,8 +31,8 @@ struct MatchTcParams {
   CUtensorMap tm_x, tm_g;
   int kw, nb, C, HW, B, tiles_per_img, total_tiles, stages, a_bytes, stage_bytes;
   int n_rolls, ld_scores_cl;
-  int wt_rows, wt_pitch;                 // windowed: membership table [wt_rows][wt_pitch] floats (pitch/4 odd: conflict free)
-  const float* wtab;
+  int L, offset, n_events;               // windowed: window length / first channel, distinct boundaries (host count)
+  int shifts[32];                        // roll shifts (channels)
   uint32_t max_mask;
   const float* gnorm;
   const __nv_bfloat16* x;
@@ -48,27 +49,8 @@ struct ShiftArg {
 
 __global__ void build_rolled_descriptor_bf16_kernel(const float* __restrict__ g, int L, int C, int offset,
                                                     const ShiftArg shifts, int n_rolls,
-                                                    __nv_bfloat16* __restrict__ G, float* __restrict__ gnorm,
-                                                    float* __restrict__ wtab, int wt_rows, int wt_pitch, int wt_unit) {
+                                                    __nv_bfloat16* __restrict__ G, float* __restrict__ gnorm) {
   const int b = blockIdx.y, i = blockIdx.x;
-  if (i > MT_N) {
-    // window-membership table (batch independent: written by the b == 0 blocks): row r covers channels
-    // [r * wt_unit, (r + 1) * wt_unit), which lie entirely inside or outside every window by construction of wt_unit
-    if (b != 0 || !wtab) return;
-    for (int e = (i - MT_N - 1) * blockDim.x + threadIdx.x; e < wt_rows * wt_pitch; e += (gridDim.x - MT_N - 1) * blockDim.x) {
-      const int r = e / wt_pitch, col = e - r * wt_pitch;
-      const int c = r * wt_unit;
-      float m = 0.f;
-      if (col < n_rolls && c < C) {
-        const int base = ((offset + shifts.s[col]) % C + C) % C;
-        int k = c - base;
-        if (k < 0) k += C;
-        m = k < L ? 1.f : 0.f;
-      }
-      wtab[e] = m;
-    }
-    return;
-  }
   if (i < MT_N) {
     __nv_bfloat16* row = G + ((int64_t)b * MT_N + i) * C;
     if (i < n_rolls) {
@@ -99,26 +81,12 @@ __global__ void build_rolled_descriptor_bf16_kernel(const float* __restrict__ g,
   }
 }
 
-// UNIT: 0 = full circle (one norm for all orientations) | 1 / 8 = membership table row per channel / per 8 channels |
-//       64 = one row per K block
 constexpr int MT_WMAX = 24;              // orientations of a windowed level (C ABI limit)
+constexpr int MT_MAX_EVENTS = 2 * MT_WMAX;
+constexpr int MT_MAX_CHUNKS = 2048 / 8 + 8;   // 16-byte chunks of a pixel (C <= 2048, padded to the K-block width)
 
-template <int UNIT>
-__device__ __forceinline__ void window_accumulate(uint64_t (&wsq)[MT_WMAX / 2], float s, const float* __restrict__ row,
-                                                  int pitch) {
-  const uint64_t ss = pack_f32x2(s, s);
-#pragma unroll
-  for (int i4 = 0; i4 < MT_WMAX / 4; ++i4) {
-    if (i4 * 4 < pitch) {                  // uniform
-      const float4 m = *reinterpret_cast<const float4*>(row + i4 * 4);
-      wsq[2 * i4] = ffma2(ss, pack_f32x2(m.x, m.y), wsq[2 * i4]);
-      wsq[2 * i4 + 1] = ffma2(ss, pack_f32x2(m.z, m.w), wsq[2 * i4 + 1]);
-    }
-  }
-}
-
-template <int UNIT>
-__global__ void __launch_bounds__(MT_THREADS, UNIT == 0 ? 4 : 2) match_tcgen05_kernel(const __grid_constant__ MatchTcParams p) {
+template <bool WINDOWED>
+__global__ void __launch_bounds__(MT_THREADS, WINDOWED ? 3 : 4) match_tcgen05_kernel(const __grid_constant__ MatchTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[MT_MAX_STAGES];
   __shared__ __align__(8) uint64_t bar_empty[MT_MAX_STAGES];
@@ -151,11 +119,55 @@ __global__ void __launch_bounds__(MT_THREADS, UNIT == 0 ? 4 : 2) match_tcgen05_k
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  float* s_wtab = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + p.stages * p.stage_bytes);
-  if (UNIT != 0) {
-    const int n4 = (p.wt_rows * p.wt_pitch) >> 2;
-    for (int e = threadIdx.x; e < n4; e += MT_THREADS)
-      reinterpret_cast<float4*>(s_wtab)[e] = __ldg(reinterpret_cast<const float4*>(p.wtab) + e);
+  // ---- windowed: boundary events (identical for every pixel of the level) ----
+  __shared__ uint32_t s_posbits[2048 / 32 + 1];      // bit p set: a window starts or ends at channel position p (0 < p < C)
+  __shared__ uint16_t s_wordrank[2048 / 32 + 1];     // number of events below word w
+  __shared__ uint8_t s_evmask[MT_MAX_CHUNKS];        // per chunk: bit t set = snapshot after element t of the chunk
+  __shared__ uint8_t s_evbase[MT_MAX_CHUNKS];        // index of the chunk's first snapshot
+  __shared__ int8_t s_roll_a[MT_WMAX], s_roll_b[MT_WMAX], s_roll_wrap[MT_WMAX];   // snapshot ids: -1 = P[0] = 0, -2 = P[C]
+  float* s_snap = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + p.stages * p.stage_bytes);
+  if (WINDOWED) {
+    const int n_words = (p.C + 31) >> 5;
+    for (int w = threadIdx.x; w <= n_words; w += MT_THREADS) s_posbits[w] = 0u;
+    __syncthreads();
+    if ((int)threadIdx.x < p.n_rolls) {
+      const int base = ((p.offset + p.shifts[threadIdx.x]) % p.C + p.C) % p.C;
+      int end = base + p.L;
+      if (end >= p.C) end -= p.C;                    // end == C maps to position 0 of the wrapped copy: handled as P[C]
+      if (base) atomicOr(&s_posbits[base >> 5], 1u << (base & 31));
+      if (end) atomicOr(&s_posbits[end >> 5], 1u << (end & 31));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int acc = 0;
+      for (int w = 0; w <= n_words; ++w) {
+        s_wordrank[w] = (uint16_t)acc;
+        acc += __popc(s_posbits[w]);
+      }
+    }
+    __syncthreads();
+    auto rank_of = [&](int pos) { return (int)s_wordrank[pos >> 5] + __popc(s_posbits[pos >> 5] & ((1u << (pos & 31)) - 1u)); };
+    if ((int)threadIdx.x < p.n_rolls) {
+      const int base = ((p.offset + p.shifts[threadIdx.x]) % p.C + p.C) % p.C;
+      const int end = base + p.L;
+      s_roll_a[threadIdx.x] = (int8_t)(base ? rank_of(base) : -1);
+      s_roll_wrap[threadIdx.x] = (int8_t)(end > p.C ? 1 : 0);
+      s_roll_b[threadIdx.x] = (int8_t)(end == p.C ? -2 : rank_of(end > p.C ? end - p.C : end));
+    }
+    const int n_chunks = (p.nb * p.kw) >> 3;
+    for (int ch = threadIdx.x; ch < n_chunks; ch += MT_THREADS) {
+      // snapshot after element t of chunk ch <=> boundary at position ch*8 + t + 1
+      const int p0 = ch * 8 + 1;
+      uint32_t bits = 0;
+      if (p0 < p.C + 8) {
+        const int w = p0 >> 5, sft = p0 & 31;
+        uint64_t two = (uint64_t)s_posbits[w < n_words + 1 ? w : n_words];
+        if (w + 1 <= n_words) two |= (uint64_t)s_posbits[w + 1] << 32;
+        bits = (uint32_t)(two >> sft) & 0xffu;
+      }
+      s_evmask[ch] = (uint8_t)bits;
+      s_evbase[ch] = (uint8_t)(p0 < p.C ? rank_of(p0) : 0);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -245,44 +257,45 @@ __global__ void __launch_bounds__(MT_THREADS, UNIT == 0 ? 4 : 2) match_tcgen05_k
       const int pix = (tile - b * p.tiles_per_img) * TC_BM + row;     // pixel within the image
       const bool valid = pix < p.HW;
       float sq = 0.f;
-      uint64_t wsq[MT_WMAX / 2];           // windowed: per-orientation sum of squares, packed fp32 pairs
-#pragma unroll
-      for (int i = 0; i < MT_WMAX / 2; ++i) wsq[i] = 0ull;
       // inverse of the TMA swizzle: 16-byte chunk position within the row ^ swz = logical chunk (128B / 64B / 32B swizzle)
       const int swz = p.kw == 64 ? (row & 7) : (p.kw == 32 ? ((row >> 1) & 3) : ((row >> 2) & 1));
+      float* snap = s_snap + row;                      // snapshot e of this pixel: snap[e * 128]
 #pragma unroll 1
       for (int kb = 0; kb < p.nb; ++kb) {
         mbar_wait(smem_u32(&bar_full[stage]), phase);
         const uint8_t* tile_ptr = smem_raw + (smem_base - smem_u32(smem_raw)) + stage * p.stage_bytes + row * row_bytes;
-        float s0 = 0.f, s1 = 0.f;
+        float s0 = WINDOWED ? sq : 0.f, s1 = 0.f;
         for (int j = 0; j < chunks; ++j) {
-          // UNIT == 0: rotate the chunk order by the row index: lanes of a warp then cover all bank groups (conflict free);
-          // the swizzle only permutes chunks inside a row, and a sum of squares does not care about their order.
+          // full circle: rotate the chunk order by the row index: lanes of a warp then cover all bank groups (conflict
+          // free); the swizzle only permutes chunks inside a row, and a sum of squares does not care about their order.
           // Windowed: every lane reads LOGICAL chunk j (physical j ^ swz -- conflict free by construction of the
-          // swizzle), so the membership-table row is the same for the whole warp (broadcast loads).
-          const int phys = UNIT == 0 ? ((j + row) & (chunks - 1)) : (j ^ swz);
+          // swizzle): channels are visited in order, so the running sum is the prefix sum the window boundaries need.
+          const int phys = WINDOWED ? (j ^ swz) : ((j + row) & (chunks - 1));
           const uint4 q = *reinterpret_cast<const uint4*>(tile_ptr + (phys << 4));
           const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q.x));
           const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q.y));
           const float2 f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q.z));
           const float2 f3 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q.w));
-          if (UNIT == 1) {
-            const float* trow = s_wtab + (kb * p.kw + j * 8) * p.wt_pitch;
-            const float e[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
+          if (WINDOWED) {
+            const int gch = kb * chunks + j;
+            const uint32_t ev = s_evmask[gch];         // warp-uniform
+            if (ev == 0u) {
+              s0 = fmaf(f0.x, f0.x, s0); s0 = fmaf(f0.y, f0.y, s0);
+              s0 = fmaf(f1.x, f1.x, s0); s0 = fmaf(f1.y, f1.y, s0);
+              s0 = fmaf(f2.x, f2.x, s0); s0 = fmaf(f2.y, f2.y, s0);
+              s0 = fmaf(f3.x, f3.x, s0); s0 = fmaf(f3.y, f3.y, s0);
+            } else {
+              int e = s_evbase[gch];
+              const float el[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
 #pragma unroll
-            for (int t = 0; t < 8; ++t) {
-              const float x2 = e[t] * e[t];
-              s0 += x2;
-              window_accumulate<UNIT>(wsq, x2, trow + t * p.wt_pitch, p.wt_pitch);
+              for (int t = 0; t < 8; ++t) {
+                s0 = fmaf(el[t], el[t], s0);
+                if ((ev >> t) & 1u) {                  // uniform
+                  snap[e * TC_BM] = s0;
+                  ++e;
+                }
+              }
             }
-          } else if (UNIT == 8) {
-            float a = f0.x * f0.x, b2 = f0.y * f0.y;
-            a = fmaf(f1.x, f1.x, a); b2 = fmaf(f1.y, f1.y, b2);
-            a = fmaf(f2.x, f2.x, a); b2 = fmaf(f2.y, f2.y, b2);
-            a = fmaf(f3.x, f3.x, a); b2 = fmaf(f3.y, f3.y, b2);
-            const float s8 = a + b2;
-            s0 += s8;
-            window_accumulate<UNIT>(wsq, s8, s_wtab + (kb * chunks + j) * p.wt_pitch, p.wt_pitch);
           } else {
             s0 = fmaf(f0.x, f0.x, s0); s1 = fmaf(f0.y, f0.y, s1);
             s0 = fmaf(f1.x, f1.x, s0); s1 = fmaf(f1.y, f1.y, s1);
@@ -290,8 +303,8 @@ __global__ void __launch_bounds__(MT_THREADS, UNIT == 0 ? 4 : 2) match_tcgen05_k
             s0 = fmaf(f3.x, f3.x, s0); s1 = fmaf(f3.y, f3.y, s1);
           }
         }
-        sq += s0 + s1;
-        if (UNIT == 64) window_accumulate<UNIT>(wsq, s0 + s1, s_wtab + kb * p.wt_pitch, p.wt_pitch);
+        if (WINDOWED) sq = s0;                         // (running prefix: carried across K blocks)
+        else sq += s0 + s1;
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bar_empty[stage]));
         if (++stage == p.stages) {
@@ -325,12 +338,14 @@ __global__ void __launch_bounds__(MT_THREADS, UNIT == 0 ? 4 : 2) match_tcgen05_k
 #pragma unroll
         for (int i = 0; i < MT_N; ++i) {
           if (i < p.n_rolls) {
-            if (UNIT != 0 && i < MT_WMAX) {
-              // windowed cosine denominator sqrt(sum_window x^2) * ||g||; a zero window gives 0 * inf = NaN like the
-              // reference's 0 / 0 (models.py:196)
-              float wlo, whi;
-              unpack_f32x2(wsq[i >> 1], wlo, whi);
-              sc[i] = __uint_as_float(v[i]) * (rsqrtf((i & 1) ? whi : wlo) * rgn);
+            if (WINDOWED && i < MT_WMAX) {
+              // windowed cosine denominator sqrt(sum_window x^2) * ||g|| from the prefix-sum snapshots; a zero window gives
+              // 0 * inf = NaN like the reference's 0 / 0 (models.py:196)
+              const int ia = s_roll_a[i], ib = s_roll_b[i];
+              const float pa = ia < 0 ? 0.f : snap[ia * TC_BM];
+              const float pb = ib == -2 ? sq : (ib < 0 ? 0.f : snap[ib * TC_BM]);
+              const float wsq = s_roll_wrap[i] ? (sq - pa) + pb : pb - pa;
+              sc[i] = __uint_as_float(v[i]) * (rsqrtf(fmaxf(wsq, 0.f)) * rgn);
             } else {
               sc[i] = __uint_as_float(v[i]) * rden;
             }
@@ -389,54 +404,32 @@ __global__ void __launch_bounds__(MT_THREADS, UNIT == 0 ? 4 : 2) match_tcgen05_k
   }
 }
 
-// Windowed levels: granularity of the window-membership table and its shape.
-struct WindowPlan {
-  int unit;       // 0 (L == C), 1, 8 or 64 (= one row per K block)
-  int rows, pitch;
-};
-
-static int gcd_int(int a, int b) {
-  while (b) {
-    const int t = a % b;
-    a = b;
-    b = t;
+static int count_window_events(int C, int L, int offset, const int32_t* shifts_host, int n_rolls) {
+  if (L == C) return 0;
+  int pos[2 * MT_WMAX], n = 0;
+  for (int i = 0; i < n_rolls && i < MT_WMAX; ++i) {
+    const int base = ((offset + shifts_host[i]) % C + C) % C;
+    int end = base + L;
+    if (end >= C) end -= C;
+    const int cand[2] = {base, end};
+    for (int k = 0; k < 2; ++k) {
+      if (cand[k] == 0) continue;
+      bool seen = false;
+      for (int j = 0; j < n; ++j) seen |= (pos[j] == cand[k]);
+      if (!seen) pos[n++] = cand[k];
+    }
   }
-  return a < 0 ? -a : a;
+  return n;
 }
-
-static WindowPlan plan_windows(int C, int L, int offset, const int32_t* shifts_host, int n_rolls) {
-  WindowPlan w = {0, 0, 0};
-  if (L == C) return w;
-  int u = gcd_int(C, L);
-  for (int i = 0; i < n_rolls; ++i) u = gcd_int(u, ((offset + shifts_host[i]) % C + C) % C);
-  const int kw = tc_block_width(C), nb = (C + kw - 1) / kw;
-  if (u % kw == 0) {
-    w.unit = 64;
-    w.rows = nb;
-  } else if (u % 8 == 0) {
-    w.unit = 8;
-    w.rows = nb * kw / 8;
-  } else {
-    w.unit = 1;
-    w.rows = nb * kw;
-  }
-  const int r4 = (n_rolls + 3) / 4;
-  w.pitch = 4 * (r4 | 1);          // pitch / 4 odd: table rows 16*odd bytes apart never share a bank group
-  return w;
-}
-
-constexpr int MT_WTAB_MAX_BYTES = 40 * 1024;
 
 bool match_tcgen05_supported(int dtype, int C, int L, int offset, const int32_t* shifts_host, int n_rolls,
                              int ld_scores_cl) {
   if (!(dtype == CCVPE_BF16 && L <= C && C % 8 == 0 && n_rolls <= MT_N && ld_scores_cl % 8 == 0)) return false;
   if (L == C) return true;
-  if (n_rolls > MT_WMAX) return false;
-  const WindowPlan w = plan_windows(C, L, offset, shifts_host, n_rolls);
-  return w.rows * w.pitch * 4 <= MT_WTAB_MAX_BYTES;
+  return n_rolls <= MT_WMAX && C <= 2048;
 }
 
-// scratch layout (bytes from `scratch`): G bf16 [B, 32, C] | gnorm fp32 [B] | window table fp32 [rows, pitch]
+// scratch layout (bytes from `scratch`): G bf16 [B, 32, C] | gnorm fp32 [B]
 int match_tcgen05(const void* x, int B, int HW, int C, const float* g, int L, int offset, const int32_t* shifts_host,
                   int n_rolls, uint32_t max_mask, float* scores, void* scores_cl, int ld_scores_cl, float* max_out,
                   float* inv_norm, void* xhat, float* scratch, cudaStream_t st) {
@@ -444,14 +437,11 @@ int match_tcgen05(const void* x, int B, int HW, int C, const float* g, int L, in
   uint8_t* base = reinterpret_cast<uint8_t*>(scratch);
   __nv_bfloat16* G = reinterpret_cast<__nv_bfloat16*>(base);
   float* gnorm = reinterpret_cast<float*>(base + up((int64_t)B * MT_N * C * 2));
-  float* wtab = reinterpret_cast<float*>(base + up((int64_t)B * MT_N * C * 2) + up((int64_t)B * 4));
-  const WindowPlan wp = plan_windows(C, L, offset, shifts_host, n_rolls);
+  const bool windowed = L < C;
+  const int n_events = count_window_events(C, L, offset, shifts_host, n_rolls);
   ShiftArg sa;   // the roll table travels as a kernel argument (no copy, no sync, graph-capturable)
   for (int i = 0; i < MT_N; ++i) sa.s[i] = i < n_rolls ? shifts_host[i] : 0;
-  const int tab_blocks = wp.unit ? (wp.rows * wp.pitch + 255) / 256 : 0;
-  build_rolled_descriptor_bf16_kernel<<<dim3(MT_N + 1 + (tab_blocks > 8 ? 8 : tab_blocks), B), 256, 0, st>>>(
-      g, L, C, offset, sa, n_rolls, G, gnorm, wp.unit ? wtab : nullptr, wp.rows, wp.pitch,
-      wp.unit == 64 ? tc_block_width(C) : wp.unit);
+  build_rolled_descriptor_bf16_kernel<<<dim3(MT_N + 1, B), 256, 0, st>>>(g, L, C, offset, sa, n_rolls, G, gnorm);
   int rc = check_launch("build_rolled_descriptor_bf16_kernel");
   if (rc != CCVPE_OK) return rc;
 
@@ -467,16 +457,17 @@ int match_tcgen05(const void* x, int B, int HW, int C, const float* g, int L, in
   p.a_bytes = TC_BM * p.kw * 2;
   p.stage_bytes = p.a_bytes + ((MT_N * p.kw * 2 + 1023) / 1024) * 1024;
   // ~52 KB of pipeline per CTA so that four CTAs (16 norm/epilogue warps) share an SM: the epilogue is scalar-ALU and
-  // store bound and needs the extra warps to hide its own latency (windowed: two CTAs per SM -- the per-orientation
-  // accumulators double the register footprint -- with a deeper ring each)
-  int stages = ((wp.unit ? 64 : 52) * 1024) / p.stage_bytes;
+  // store bound and needs the extra warps to hide its own latency (windowed: three CTAs per SM, each with up to 24 KB of
+  // prefix-sum snapshots behind its ring)
+  int stages = (52 * 1024) / p.stage_bytes;
   if (stages < 2) stages = 2;
   p.stages = stages > MT_MAX_STAGES ? MT_MAX_STAGES : stages;
   p.n_rolls = n_rolls;
   p.ld_scores_cl = scores_cl ? ld_scores_cl : 0;
-  p.wt_rows = wp.rows;
-  p.wt_pitch = wp.pitch;
-  p.wtab = wtab;
+  p.L = L;
+  p.offset = offset;
+  p.n_events = n_events;
+  for (int i = 0; i < 32; ++i) p.shifts[i] = sa.s[i];
   p.max_mask = max_mask;
   p.gnorm = gnorm;
   p.x = static_cast<const __nv_bfloat16*>(x);
@@ -494,25 +485,18 @@ int match_tcgen05(const void* x, int B, int HW, int C, const float* g, int L, in
     uint32_t gbox[2] = {(uint32_t)p.kw, MT_N};
     if ((rc = encode_map(&p.tm_g, G, 2, gdims, str, gbox, p.kw)) != CCVPE_OK) return rc;
   }
-  const int smem = p.stages * p.stage_bytes + 1024 + (wp.unit ? wp.rows * wp.pitch * 4 : 0);
+  const int smem = p.stages * p.stage_bytes + 1024 + (windowed ? (n_events > 0 ? n_events : 1) * TC_BM * 4 : 0);
   static thread_local uint64_t attr_set = 0;
   if (first_use_on_device(attr_set)) {
-    cudaError_t e = cudaSuccess;
-#define CCVPE_MT_ATTR(U)                                                                                             \
-  if (e == cudaSuccess)                                                                                              \
-    e = cudaFuncSetAttribute(match_tcgen05_kernel<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, 170 * 1024)
-    CCVPE_MT_ATTR(0); CCVPE_MT_ATTR(1); CCVPE_MT_ATTR(8); CCVPE_MT_ATTR(64);
-#undef CCVPE_MT_ATTR
+    cudaError_t e = cudaFuncSetAttribute(match_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 170 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(match_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 170 * 1024);
     if (e != cudaSuccess) return fail(CCVPE_ERR_CUDA, "cudaFuncSetAttribute(match): %s", cudaGetErrorString(e));
   }
-  const int per_sm = wp.unit ? 2 : 4;
+  const int per_sm = windowed ? 3 : 4;
   const int grid = p.total_tiles < per_sm * sm_count() ? p.total_tiles : per_sm * sm_count();
-  switch (wp.unit) {
-    case 0: match_tcgen05_kernel<0><<<grid, MT_THREADS, smem, st>>>(p); break;
-    case 1: match_tcgen05_kernel<1><<<grid, MT_THREADS, smem, st>>>(p); break;
-    case 8: match_tcgen05_kernel<8><<<grid, MT_THREADS, smem, st>>>(p); break;
-    default: match_tcgen05_kernel<64><<<grid, MT_THREADS, smem, st>>>(p); break;
-  }
+  if (windowed) match_tcgen05_kernel<true><<<grid, MT_THREADS, smem, st>>>(p);
+  else match_tcgen05_kernel<false><<<grid, MT_THREADS, smem, st>>>(p);
   return check_launch("match_tcgen05_kernel");
 }
 

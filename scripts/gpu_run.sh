@@ -14,6 +14,8 @@ for w in $what; do
       declare -A m=([bench_kitti]=kitti_b32 [bench_fov180]=vigor_prior72_fov180 [bench_fov108]=vigor_prior72_fov108 [bench_oxford]=oxford_b1)
       k=${m[$w]}
       timeout 900 python bench.py --workload $k --steps 10 --warmup 3 --layers gpurun_out/${tag}_layers_$k.txt > gpurun_out/${tag}_bench_$k.json 2> gpurun_out/${tag}_bench_$k.err; head -c 400 gpurun_out/${tag}_bench_$k.json; echo; tail -3 gpurun_out/${tag}_bench_$k.err;;
+    pytest_match) timeout 900 python -m pytest tests/test_gpu_kernels.py -m gpu -q --timeout 600 -k match > gpurun_out/${tag}_pytest_match.log 2>&1; tail -8 gpurun_out/${tag}_pytest_match.log;;
+    pytest_train) timeout 1200 python -m pytest tests/test_gpu_train.py -m gpu -q --timeout 900 > gpurun_out/${tag}_pytest_train.log 2>&1; tail -25 gpurun_out/${tag}_pytest_train.log;;
     *) echo "unknown step $w";;
   esac
 done
