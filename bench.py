@@ -353,15 +353,21 @@ def run_ours(args):
         return model.decode_pose(out[1], out[2])
 
     copy_stream = torch.cuda.Stream(device=dev)
+    # e2e: two preallocated device input slots (no allocator traffic inside the timed region): the H2D copy of step i+1
+    # lands in the slot step i-1 used, guarded by an event recorded when that step's kernels were enqueued
+    dev_in = [(torch.empty_like(grd_d), torch.empty_like(sat_d)) for _ in range(2)]
+    slot_free = [None, None]
 
-    def upload():
-        """H2D of one step's inputs from pinned host memory on the copy stream; returns (grd, sat, done-event)."""
+    def upload(slot):
+        """H2D of one step's inputs from pinned host memory on the copy stream; returns the copy-done event."""
         with torch.cuda.stream(copy_stream):
-            g = grd_h.to(dev, non_blocking=True)
-            s = sat_h.to(dev, non_blocking=True)
+            if slot_free[slot] is not None:
+                copy_stream.wait_event(slot_free[slot])
+            dev_in[slot][0].copy_(grd_h, non_blocking=True)
+            dev_in[slot][1].copy_(sat_h, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
-        return g, s, ev
+        return ev
 
     host_results = [None, None]      # double-buffered pinned host copies of the pose tensors
 
@@ -370,19 +376,19 @@ def run_ours(args):
         serving loop: the copy of step i+1 is issued before step i computes (double buffering) and the host reads the
         poses of step i-1 after it has enqueued step i, so the GPU never drains between steps; nothing is reused across
         steps and every step's result is read on the host inside the timed region."""
-        nxt = upload()
+        nxt = upload(0)
         pending = None
         last = None
         for i in range(steps):
-            g, s_, ev = nxt
-            if i + 1 < steps:
-                nxt = upload()
-            torch.cuda.current_stream().wait_event(ev)
-            out = model(g, s_)
-            pose = model.decode_pose(out[1], out[2])
-            g.record_stream(torch.cuda.current_stream())
-            s_.record_stream(torch.cuda.current_stream())
             slot = i % 2
+            ev = nxt
+            if i + 1 < steps:
+                nxt = upload(1 - slot)
+            torch.cuda.current_stream().wait_event(ev)
+            out = model(dev_in[slot][0], dev_in[slot][1])
+            pose = model.decode_pose(out[1], out[2])
+            slot_free[slot] = torch.cuda.Event()
+            slot_free[slot].record()
             if host_results[slot] is None:
                 host_results[slot] = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in pose.items()}
             for k, v in pose.items():
@@ -451,15 +457,14 @@ def run_ours(args):
         model.pipeline.timer = None
         # ---- timed region: end to end from host buffers ------------------------------------------------------
         h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        _g, _s, _ev = upload()                          # first use of the copy stream allocates: not representative
+        upload(0)                                       # first use of the copy stream: not representative
         torch.cuda.synchronize()
         h0.record()
-        _g, _s, _ev = upload()
+        _ev = upload(0)
         torch.cuda.current_stream().wait_event(_ev)
         h1.record()
         torch.cuda.synchronize()
         h2d_ms = h0.elapsed_time(h1)                    # diagnostic: one un-overlapped H2D copy of a step's inputs
-        del _g, _s
         run_e2e(2)
         barrier()
         w0 = time.time()

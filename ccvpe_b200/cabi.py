@@ -25,6 +25,11 @@ EXPORTED_SYMBOLS = (
     "ccvpe_pose_scratch_bytes", "ccvpe_pose_decode", "ccvpe_bias_silu_nhwc", "ccvpe_dwconv_bias_silu_nhwc",
     "ccvpe_pointwise_silu_nhwc", "ccvpe_stem_conv_silu_nhwc", "ccvpe_se_gate_scale",
     "ccvpe_wrap_columns_nhwc",
+    # training step (config 5)
+    "ccvpe_wgrad_workspace_elems", "ccvpe_wgrad", "ccvpe_wgrad_plan", "ccvpe_colsum_workspace_elems", "ccvpe_colsum",
+    "ccvpe_relu_bwd", "ccvpe_planar_to_cl", "ccvpe_cl_to_planar", "ccvpe_ori_normalize_bwd",
+    "ccvpe_match_bwd_scratch_elems", "ccvpe_match_level_bwd", "ccvpe_loss_workspace_elems", "ccvpe_infonce_loss",
+    "ccvpe_cross_entropy_loss", "ccvpe_orientation_loss", "ccvpe_grd_descriptors_bwd",
 )
 
 
@@ -44,6 +49,22 @@ class IgemmDesc(C.Structure):
         ("bias", C.c_void_p), ("row_scale", C.c_void_p), ("row_r1", C.c_void_p), ("r1_w", C.c_void_p),
         ("relu", C.c_int32), ("out_mode", C.c_int32), ("out_dtype", C.c_int32), ("ldo", C.c_int32),
         ("out", C.c_void_p),
+        ("backend", C.c_int32),
+    ]
+
+
+class WgradDesc(C.Structure):
+    """Mirror of `ccvpe_wgrad_desc` (include/ccvpe_b200.h)."""
+    _fields_ = [
+        ("a0", C.c_void_p), ("a1", C.c_void_p),
+        ("c0", C.c_int32), ("c1", C.c_int32), ("ld0", C.c_int32), ("ld1", C.c_int32),
+        ("B", C.c_int32), ("Hin", C.c_int32), ("Win", C.c_int32), ("Hout", C.c_int32), ("Wout", C.c_int32),
+        ("stride", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32), ("pad", C.c_int32),
+        ("g", C.c_void_p), ("N", C.c_int32), ("ldg", C.c_int32),
+        ("g_row_scale", C.c_void_p),
+        ("dtype", C.c_int32),
+        ("out", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_elems", C.c_int64),
         ("backend", C.c_int32),
     ]
 
@@ -122,6 +143,51 @@ def load() -> C.CDLL:
     lib.ccvpe_se_gate_scale.argtypes = [C.c_void_p, C.c_float] + [C.c_void_p] * 6 + [C.c_int] * 4 + [C.c_void_p]
     lib.ccvpe_wrap_columns_nhwc.restype = C.c_int
     lib.ccvpe_wrap_columns_nhwc.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.ccvpe_wgrad_workspace_elems.restype = C.c_int64
+    lib.ccvpe_wgrad_workspace_elems.argtypes = [C.POINTER(WgradDesc)]
+    lib.ccvpe_wgrad.restype = C.c_int
+    lib.ccvpe_wgrad.argtypes = [C.POINTER(WgradDesc), C.c_void_p]
+    lib.ccvpe_wgrad_plan.restype = C.c_int
+    lib.ccvpe_wgrad_plan.argtypes = [C.POINTER(WgradDesc)]
+    lib.ccvpe_colsum_workspace_elems.restype = C.c_int64
+    lib.ccvpe_colsum_workspace_elems.argtypes = [C.c_int64, C.c_int, C.c_int]
+    lib.ccvpe_colsum.restype = C.c_int
+    lib.ccvpe_colsum.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                 C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ccvpe_relu_bwd.restype = C.c_int
+    lib.ccvpe_relu_bwd.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p]
+    lib.ccvpe_planar_to_cl.restype = C.c_int
+    lib.ccvpe_planar_to_cl.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_void_p]
+    lib.ccvpe_cl_to_planar.restype = C.c_int
+    lib.ccvpe_cl_to_planar.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_void_p]
+    lib.ccvpe_ori_normalize_bwd.restype = C.c_int
+    lib.ccvpe_ori_normalize_bwd.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                            C.c_int64, C.c_void_p]
+    lib.ccvpe_match_bwd_scratch_elems.restype = C.c_int64
+    lib.ccvpe_match_bwd_scratch_elems.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.ccvpe_match_level_bwd.restype = C.c_int
+    lib.ccvpe_match_level_bwd.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                          C.POINTER(C.c_int32), C.c_int, C.c_uint32, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                          C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ccvpe_loss_workspace_elems.restype = C.c_int64
+    lib.ccvpe_loss_workspace_elems.argtypes = [C.c_int]
+    lib.ccvpe_infonce_loss.restype = C.c_int
+    lib.ccvpe_infonce_loss.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p]
+    lib.ccvpe_cross_entropy_loss.restype = C.c_int
+    lib.ccvpe_cross_entropy_loss.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_void_p]
+    lib.ccvpe_orientation_loss.restype = C.c_int
+    lib.ccvpe_orientation_loss.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_void_p]
+    lib.ccvpe_grd_descriptors_bwd.restype = C.c_int
+    lib.ccvpe_grd_descriptors_bwd.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                              C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int,
+                                              C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                              C.POINTER(C.c_int32), C.POINTER(C.c_void_p), C.c_void_p,
+                                              C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                              C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]
     if lib.ccvpe_abi_version() != ABI_VERSION:
         raise CcvpeError("libccvpe_b200.so ABI version mismatch")
     _lib = lib
@@ -398,3 +464,144 @@ def wrap_columns_nhwc(buf: torch.Tensor, H: int, W: int, pad_lo: int, pad_hi: in
     if buf.dtype != torch.bfloat16 or not buf.is_contiguous() or Hp != H + pad_lo + pad_hi or Wp != W + pad_lo + pad_hi:
         raise CcvpeError("wrap_columns_nhwc: buf must be contiguous bf16 [B, H+lo+hi, W+lo+hi, C]")
     _check(load().ccvpe_wrap_columns_nhwc(_ptr(buf), B, H, W, Cc, pad_lo, pad_hi, _stream()), "ccvpe_wrap_columns_nhwc")
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# training step (config 5): backward operators
+# ------------------------------------------------------------------------------------------------------------------
+WGRAD_KERNELS = ("wgrad_simt_kernel", "wgrad_tcgen05_kernel")
+
+
+def wgrad(desc: WgradDesc):
+    _check(load().ccvpe_wgrad(C.byref(desc), _stream()), "ccvpe_wgrad")
+
+
+def wgrad_workspace_elems(desc: WgradDesc) -> int:
+    n = int(load().ccvpe_wgrad_workspace_elems(C.byref(desc)))
+    if n < 0:
+        raise CcvpeError("ccvpe_wgrad_workspace_elems: %s" % load().ccvpe_last_error().decode())
+    return n
+
+
+def wgrad_kernel_name(desc: WgradDesc) -> str:
+    rc = load().ccvpe_wgrad_plan(C.byref(desc))
+    if rc < 0:
+        _check(rc, "ccvpe_wgrad_plan")
+    return WGRAD_KERNELS[rc]
+
+
+def colsum(x: torch.Tensor, C_: int, out: torch.Tensor, w: Optional[torch.Tensor] = None, s: int = 1):
+    """x channels-last [B, H, W, ld] (first C_ channels); out fp32 [s*s, C_];  out[(y%s)*s + x%s][c] = sum w[b,y/s,x/s] * x."""
+    _require_cuda(x, out, w)
+    B, H, W, ld = x.shape
+    ws = torch.empty(int(load().ccvpe_colsum_workspace_elems(B * H * W, C_, s)), dtype=torch.float32, device=x.device)
+    _check(load().ccvpe_colsum(_ptr(x), dtype_code(x.dtype), B, H, W, C_, ld, _ptr(w), s, _ptr(out), _ptr(ws), _stream()),
+           "ccvpe_colsum")
+
+
+def relu_bwd(dh: torch.Tensor, h: torch.Tensor):
+    """In place: dh = (h > 0) * dh; both contiguous, same dtype and shape."""
+    _require_cuda(dh, h)
+    if dh.dtype != h.dtype or dh.shape != h.shape or not dh.is_contiguous() or not h.is_contiguous():
+        raise CcvpeError("relu_bwd: dh and h must be contiguous tensors of the same shape and dtype")
+    _check(load().ccvpe_relu_bwd(_ptr(dh), _ptr(h), dtype_code(dh.dtype), dh.numel(), _stream()), "ccvpe_relu_bwd")
+
+
+def planar_to_cl(src: torch.Tensor, dst: torch.Tensor):
+    """src fp32 planar [B, N, H, W] (or [B, N, HW]) -> dst channels-last [B, H, W, ld] (channels >= N zero filled)."""
+    _require_cuda(src, dst)
+    B, N = src.shape[0], src.shape[1]
+    HW = src.numel() // (B * N)
+    if src.dtype != torch.float32 or not src.is_contiguous() or not dst.is_contiguous():
+        raise CcvpeError("planar_to_cl: src must be contiguous fp32, dst contiguous")
+    _check(load().ccvpe_planar_to_cl(_ptr(src), _ptr(dst), dtype_code(dst.dtype), B, N, HW, dst.shape[-1], _stream()),
+           "ccvpe_planar_to_cl")
+
+
+def cl_to_planar(src: torch.Tensor, n: int, dst: torch.Tensor):
+    """src channels-last [B, H, W, ld] (first n channels) -> dst fp32 planar [B, n, H, W]."""
+    _require_cuda(src, dst)
+    B = src.shape[0]
+    HW = src.numel() // (B * src.shape[-1])
+    if dst.dtype != torch.float32 or not src.is_contiguous() or not dst.is_contiguous():
+        raise CcvpeError("cl_to_planar: dst must be contiguous fp32, src contiguous")
+    _check(load().ccvpe_cl_to_planar(_ptr(src), dtype_code(src.dtype), _ptr(dst), B, n, HW, src.shape[-1], _stream()),
+           "ccvpe_cl_to_planar")
+
+
+def ori_normalize_bwd(v_cl: torch.Tensor, d_ori: torch.Tensor, dv: torch.Tensor):
+    """v_cl channels-last [B, H, W, ldv]; d_ori fp32 planar [B, 2, H, W]; dv channels-last [B, H, W, ldo]."""
+    _require_cuda(v_cl, d_ori, dv)
+    B, H, W, ldv = v_cl.shape
+    if d_ori.dtype != torch.float32 or not d_ori.is_contiguous() or not dv.is_contiguous() or not v_cl.is_contiguous():
+        raise CcvpeError("ori_normalize_bwd: contiguous tensors, d_ori fp32")
+    _check(load().ccvpe_ori_normalize_bwd(_ptr(v_cl), dtype_code(v_cl.dtype), ldv, _ptr(d_ori), _ptr(dv),
+                                          dtype_code(dv.dtype), dv.shape[-1], B, H * W, _stream()),
+           "ccvpe_ori_normalize_bwd")
+
+
+def match_level_bwd(x: torch.Tensor, g: torch.Tensor, offset: int, shifts: Sequence[int], max_mask: int,
+                    scores: torch.Tensor, d_scores, d_scores_cl, d_max, d_xhat, d_xhat2, dx: torch.Tensor, dg: torch.Tensor):
+    """x channels-last [B, H, W, C]; g fp32 [B, L]; scores / d_scores fp32 [B, R, H, W]; d_scores_cl, d_max, d_xhat, d_xhat2:
+    2-D strided views [B*H*W, >=cols] in x's dtype (last dim contiguous; only the row stride is used) or None."""
+    _require_cuda(x, g, scores, d_scores, d_scores_cl, d_max, d_xhat, d_xhat2, dx, dg)
+    B, H, W, Cch = x.shape
+    n = len(shifts)
+    arr = (C.c_int32 * n)(*[int(s) for s in shifts])
+
+    def ld(t):
+        if t is None:
+            return 0
+        if t.dtype != x.dtype or t.stride(-1) != 1:
+            raise CcvpeError("match_level_bwd: gradient views must have x's dtype and a contiguous last dim")
+        return t.stride(-2)
+
+    scratch = torch.empty(int(load().ccvpe_match_bwd_scratch_elems(B, H * W, Cch, n)), dtype=torch.float32, device=x.device)
+    _check(load().ccvpe_match_level_bwd(_ptr(x), dtype_code(x.dtype), B, H * W, Cch, _ptr(g), g.shape[1], int(offset), arr, n,
+                                        C.c_uint32(max_mask & 0xFFFFFFFF), _ptr(scores), _ptr(d_scores),
+                                        _ptr(d_scores_cl), ld(d_scores_cl), _ptr(d_max), ld(d_max), _ptr(d_xhat), ld(d_xhat),
+                                        _ptr(d_xhat2), ld(d_xhat2), _ptr(dx), _ptr(dg), _ptr(scratch), _stream()),
+           "ccvpe_match_level_bwd")
+
+
+def _loss_ws(B: int, device) -> torch.Tensor:
+    return torch.empty(int(load().ccvpe_loss_workspace_elems(B)), dtype=torch.float32, device=device)
+
+
+def infonce_loss(scores: torch.Tensor, labels: torch.Tensor, temperature: float, loss: torch.Tensor, d_scores: torch.Tensor):
+    _require_cuda(scores, labels, loss, d_scores)
+    B, n = scores.shape
+    _check(load().ccvpe_infonce_loss(_ptr(scores), _ptr(labels), B, n, C.c_float(temperature), _ptr(loss), _ptr(d_scores),
+                                     _ptr(_loss_ws(B, scores.device)), _stream()), "ccvpe_infonce_loss")
+
+
+def cross_entropy_loss(logits: torch.Tensor, labels: torch.Tensor, loss: torch.Tensor, d_logits: torch.Tensor):
+    _require_cuda(logits, labels, loss, d_logits)
+    B, n = logits.shape
+    _check(load().ccvpe_cross_entropy_loss(_ptr(logits), _ptr(labels), B, n, _ptr(loss), _ptr(d_logits),
+                                           _ptr(_loss_ws(B, logits.device)), _stream()), "ccvpe_cross_entropy_loss")
+
+
+def orientation_loss(ori: torch.Tensor, gt_ori: torch.Tensor, gt: torch.Tensor, loss: torch.Tensor, d_ori: torch.Tensor):
+    _require_cuda(ori, gt_ori, gt, loss, d_ori)
+    B = ori.shape[0]
+    HW = ori.numel() // (2 * B)
+    ws = torch.empty(2048, dtype=torch.float32, device=ori.device)
+    _check(load().ccvpe_orientation_loss(_ptr(ori), _ptr(gt_ori), _ptr(gt), B, HW, _ptr(loss), _ptr(d_ori), _ptr(ws),
+                                         _stream()), "ccvpe_orientation_loss")
+
+
+def grd_descriptors_bwd(feat: torch.Tensor, heads, dgs, dfeat: torch.Tensor, dw1, db1, dw2, db2):
+    """Backward of `grd_descriptors`: heads as there; dgs: list of fp32 [B, W*c]; dfeat fp32 [B, K, H, W] contiguous;
+    dw1 / db1 / dw2 / db2: lists of fp32 output tensors shaped like the head parameters."""
+    B, K, H, W = feat.shape
+    sb, sk, sh, sw = feat.stride()
+    n = len(heads)
+    _require_cuda(feat, dfeat, *[t for h in heads for t in h], *dgs, *dw1, *db1, *dw2, *db2)
+    arr = lambda ts: (C.c_void_p * n)(*[t.data_ptr() for t in ts])
+    cs = (C.c_int32 * n)(*[h[0].shape[0] for h in heads])
+    scratch = torch.empty(n * B * K * W, dtype=torch.float32, device=feat.device)
+    _check(load().ccvpe_grd_descriptors_bwd(_ptr(feat), dtype_code(feat.dtype), B, K, H, W, sb, sk, sh, sw, n,
+                                            arr([h[0] for h in heads]), arr([h[1] for h in heads]),
+                                            arr([h[2] for h in heads]), cs, arr(dgs), _ptr(dfeat), arr(dw1), arr(db1),
+                                            arr(dw2), arr(db2), _ptr(scratch), _stream()), "ccvpe_grd_descriptors_bwd")

@@ -189,6 +189,15 @@ int launch_match_simt(const T* x, int B, int HW, int C, const float* G, const fl
   return check_launch("match_level_simt_kernel");
 }
 
+// shared with the backward kernel (train_ops.cu): G [B, R, C], M [R, C] (NULL when the windows cover all channels), gnorm [B]
+int build_rolled_descriptor_f32(const float* g, int B, int L, int C, int offset, const int32_t* shifts_host, int n_rolls,
+                                float* G, float* M, float* gnorm, cudaStream_t st) {
+  RollTable rt;
+  for (int i = 0; i < kMaxRolls; ++i) rt.shift[i] = i < n_rolls ? shifts_host[i] : 0;
+  build_rolled_descriptor_kernel<<<dim3(n_rolls + 1, B), 256, 0, st>>>(g, B, L, C, offset, rt, n_rolls, G, M, gnorm);
+  return check_launch("build_rolled_descriptor_kernel");
+}
+
 bool match_tcgen05_supported(int dtype, int C, int L, int offset, const int32_t* shifts_host, int n_rolls,
                              int ld_scores_cl);   // match_tcgen05.cu
 int match_tcgen05(const void* x, int B, int HW, int C, const float* g, int L, int offset, const int32_t* shifts_host,
@@ -239,11 +248,10 @@ extern "C" int ccvpe_match_level(const void* x, int dtype, int B, int HW, int C,
   float* M = G + up((int64_t)B * n_rolls * C);
   float* gnorm = M + up((int64_t)n_rolls * C);
   const bool windowed = L < C;
-  RollTable rt;
-  for (int i = 0; i < kMaxRolls; ++i) rt.shift[i] = i < n_rolls ? shifts_host[i] : 0;
-  build_rolled_descriptor_kernel<<<dim3(n_rolls + 1, B), 256, 0, st>>>(g, B, L, C, offset, rt, n_rolls, G,
-                                                                      windowed ? M : nullptr, gnorm);
-  CCVPE_LAUNCH_CHECK("build_rolled_descriptor_kernel");
+  {
+    const int rc = build_rolled_descriptor_f32(g, B, L, C, offset, shifts_host, n_rolls, G, windowed ? M : nullptr, gnorm, st);
+    if (rc != CCVPE_OK) return rc;
+  }
   if (dtype == CCVPE_F32)
     return launch_match_simt<float>((const float*)x, B, HW, C, G, M, gnorm, n_rolls, max_mask, windowed, scores,
                                     (float*)scores_cl, ld_scores_cl, max_out, inv_norm, (float*)xhat, st);

@@ -30,6 +30,20 @@ def _cl(t: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     return v.contiguous()
 
 
+def _nk(per_tap_rows: torch.Tensor, splits: Sequence[int]) -> torch.Tensor:
+    """[N, taps, K] -> [N, taps, sum(pad(split))] bf16: every source's K range zero padded to its K-block width (16 if
+    c <= 16, 32 if c < 64, else 64 -- the tcgen05 backend's w_nk layout, see include/ccvpe_b200.h)."""
+    N_, taps, _ = per_tap_rows.shape
+    pads = [-(-c // kw) * kw for c, kw in ((c, 16 if c <= 16 else (32 if c < 64 else 64)) for c in splits)]
+    out = torch.zeros((N_, taps, sum(pads)), dtype=torch.bfloat16, device=per_tap_rows.device)
+    src = dst = 0
+    for c, cp in zip(splits, pads):
+        out[:, :, dst:dst + c] = per_tap_rows[:, :, src:src + c]
+        src += c
+        dst += cp
+    return out.contiguous()
+
+
 class OpTimer:
     """Optional per-operator CUDA-event timer (bench.py): events are recorded on torch's current stream, which is the
     stream every kernel of the pipeline is launched on.  `flops` / `nbytes` are the ALGORITHMIC work of the call."""
@@ -106,17 +120,7 @@ class PostEncoderPipeline:
         D = lw.shape[0]
         tc = dtype == torch.bfloat16     # also build the K-major layout of the tcgen05 backend
 
-        def nk(per_tap_rows: torch.Tensor, splits: Sequence[int]) -> torch.Tensor:
-            """[N, taps, K] -> [N, taps, sum(pad64(split))] bf16 with every source K range zero padded to its K-block width (see ccvpe_b200.h)."""
-            N_, taps, _ = per_tap_rows.shape
-            pads = [-(-c // kw) * kw for c, kw in ((c, 16 if c <= 16 else (32 if c < 64 else 64)) for c in splits)]
-            out = torch.zeros((N_, taps, sum(pads)), dtype=torch.bfloat16, device=per_tap_rows.device)
-            src = dst = 0
-            for c, cp in zip(splits, pads):
-                out[:, :, dst:dst + c] = per_tap_rows[:, :, src:src + c]
-                src += c
-                dst += cp
-            return out.contiguous()
+        nk = _nk
 
         w["cell"] = dict(w_kn=lw.view(D, ENCODER_CHANNELS, 2, 2).permute(2, 3, 1, 0).reshape(4, ENCODER_CHANNELS, D)
                          .to(dtype).contiguous(), bias=f32(params["sat_feature_to_descriptors.1.bias"]))
@@ -178,7 +182,7 @@ class PostEncoderPipeline:
         d.N, d.dtype = N, cabi.dtype_code(dtype)
         d.w_kn = wt["w_kn"].data_ptr()
         d.w_nk = wt["w_nk"].data_ptr() if "w_nk" in wt else None
-        d.bias = wt["bias"].data_ptr()
+        d.bias = wt["bias"].data_ptr() if wt.get("bias") is not None else None
         d.row_scale = row_scale.data_ptr() if row_scale is not None else None
         d.row_r1 = row_r1.data_ptr() if row_r1 is not None else None
         d.r1_w = r1_w.data_ptr() if r1_w is not None else None
@@ -218,7 +222,8 @@ class PostEncoderPipeline:
     # -- the path ---------------------------------------------------------------------------------------------
     @torch.no_grad()
     def run(self, grd_feat: torch.Tensor, sat_feat: torch.Tensor, multiscale: Sequence[torch.Tensor],
-            dtype: torch.dtype) -> Tuple[torch.Tensor, ...]:
+            dtype: torch.dtype, save: Optional[dict] = None) -> Tuple[torch.Tensor, ...]:
+        """`save`: a dict that receives every intermediate the backward pass needs (training.py)."""
         if not (grd_feat.is_cuda and sat_feat.is_cuda):
             raise cabi.CcvpeError("the post-encoder path runs on CUDA only (sm_100a); there is no CPU fallback")
         spec = self.spec
@@ -250,6 +255,8 @@ class PostEncoderPipeline:
         self._igemm("igemm:cell|", fs, ENCODER_CHANNELS, None, 0, B, Hs, Ws, Hs // 2, Ws // 2, 2, 2, 0, D, dtype,
                     w["cell"], x, 0, D)
         skips = [_cl(multiscale[i], dtype) for i in SKIP_BLOCKS]
+        if save is not None:
+            save.update(dtype=dtype, B=B, grd_feat=grd_feat, fs=fs, skips=skips, g=g, loc=[], ori=[])
 
         loc_rolls = loc_roll_indices(spec, self.ori_noise)
         scores_out: List[torch.Tensor] = []
@@ -295,6 +302,7 @@ class PostEncoderPipeline:
             scores_out.append(scores)
             lw = w["loc"][l]
             nm = "loc%d" % (6 - l)
+            x_level = x
             up = self._deconv(lw["deconv"], x, C, None, 0, dtype, row_scale=inv, row_r1=mx, name=nm)
             if l < 5:
                 h = self._conv3(lw["conv_a"], up, skips[l], dtype, relu=True, name=nm + "a")
@@ -303,6 +311,9 @@ class PostEncoderPipeline:
                 h = self._conv3(lw["conv_a"], up, None, dtype, relu=True, name=nm + "a")
                 logits = self._conv3(lw["conv_b"], h, None, dtype, relu=False, planar_f32=True,
                                      name=nm + "b")                                              # [B,1,512,512]
+            if save is not None:
+                save["loc"].append(dict(x=x_level, scores=scores, mx=mx, inv=inv, up=up, h=h, mask=mask,
+                                        shifts=[i * stride for i in rolls], offset=spec.window_offset(C, L)))
 
         # a10 -- heatmap
         Hh, Wh = logits.shape[-2:]
@@ -317,17 +328,25 @@ class PostEncoderPipeline:
         for l in range(6):
             ow = w["ori"][l]
             nm = "ori%d" % (6 - l)
+            o_in = o
             if l == 0:
                 o = self._deconv(ow["deconv"], scores_cl, SCORES_CL_PAD, xhat, D, dtype, name=nm)
             else:
                 o = self._deconv(ow["deconv"], o, o.shape[-1], None, 0, dtype, name=nm)
+            o_up = o
             if l < 5:
                 o = self._conv3(ow["conv_a"], o, skips[l], dtype, relu=True, name=nm + "a")
+                o_h = o
                 o = self._conv3(ow["conv_b"], o, None, dtype, relu=False, name=nm + "b")
             else:
                 o = self._conv3(ow["conv_a"], o, None, dtype, relu=True, name=nm + "a")
+                o_h = o
                 o = self._conv3(ow["conv_b"], o, None, dtype, relu=False, out_f32=True, name=nm + "b")  # fp32 [B,512,512,2]
+            if save is not None:
+                save["ori"].append(dict(inp=o_in, up=o_up, h=o_h))
         ori = torch.empty((B, 2, Hh, Wh), dtype=f32, device=dev)
+        if save is not None:
+            save.update(o_raw=o, scores_cl=scores_cl, xhat=xhat)
         o_in = o
         self._op("ori_normalize_kernel:ori_normalize|", 6.0 * B * Hh * Wh, 2.0 * B * Hh * Wh * (o.element_size() + 4),
                  lambda: cabi.ori_normalize(o_in, ori))                                   # a12

@@ -85,6 +85,7 @@ class _CVMBase(nn.Module):
         self._precision = "fp32"
         self._fast_encoders = [None]                                    # (signature, grd_enc_bf16, sat_enc_bf16)
         self._graphs = [None]                                           # None = eager; dict = CUDA-graph cache
+        self._trainer = [None]                                          # training.PostEncoderTrainer, built on first use
 
     # -- configuration ----------------------------------------------------------------------------------------
     @property
@@ -141,13 +142,14 @@ class _CVMBase(nn.Module):
         new = cls.__new__(cls)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            if k in ("_pipeline", "_fast_encoders", "_graphs"):
+            if k in ("_pipeline", "_fast_encoders", "_graphs", "_trainer"):
                 continue
             setattr(new, k, copy.deepcopy(v, memo))
         new._pipeline = [PostEncoderPipeline(new, self.spec, self.pipeline.ori_noise)]
         new._pipeline[0].backend = self.pipeline.backend
         new._fast_encoders = [None]
         new._graphs = [None if self._graphs[0] is None else {}]
+        new._trainer = [None]
         return new
 
     # -- encoders (PyTorch) -----------------------------------------------------------------------------------
@@ -180,19 +182,35 @@ class _CVMBase(nn.Module):
     def forward(self, grd, sat):
         """Returns (logits_flattened, heatmap, x_ori, matching_score_stacked, ..._stacked2, ..., ..._stacked6)
         with the reference's shapes (models.py:343)."""
-        if torch.is_grad_enabled() and self.training:
-            raise NotImplementedError(
-                "ccvpe_b200: the CUDA decoder path is inference-only in this version (backward kernels for the "
-                "training config are the next scope row); call under torch.no_grad() / model.eval()")
         if not (grd.is_cuda and sat.is_cuda):
             raise cabi.CcvpeError("ccvpe_b200 models run on CUDA (sm_100a) only; there is no CPU fallback -- "
                                   "move the model and inputs to a B200")
         if sat.device != grd.device:
             raise cabi.CcvpeError("grd (%s) and sat (%s) must be on the same device" % (grd.device, sat.device))
+        if torch.is_grad_enabled() and (self.training or grd.requires_grad or sat.requires_grad):
+            return self._forward_train(grd, sat)           # autograd through the CUDA path (training.py)
         with torch.no_grad(), cabi.device_of(grd):     # kernels / stream / func attributes follow the tensors' device
             if self._graphs[0] is not None and not self.training and self.pipeline.timer is None:
                 return self._forward_graphed(grd, sat)
             return self._forward_eager(grd, sat)
+
+    def _forward_train(self, grd, sat):
+        """The reference's training forward (train_VIGOR.py:134-135): PyTorch-autograd encoders (train-mode BatchNorm and
+        stochastic depth exactly as the reference's), then ONE autograd Function for the whole CUDA post-encoder path whose
+        backward runs this library's backward kernels (training.PostEncoderFunction).  Gradients flow to all 98 head /
+        decoder parameters, into both encoders, and to `grd` / `sat` if they require grad."""
+        from .training import PostEncoderFunction, PostEncoderTrainer
+        if self._trainer[0] is None:
+            self._trainer[0] = PostEncoderTrainer(self.pipeline)
+        with cabi.device_of(grd):
+            cudnn = torch.backends.cudnn
+            with cudnn.flags(enabled=True, benchmark=cudnn.benchmark, deterministic=cudnn.deterministic, allow_tf32=False):
+                fg = self.grd_efficientnet.extract_features(grd)                      # reference models.py:151
+                fs, multi = self.sat_efficientnet.extract_features_multiscale(sat)    # reference models.py:166
+            dtype = torch.bfloat16 if self._precision == "bf16" else torch.float32
+            skips = [multi[i] for i in SKIP_BLOCKS]
+            params = list(self.pipeline._params().values())
+            return PostEncoderFunction.apply(self._trainer[0], dtype, fg, fs, *skips, *skips, *params)
 
     def _forward_eager(self, grd, sat):
         fg, fs, multi, dtype = self._encode(grd, sat)

@@ -9,6 +9,7 @@ which makes end-to-end argmax comparisons meaningless -- SURVEY.md section 7.3-4
 """
 from __future__ import annotations
 
+import math
 import zlib
 from typing import Dict
 
@@ -64,3 +65,29 @@ def synthetic_pair(batch: int, ground_hw, seed: int = 0, dtype=torch.float32):
     grd = torch.randn((batch, 3) + tuple(ground_hw), generator=g).to(dtype)
     sat = torch.randn((batch, 3) + AERIAL_SHAPE, generator=g).to(dtype)
     return grd, sat
+
+
+def synthetic_ground_truth(batch: int, seed: int = 0, size: int = 512, n_bins: int = 20):
+    """Synthetic training ground truth with the statistics of the reference dataset (reference datasets.py:142-166): a sigma-4 Gaussian at a random
+    pixel, the same Gaussian split over two adjacent orientation bins, and a constant unit-vector orientation field."""
+    g = torch.Generator().manual_seed(20_000 + seed)
+    ys = torch.arange(size, dtype=torch.float32).view(size, 1)
+    xs = torch.arange(size, dtype=torch.float32).view(1, size)
+    gt = torch.zeros(batch, 1, size, size)
+    gt_with_ori = torch.zeros(batch, n_bins, size, size)
+    gt_orientation = torch.zeros(batch, 2, size, size)
+    for b in range(batch):
+        cy, cx = (torch.rand(2, generator=g) * (size - 64) + 32).tolist()
+        blob = torch.exp(-((ys - cy) ** 2 + (xs - cx) ** 2) / (2.0 * 4.0 ** 2))
+        gt[b, 0] = blob
+        angle = float(torch.rand(1, generator=g)) * 360.0
+        index, ratio = int(angle // 18), (angle % 18) / 18
+        if index == 0:
+            gt_with_ori[b, 0] = blob * (1 - ratio)
+            gt_with_ori[b, n_bins - 1] = blob * ratio
+        else:
+            gt_with_ori[b, n_bins - index] = blob * (1 - ratio)
+            gt_with_ori[b, n_bins - index - 1] = blob * ratio
+        gt_orientation[b, 0] = math.cos(math.radians(angle))
+        gt_orientation[b, 1] = math.sin(math.radians(angle))
+    return gt, gt_with_ori, gt_orientation

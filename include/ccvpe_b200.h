@@ -217,6 +217,92 @@ int ccvpe_se_gate_scale(const int64_t* chan_sum, float inv_hw, const void* w_red
 int ccvpe_pointwise_silu_nhwc(const void* x, int B, int H, int W, int K, int ldx, const void* w_nk, const float* bias,
                               int N, void* out, int pad_lo, int pad_hi, void* stream);
 
+/* =================================================================================================================
+ * Training step (BASELINE.json configs[4]; reference train_VIGOR.py:120-150, losses.py:4-29): backward kernels.
+ * The data gradient of every convolution is a `ccvpe_igemm` call on re-laid-out weights (a 3x3 pad-1 conv's is a 3x3 pad-1
+ * conv with flipped, transposed weights; a k2 s2 transposed conv's is a k2 s2 conv and vice versa); what follows are the
+ * operators that have no forward counterpart.  All reductions are deterministic (workspace partials, fixed order).
+ * ================================================================================================================= */
+
+/* Weight gradient of the implicit GEMM of ccvpe_igemm:
+ *   out[tap][c][n] = sum_m A_src[b, ho*stride + ty - pad, wo*stride + tx - pad, c] * G[m, n] * (g_row_scale ? g_row_scale[m] : 1)
+ * A sources as in ccvpe_igemm_desc (channels-last, two K-concatenated sources); G: channels-last [B*Hout*Wout, N] with row
+ * stride ldg.  3x3 conv: A = layer input, G = dY.  k2 s2 transposed conv: A = dY (the pixel-shuffled output gradient,
+ * kh = kw = 2, stride 2), G = the layer input with g_row_scale = 1/||x|| (F.normalize).  k2 s2 cell conv: A = aerial
+ * features, G = d(cell descriptors).  out is fp32 in the w_kn layout of the forward weights [taps][c0 + c1][N].
+ * Channel counts and strides: multiples of 4.  workspace: >= ccvpe_wgrad_workspace_elems(desc) floats. */
+typedef struct ccvpe_wgrad_desc {
+  const void* a0; const void* a1;
+  int32_t c0, c1, ld0, ld1;
+  int32_t B, Hin, Win, Hout, Wout;
+  int32_t stride, kh, kw, pad;
+  const void* g; int32_t N, ldg;
+  const float* g_row_scale;
+  int32_t dtype;                 /* CCVPE_F32 / CCVPE_BF16: element type of a0, a1 and g */
+  float* out;
+  float* workspace; int64_t workspace_elems;
+  int32_t backend;               /* CCVPE_BACKEND_* */
+} ccvpe_wgrad_desc;
+int64_t ccvpe_wgrad_workspace_elems(const ccvpe_wgrad_desc* desc);
+int ccvpe_wgrad(const ccvpe_wgrad_desc* desc, void* stream);
+/* 0 = wgrad_simt_kernel, 1 = wgrad_tcgen05_kernel; < 0 = error */
+int ccvpe_wgrad_plan(const ccvpe_wgrad_desc* desc);
+
+/* Bucketed, weighted column sums over a channels-last image x [B, H, W, ld] (first C channels):
+ *   out[(y % s) * s + (x % s)][c] = sum_{b,y,x} w[b, y/s, x/s] * x[b, y, x, c]        (w NULL: 1;  s = 1 or 2)
+ * s = 1: bias gradient of a conv.  s = 2, w = max-score map: gradient of the rank-1 weight row of a k2 s2 transposed conv
+ * (torch.cat([max, normalize(x)]) channel 0, models.py:205); s = 2, w NULL: the four bucket sums of its bias gradient.
+ * out fp32 [s*s][C]; workspace >= ccvpe_colsum_workspace_elems(B*H*W, C, s) floats. */
+int64_t ccvpe_colsum_workspace_elems(int64_t n_pix, int C, int s);
+int ccvpe_colsum(const void* x, int dtype, int B, int H, int W, int C, int ld, const float* w, int s, float* out,
+                 float* workspace, void* stream);
+
+/* ReLU backward in place: dh[i] = h[i] > 0 ? dh[i] : 0 (models.py:45).  n % 4 == 0. */
+int ccvpe_relu_bwd(void* dh, const void* h, int dtype, int64_t n, void* stream);
+/* planar fp32 [B, N, HW] -> channels-last (dtype) [B, HW, ld], channels >= N zero filled (incoming d logits) */
+int ccvpe_planar_to_cl(const float* src, void* dst, int dtype, int B, int N, int64_t HW, int ld, void* stream);
+/* channels-last (dtype) [B, HW, ld] (first N channels) -> planar fp32 [B, N, HW] (outgoing gradients of NCHW inputs) */
+int ccvpe_cl_to_planar(const void* src, int dtype, float* dst, int B, int N, int64_t HW, int ld, void* stream);
+/* Backward of the orientation-field normalisation (models.py:341): v channels-last [B, HW, ldv] (raw 2-vector field),
+ * d_ori planar fp32 [B, 2, HW] -> dv channels-last (dv_dtype) [B, HW, ldo], channels >= 2 zero filled. */
+int ccvpe_ori_normalize_bwd(const void* v, int v_dtype, int ldv, const float* d_ori, void* dv, int dv_dtype, int ldo,
+                            int B, int64_t HW, void* stream);
+
+/* Backward of one matching level (models.py:186-205): given the saved forward scores, the incoming gradients of the score
+ * volume (d_scores fp32 [B, R, HW] and/or d_scores_cl: columns 0..R-1 of a (dtype) [B*HW, ld_dscl] matrix -- the
+ * orientation decoder's input gradient at the bottleneck level; either may be NULL), of the max-over-orientations channel
+ * (d_max: column 0 of a (dtype) [B*HW, ld_dmax] matrix, may be NULL) and of the normalised map (d_xhat / d_xhat2: first C
+ * columns of (dtype) [B*HW, ld] matrices, summed; may be NULL) -> dx (dtype) [B, HW, C] and dg fp32 [B, L].
+ * scratch: >= ccvpe_match_bwd_scratch_elems floats. */
+int64_t ccvpe_match_bwd_scratch_elems(int B, int HW, int C, int n_rolls);
+int ccvpe_match_level_bwd(const void* x, int dtype, int B, int HW, int C, const float* g, int L, int offset,
+                          const int32_t* shifts_host, int n_rolls, uint32_t max_mask, const float* scores,
+                          const float* d_scores, const void* d_scores_cl, int ld_dscl, const void* d_max, int ld_dmax,
+                          const void* d_xhat, int ld_dxhat, const void* d_xhat2, int ld_dxhat2, void* dx, float* dg,
+                          float* scratch, void* stream);
+
+/* Training losses, value and gradient in one call (reference losses.py).  All tensors fp32; workspace >=
+ * ccvpe_loss_workspace_elems(B) floats; `loss` is a device scalar.
+ *   infoNCE (losses.py:4-20): scores, labels [B, n]; positives = labels > 1e-2; d_scores [B, n]
+ *   cross entropy (losses.py:23-24): logits, labels [B, n]; d_logits [B, n]
+ *   orientation (losses.py:28-29): ori, gt_ori planar [B, 2, HW], gt [B, HW]; d_ori [B, 2, HW] */
+int64_t ccvpe_loss_workspace_elems(int B);
+int ccvpe_infonce_loss(const float* scores, const float* labels, int B, int64_t n, float temperature, float* loss,
+                       float* d_scores, float* workspace, void* stream);
+int ccvpe_cross_entropy_loss(const float* logits, const float* labels, int B, int64_t n, float* loss, float* d_logits,
+                             float* workspace, void* stream);
+int ccvpe_orientation_loss(const float* ori, const float* gt_ori, const float* gt, int B, int64_t HW, float* loss,
+                           float* d_ori, float* workspace, void* stream);
+
+/* Backward of the ground descriptor heads (models.py:57-97, 152-157); arguments as ccvpe_grd_descriptors plus the incoming
+ * dg[l] fp32 [B, W*c[l]].  Outputs: dfeat fp32 [B, K, H, W] contiguous (NCHW), dw1[l] [c, K], db1[l] [c], dw2[l] [H],
+ * db2[l] [1].  scratch: fp32, >= n_heads*B*K*W elements. */
+int ccvpe_grd_descriptors_bwd(const void* feat, int dtype, int B, int K, int H, int W, int64_t sb, int64_t sk, int64_t sh,
+                              int64_t sw, int n_heads, const float* const* w1, const float* const* b1,
+                              const float* const* w2, const int32_t* c, const float* const* dg, float* dfeat,
+                              float* const* dw1, float* const* db1, float* const* dw2, float* const* db2, float* scratch,
+                              void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -221,3 +221,38 @@ def forward_full(variant: str, sd: Dict[str, Tensor], grd_encoder, sat_encoder, 
     fg = grd_encoder.extract_features(grd)                              # models.py:151
     fs, multi = sat_encoder.extract_features_multiscale(sat)            # models.py:166
     return forward_post_encoder(variant, sd, fg, fs, multi, ori_noise, intermediates)
+
+
+# ---------------------------------------------------------------------------------------------
+# training losses   (losses.py:4-29) and their combination (train_VIGOR.py:120-146) -- used with torch autograd as the
+# reference for the loss values and for every gradient of the training step (tests/test_gpu_train.py)
+# ---------------------------------------------------------------------------------------------
+def infonce_loss(scores: Tensor, labels: Tensor, temperature: float = 0.1) -> Tensor:
+    exp_scores = torch.exp(scores / temperature)                         # losses.py:13
+    mask = labels > 1e-2                                                 # losses.py:14
+    denominator = torch.sum(exp_scores, dim=1, keepdim=True)             # losses.py:16
+    inner = torch.log(torch.masked_select(exp_scores / denominator, mask))
+    w = torch.masked_select(labels, mask)
+    return -torch.sum(inner * w) / torch.sum(w)                          # losses.py:18
+
+
+def cross_entropy_loss(logits: Tensor, labels: Tensor) -> Tensor:
+    return -torch.sum(labels * F.log_softmax(logits, dim=1)) / logits.size()[0]      # losses.py:24
+
+
+def orientation_loss(ori: Tensor, gt_orientation: Tensor, gt: Tensor) -> Tensor:
+    return torch.sum(torch.sum(torch.square(gt_orientation - ori), dim=1, keepdim=True) * gt) / ori.size()[0]   # losses.py:29
+
+
+def training_loss(outputs, gt: Tensor, gt_with_ori: Tensor, gt_orientation: Tensor, weight_infonce: float = 1e4,
+                  weight_ori: float = 1e1) -> Tensor:
+    """train_VIGOR.py:120-146."""
+    gt_flattened = torch.flatten(gt, start_dim=1)
+    gt_flattened = gt_flattened / torch.sum(gt_flattened, dim=1, keepdim=True)
+    loss_ori = orientation_loss(outputs[2], gt_orientation, gt)
+    nce = 0
+    for scores, k in zip(outputs[3:9], (64, 32, 16, 8, 4, 2)):
+        gt_b = F.max_pool2d(gt_with_ori, k, stride=k)
+        nce = nce + infonce_loss(torch.flatten(scores, start_dim=1), torch.flatten(gt_b, start_dim=1))
+    loss_ce = cross_entropy_loss(outputs[0], gt_flattened)
+    return loss_ce + weight_infonce * nce / 6 + weight_ori * loss_ori
