@@ -25,6 +25,7 @@ EXPORTED_SYMBOLS = (
     "ccvpe_pose_scratch_bytes", "ccvpe_pose_decode", "ccvpe_bias_silu_nhwc", "ccvpe_dwconv_bias_silu_nhwc",
     "ccvpe_pointwise_silu_nhwc", "ccvpe_stem_conv_silu_nhwc", "ccvpe_se_gate_scale",
     "ccvpe_wrap_columns_nhwc",
+    "ccvpe_ingest_u8",
     # training step (config 5)
     "ccvpe_wgrad_workspace_elems", "ccvpe_wgrad", "ccvpe_wgrad_plan", "ccvpe_colsum_workspace_elems", "ccvpe_colsum",
     "ccvpe_relu_bwd", "ccvpe_planar_to_cl", "ccvpe_cl_to_planar", "ccvpe_ori_normalize_bwd",
@@ -143,6 +144,9 @@ def load() -> C.CDLL:
     lib.ccvpe_se_gate_scale.argtypes = [C.c_void_p, C.c_float] + [C.c_void_p] * 6 + [C.c_int] * 4 + [C.c_void_p]
     lib.ccvpe_wrap_columns_nhwc.restype = C.c_int
     lib.ccvpe_wrap_columns_nhwc.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.ccvpe_ingest_u8.restype = C.c_int
+    lib.ccvpe_ingest_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                    C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p, C.c_void_p]
     lib.ccvpe_wgrad_workspace_elems.restype = C.c_int64
     lib.ccvpe_wgrad_workspace_elems.argtypes = [C.POINTER(WgradDesc)]
     lib.ccvpe_wgrad.restype = C.c_int
@@ -605,3 +609,32 @@ def grd_descriptors_bwd(feat: torch.Tensor, heads, dgs, dfeat: torch.Tensor, dw1
                                             arr([h[0] for h in heads]), arr([h[1] for h in heads]),
                                             arr([h[2] for h in heads]), cs, arr(dgs), _ptr(dfeat), arr(dw1), arr(db1),
                                             arr(dw2), arr(db2), _ptr(scratch), _stream()), "ccvpe_grd_descriptors_bwd")
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# input pipeline (f4)
+# ------------------------------------------------------------------------------------------------------------------
+IMAGENET_MEAN = (0.485, 0.456, 0.406)      # reference train_VIGOR.py:58, 66
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+def ingest_u8(img: torch.Tensor, out: torch.Tensor, shift: Optional[torch.Tensor] = None, mean=IMAGENET_MEAN,
+              std=IMAGENET_STD):
+    """img: uint8 [B,3,H,W] (NCHW) or [B,H,W,3] (NHWC), contiguous; out: fp32 [B,3,H,crop_w] contiguous (crop_w <= W);
+    shift: int32 [B] device tensor of per-image torch.roll shifts along the width, or None."""
+    _require_cuda(img, out, shift)
+    if img.dtype != torch.uint8 or not img.is_contiguous() or img.dim() != 4:
+        raise CcvpeError("ingest_u8: img must be a contiguous uint8 [B,3,H,W] or [B,H,W,3] tensor")
+    nhwc = img.shape[1] != 3
+    if nhwc and img.shape[3] != 3:
+        raise CcvpeError("ingest_u8: neither dim 1 nor dim 3 has 3 channels")
+    B = img.shape[0]
+    H, W = (img.shape[1], img.shape[2]) if nhwc else (img.shape[2], img.shape[3])
+    if out.dtype != torch.float32 or not out.is_contiguous() or tuple(out.shape[:3]) != (B, 3, H) or out.shape[3] > W:
+        raise CcvpeError("ingest_u8: out must be contiguous fp32 [B,3,H,crop_w<=W]")
+    if shift is not None and (shift.dtype != torch.int32 or shift.numel() != B):
+        raise CcvpeError("ingest_u8: shift must be int32 [B]")
+    m = (C.c_float * 3)(*[float(v) for v in mean])
+    s = (C.c_float * 3)(*[float(v) for v in std])
+    _check(load().ccvpe_ingest_u8(_ptr(img), 1 if nhwc else 0, B, H, W, out.shape[3], _ptr(shift), m, s, _ptr(out), _stream()),
+           "ccvpe_ingest_u8")

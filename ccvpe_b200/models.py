@@ -255,6 +255,25 @@ class _CVMBase(nn.Module):
         out = self.forward(grd, sat)
         return decode_pose(out[1], out[2])
 
+    @staticmethod
+    def ingest(img_u8, shift=None, crop_w=None, out=None):
+        """The scripts' input pipeline after image decoding, on the GPU (reference train_VIGOR.py:55-70 ToTensor + ImageNet
+        Normalize; datasets.py:118 panorama roll; train_VIGOR.py:272-273 limited-FoV crop): uint8 [B,3,H,W] / [B,H,W,3] ->
+        fp32 [B,3,H,crop_w], bit-identical to torchvision's transforms on the same pixels.  `shift`: per-image torch.roll
+        shifts along the width (int32 [B] device tensor) or None; `crop_w`: int(W * FoV / 360) or None for the full width."""
+        nhwc = img_u8.shape[1] != 3
+        B = img_u8.shape[0]
+        H, W = (img_u8.shape[1], img_u8.shape[2]) if nhwc else (img_u8.shape[2], img_u8.shape[3])
+        if out is None:
+            out = torch.empty((B, 3, H, crop_w or W), dtype=torch.float32, device=img_u8.device)
+        with cabi.device_of(img_u8):
+            cabi.ingest_u8(img_u8, out, shift)
+        return out
+
+    def localize_u8(self, grd_u8, sat_u8, shift=None, crop_w=None):
+        """uint8 images in, poses out: ingest (normalise / roll / crop) + forward + pose decode, all on the device."""
+        return self.localize(self.ingest(grd_u8, shift, crop_w), self.ingest(sat_u8))
+
 
 class CVM_VIGOR(_CVMBase):
     """reference models.py:49 -- `CVM_VIGOR(device, circular_padding)`."""

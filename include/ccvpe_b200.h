@@ -217,6 +217,14 @@ int ccvpe_se_gate_scale(const int64_t* chan_sum, float inv_hw, const void* w_red
 int ccvpe_pointwise_silu_nhwc(const void* x, int B, int H, int W, int K, int ldx, const void* w_nk, const float* bias,
                               int N, void* out, int pad_lo, int pad_hi, void* stream);
 
+/* f4  Input pipeline after image decoding -- reference train_VIGOR.py:55-70 (ToTensor + Normalize), datasets.py:118
+ * (random panorama roll: torch.roll(grd, shift, dims=2)), train_VIGOR.py:272-273 (limited-FoV crop of the panorama):
+ *   dst[b, c, h, w] = (src[b, c, h, (w - shift[b]) mod W] / 255 - mean[c]) / std[c]        for w < crop_w
+ * src: uint8 image batch, NCHW [B,3,H,W] (nhwc == 0) or NHWC [B,H,W,3] (nhwc != 0); shift: device int32 [B] or NULL;
+ * mean_host / std_host: HOST float[3]; dst: fp32 NCHW [B,3,H,crop_w].  Bit-identical to torchvision's transforms. */
+int ccvpe_ingest_u8(const uint8_t* src, int nhwc, int B, int H, int W, int crop_w, const int32_t* shift,
+                    const float* mean_host, const float* std_host, float* dst, void* stream);
+
 /* =================================================================================================================
  * Training step (BASELINE.json configs[4]; reference train_VIGOR.py:120-150, losses.py:4-29): backward kernels.
  * The data gradient of every convolution is a `ccvpe_igemm` call on re-laid-out weights (a 3x3 pad-1 conv's is a 3x3 pad-1

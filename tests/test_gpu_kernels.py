@@ -641,3 +641,27 @@ def test_wrap_columns_nhwc(cuda_device, B, H, W, C, lo, hi):
     cabi.wrap_columns_nhwc(dbuf, H, W, lo, hi)
     torch.cuda.synchronize()
     assert torch.equal(dbuf.cpu(), ref)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# f4 input pipeline: uint8 -> normalised fp32 with roll and FoV crop
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,H,W,crop,nhwc,rolled", [(3, 32, 64, 64, False, True), (2, 20, 40, 18, True, True),
+                                                     (2, 16, 24, 24, True, False), (1, 7, 13, 9, False, True)])
+def test_ingest_u8_matches_torchvision_arithmetic(cuda_device, B, H, W, crop, nhwc, rolled):
+    """ToTensor + Normalize (train_VIGOR.py:55-70) + torch.roll along the width (datasets.py:118) + FoV crop
+    (train_VIGOR.py:272-273) in one kernel: bit-identical to the same torch ops on the same uint8 pixels."""
+    from ccvpe_b200 import models
+    g = _gen(41)
+    img = torch.randint(0, 256, (B, 3, H, W), generator=g, dtype=torch.uint8)
+    shifts = torch.randint(-2 * W, 2 * W, (B,), generator=g, dtype=torch.int32) if rolled else None
+    mean = torch.tensor(cabi.IMAGENET_MEAN).view(1, 3, 1, 1)
+    std = torch.tensor(cabi.IMAGENET_STD).view(1, 3, 1, 1)
+    ref = (img.float().div(255) - mean) / std                             # ToTensor, Normalize
+    if rolled:
+        ref = torch.stack([torch.roll(ref[b], int(shifts[b]), dims=2) for b in range(B)])
+    ref = ref[:, :, :, :crop]
+    src = img.permute(0, 2, 3, 1).contiguous() if nhwc else img
+    out = models.CVM_VIGOR.ingest(src.to(cuda_device), shifts.to(cuda_device) if rolled else None, crop)
+    torch.cuda.synchronize()
+    assert out.shape == ref.shape and torch.equal(out.cpu(), ref)
