@@ -155,6 +155,14 @@ __global__ void reduce_splits_kernel(const float* __restrict__ ws, float* __rest
   }
 }
 
+// host-side launcher (also used by wgrad_tcgen05.cu: kernels cannot be launched across translation units without -rdc)
+int launch_reduce_splits(const float* ws, float* out, int64_t n, int splits, cudaStream_t st) {
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 8 * sm_count()) blocks = 8 * sm_count();
+  reduce_splits_kernel<<<blocks < 1 ? 1 : blocks, 256, 0, st>>>(ws, out, n, splits);
+  return check_launch("reduce_splits_kernel");
+}
+
 struct WgradPlan {
   int tq, tn, q_tiles, n_tiles, splits, pix_per_split;
 };

@@ -74,6 +74,31 @@ def test_wgrad_conv3x3(cuda_device, B, c0, c1, cout, H, dtype, tol):
     assert rel_err(got, w.grad) < tol
 
 
+@pytest.mark.parametrize("B,c0,c1,cout,H,W", [
+    (2, 64, 0, 128, 16, 16),      # one c tile pair, one n tile, 8 pixel steps
+    (3, 40, 24, 72, 8, 32),       # two sources with channel tails (40 = 32 + 8, 24), N tail (72 of 128), W = 32 boxes
+    (1, 16, 0, 16, 64, 64),       # finest-level shape: 16 -> 16, split-K over pixels
+    (2, 320, 112, 320, 32, 32),   # level-5 conv_a of the decoder: 14 c tiles x 3 n tiles
+    (1, 16, 0, 8, 128, 128),      # padded 1-channel gradient (N = 8), W = 128: two boxes per row
+])
+def test_wgrad_conv3x3_tcgen05(cuda_device, B, c0, c1, cout, H, W):
+    """Tensor-core weight gradient (MN-major UMMA operands, pixels on K) vs autograd on the same bf16-rounded inputs;
+    fp32 accumulation on both sides: 1e-3 of max|ref|."""
+    g = _gen(39)
+    dev = cuda_device
+    dt = torch.bfloat16
+    x0 = torch.randn(B, c0, H, W, generator=g).to(dt).float()
+    x1 = torch.randn(B, c1, H, W, generator=g).to(dt).float() if c1 else None
+    dy = torch.randn(B, cout, H, W, generator=g).to(dt).float()
+    w = torch.zeros(cout, c0 + c1, 3, 3, requires_grad=True)
+    xin = torch.cat([x0, x1], dim=1) if c1 else x0
+    (F.conv2d(xin, w, padding=1) * dy).sum().backward()
+    out = _wgrad_call(_cl(x0, dt, dev), _cl(x1, dt, dev) if c1 else None, (B, H, W, H, W, 1, 3, 1),
+                      _cl(dy, dt, dev).view(B * H * W, cout), cout, None, backend=cabi.BACKEND_TCGEN05)
+    got = out.view(3, 3, c0 + c1, cout).permute(3, 2, 0, 1)
+    assert rel_err(got, w.grad) < 1e-3, rel_err(got, w.grad)
+
+
 @pytest.mark.parametrize("B,cin,cout,H,with_scale", [(2, 40, 16, 12, True), (1, 160, 80, 8, False), (2, 32, 24, 5, True)])
 def test_wgrad_deconv_and_colsum(cuda_device, B, cin, cout, H, with_scale):
     """ConvTranspose2d(k2, s2) over [max | x * inv]: weight rows 1.. from ccvpe_wgrad (A = dY as a k2 s2 image, G = x with
