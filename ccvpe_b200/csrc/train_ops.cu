@@ -339,10 +339,21 @@ extern "C" int ccvpe_colsum(const void* x, int dtype, int B, int H, int W, int C
                             float* out, float* workspace, void* stream) {
   using namespace ccvpe;
   CCVPE_REQUIRE(x && out && workspace, "ccvpe_colsum: null pointer");
-  CCVPE_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0 && C <= 1024 && ld >= C && ld % 4 == 0,
+  CCVPE_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0 && ld >= C && ld % 4 == 0,
                 "ccvpe_colsum: bad shape C=%d ld=%d", C, ld);
   CCVPE_REQUIRE(s == 1 || (s == 2 && H % 2 == 0 && W % 2 == 0), "ccvpe_colsum: s must be 1 or 2 (even H, W)");
   CCVPE_REQUIRE(dtype == CCVPE_F32 || dtype == CCVPE_BF16, "ccvpe_colsum: bad dtype");
+  if (C > 512) {   // wide maps (the 1280- / 2048-channel cell descriptors): 512 columns per pass, same workspace
+    CCVPE_REQUIRE(s == 1, "ccvpe_colsum: C=%d > 512 is only supported for s == 1", C);
+    const int esz = dtype == CCVPE_F32 ? 4 : 2;
+    for (int c0 = 0; c0 < C; c0 += 512) {
+      const int cc = C - c0 < 512 ? C - c0 : 512;
+      const int rc = ccvpe_colsum(static_cast<const uint8_t*>(x) + (int64_t)c0 * esz, dtype, B, H, W, cc, ld, w, 1, out + c0,
+                                  workspace, stream);
+      if (rc != CCVPE_OK) return rc;
+    }
+    return CCVPE_OK;
+  }
   const int64_t n_pix = (int64_t)B * H * W;
   int64_t blocks = (n_pix + 255) / 256;
   if (blocks > 4LL * sm_count()) blocks = 4LL * sm_count();
@@ -701,7 +712,8 @@ struct RollShifts {
   int s[32];
 };
 
-// dg[b, k] = (1 / gn) * sum_i sum_tiles T[b, tile, i, (k + base_i) % C]  -  g[b, k] / gn^2 * sum_tiles c_part[b, tile]
+// dg[b, k] = sum_i sum_tiles T[b, tile, i, (k + base_i) % C]  -  g[b, k] / gn^2 * sum_tiles c_part[b, tile]
+// (T already carries the 1 / (n_i gn) of the per-pixel coefficients)
 __global__ void match_bwd_finalize_kernel(const float* __restrict__ t_part, const float* __restrict__ c_part, int tiles,
                                           int R, int C, int L, int offset, RollShifts sh, const float* __restrict__ g,
                                           const float* __restrict__ gnorm, float* __restrict__ dg) {
@@ -717,7 +729,7 @@ __global__ void match_bwd_finalize_kernel(const float* __restrict__ t_part, cons
       if (c >= C) c -= C;
       for (int tl = 0; tl < tiles; ++tl) s += t_part[(((int64_t)b * tiles + tl) * R + i) * C + c];
     }
-    dg[(int64_t)b * L + k] = s / gn - g[(int64_t)b * L + k] * csum / (gn * gn);
+    dg[(int64_t)b * L + k] = s - g[(int64_t)b * L + k] * csum / (gn * gn);
   }
 }
 

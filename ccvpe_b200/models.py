@@ -187,7 +187,8 @@ class _CVMBase(nn.Module):
                                   "move the model and inputs to a B200")
         if sat.device != grd.device:
             raise cabi.CcvpeError("grd (%s) and sat (%s) must be on the same device" % (grd.device, sat.device))
-        if torch.is_grad_enabled() and (self.training or grd.requires_grad or sat.requires_grad):
+        if torch.is_grad_enabled() and (grd.requires_grad or sat.requires_grad or
+                                        any(p.requires_grad for p in self.parameters())):
             return self._forward_train(grd, sat)           # autograd through the CUDA path (training.py)
         with torch.no_grad(), cabi.device_of(grd):     # kernels / stream / func attributes follow the tensors' device
             if self._graphs[0] is not None and not self.training and self.pipeline.timer is None:
@@ -251,6 +252,7 @@ class _CVMBase(nn.Module):
     def decode_pose(heatmap, ori):
         return decode_pose(heatmap, ori)
 
+    @torch.no_grad()
     def localize(self, grd, sat):
         out = self.forward(grd, sat)
         return decode_pose(out[1], out[2])
