@@ -248,10 +248,12 @@ def _chunked_oracle(model, variant, noise, grd, sat, chunk=4):
     return [torch.cat([o[k] for o in outs], dim=0) for k in range(9)], torch.cat(raws, dim=0)
 
 
-#: stated bf16 tolerance of the full-size configurations (bf16 encoders + bf16 tcgen05 decoder vs the fp32 oracle), per tensor
-BF16_MAX_TOL = 1.5e-1      # max|err| / max|ref|
-BF16_RMS_TOL = 6e-2        # rms(err) / rms(ref)
-BF16_ORI_DEG = 10.0        # 95th percentile of the angular error of the orientation field where |v| > 1 % of max|v|
+#: stated bf16 tolerance of the full-size configurations (bf16 encoders + bf16 tcgen05 decoder vs the fp32 oracle), per tensor.
+#: Measured on B200 (profiles/r02_parity.md): max <= 2.3e-2, rms <= 1.9e-2, orientation p95 <= 0.95 deg -- SURVEY section 8(c)'s
+#: proposed 2e-2 * max|ref| with a 1.7x margin.
+BF16_MAX_TOL = 4e-2        # max|err| / max|ref|
+BF16_RMS_TOL = 3e-2        # rms(err) / rms(ref)
+BF16_ORI_DEG = 3.0         # 95th percentile of the angular error of the orientation field where |v| > 1 % of max|v|
 
 
 @pytest.mark.parametrize("variant,shape_key,batch,wseed", [("vigor", "vigor", 64, 21), ("kitti", "kitti", 32, 22)])
