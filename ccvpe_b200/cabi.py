@@ -25,7 +25,7 @@ EXPORTED_SYMBOLS = (
     "ccvpe_pose_scratch_bytes", "ccvpe_pose_decode", "ccvpe_bias_silu_nhwc", "ccvpe_dwconv_bias_silu_nhwc",
     "ccvpe_pointwise_silu_nhwc", "ccvpe_stem_conv_silu_nhwc", "ccvpe_se_gate_scale",
     "ccvpe_wrap_columns_nhwc",
-    "ccvpe_ingest_u8",
+    "ccvpe_ingest_u8", "ccvpe_stem_conv_silu_u8_nhwc",
     # training step (config 5)
     "ccvpe_wgrad_workspace_elems", "ccvpe_wgrad", "ccvpe_wgrad_plan", "ccvpe_colsum_workspace_elems", "ccvpe_colsum",
     "ccvpe_relu_bwd", "ccvpe_planar_to_cl", "ccvpe_cl_to_planar", "ccvpe_ori_normalize_bwd",
@@ -140,6 +140,10 @@ def load() -> C.CDLL:
     lib.ccvpe_stem_conv_silu_nhwc.restype = C.c_int
     lib.ccvpe_stem_conv_silu_nhwc.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                               C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.ccvpe_stem_conv_silu_u8_nhwc.restype = C.c_int
+    lib.ccvpe_stem_conv_silu_u8_nhwc.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                                 C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p, C.c_void_p, C.c_int,
+                                                 C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.ccvpe_se_gate_scale.restype = C.c_int
     lib.ccvpe_se_gate_scale.argtypes = [C.c_void_p, C.c_float] + [C.c_void_p] * 6 + [C.c_int] * 4 + [C.c_void_p]
     lib.ccvpe_wrap_columns_nhwc.restype = C.c_int
@@ -441,6 +445,30 @@ def stem_conv_silu_nhwc(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, ou
     _check(load().ccvpe_stem_conv_silu_nhwc(_ptr(x), B, H, W, _ptr(w.contiguous()), _ptr(bias), CO, _ptr(out), in_pad_lo,
                                             in_pad_hi, out_pad_lo, out_pad_hi, 1 if circular else 0, _stream()),
            "ccvpe_stem_conv_silu_nhwc")
+
+
+def stem_conv_silu_u8_nhwc(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, out: torch.Tensor, in_pad_lo: int,
+                           in_pad_hi: int, out_pad_lo: int, out_pad_hi: int, circular: bool, crop_w: Optional[int] = None,
+                           shift: Optional[torch.Tensor] = None, mean=None, std=None):
+    """The stem over a uint8 NCHW image [B,3,H,Wsrc] with ToTensor + Normalize, panorama roll and FoV crop fused into the
+    loads.  out: contiguous bf16 [B, Ho+lo+hi, Wo+lo+hi, CO] for the cropped width."""
+    _require_cuda(x, w, bias, out, shift)
+    B, Cin, H, Wsrc = x.shape
+    if Cin != 3 or x.dtype != torch.uint8 or not x.is_contiguous():
+        raise CcvpeError("stem_conv_silu_u8_nhwc: x must be contiguous uint8 [B,3,H,W]")
+    W = int(crop_w or Wsrc)
+    CO = w.shape[1]
+    Ho, Wo = (H + in_pad_lo + in_pad_hi - 3) // 2 + 1, (W + in_pad_lo + in_pad_hi - 3) // 2 + 1
+    want = (B, Ho + out_pad_lo + out_pad_hi, Wo + out_pad_lo + out_pad_hi, CO)
+    if tuple(out.shape) != want or out.dtype != torch.bfloat16 or not out.is_contiguous():
+        raise CcvpeError(f"stem_conv_silu_u8_nhwc: out must be contiguous bf16 {want}, got {tuple(out.shape)}")
+    if shift is not None and (shift.dtype != torch.int32 or shift.numel() != B):
+        raise CcvpeError("stem_conv_silu_u8_nhwc: shift must be int32 [B]")
+    m = (C.c_float * 3)(*[float(v) for v in (mean or IMAGENET_MEAN)])
+    s = (C.c_float * 3)(*[float(v) for v in (std or IMAGENET_STD)])
+    _check(load().ccvpe_stem_conv_silu_u8_nhwc(_ptr(x), B, H, Wsrc, W, _ptr(shift), m, s, _ptr(w.contiguous()), _ptr(bias), CO,
+                                               _ptr(out), in_pad_lo, in_pad_hi, out_pad_lo, out_pad_hi, 1 if circular else 0,
+                                               _stream()), "ccvpe_stem_conv_silu_u8_nhwc")
 
 
 def se_gate_scale(chan_sum: torch.Tensor, inv_hw: float, w_red: torch.Tensor, b_red: torch.Tensor, w_se: torch.Tensor,

@@ -306,10 +306,21 @@ dwconv_bias_silu_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_sb, int64
 // layout conversion of the image, two F.pad copies, cuDNN's conv + its own padding pass, and the bias/SiLU pass.
 // One thread = two horizontally adjacent output pixels x all CO output channels (weights broadcast from shared memory).
 // ---------------------------------------------------------------------------------------------------------------------
-template <int CO, bool CIRC>
+// U8: the image arrives as uint8 NCHW [B, 3, H, Wsrc] and ToTensor + Normalize (v = u8 * sc[c] + sh[c]), the per-image
+// panorama roll (torch.roll along the width) and the FoV crop to the first W columns happen in the load (reference
+// train_VIGOR.py:55-70, 272-273; datasets.py:118) -- the f4 input pipeline fused into the first kernel of the encoder.
+struct StemU8 {
+  const uint8_t* x;
+  const int32_t* shift;      // [B] or NULL
+  int Wsrc;
+  float sc[3], sh[3];
+};
+
+template <int CO, bool CIRC, bool U8>
 __global__ void __launch_bounds__(128)
 stem_conv_silu_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                      __nv_bfloat16* __restrict__ out, int H, int W, int Ho, int Wo, int in_lo, int out_lo, int Hp, int Wp) {
+                      __nv_bfloat16* __restrict__ out, int H, int W, int Ho, int Wo, int in_lo, int out_lo, int Hp, int Wp,
+                      const StemU8 u8) {
   __shared__ __align__(16) float s_w[27 * CO];
   __shared__ __align__(16) float s_b[CO];
   for (int i = threadIdx.x; i < 27 * CO; i += blockDim.x) s_w[i] = w[i];
@@ -322,7 +333,13 @@ stem_conv_silu_kernel(const float* __restrict__ x, const float* __restrict__ w, 
   uint64_t acc[2][CO / 2];                                    // packed fp32 pairs over the output channels (FFMA2)
 #pragma unroll
   for (int c = 0; c < CO / 2; ++c) acc[0][c] = acc[1][c] = pack_f32x2(s_b[2 * c], s_b[2 * c + 1]);
-  const float* xb = x + (int64_t)b * 3 * H * W;
+  const float* xb = U8 ? nullptr : x + (int64_t)b * 3 * H * W;
+  const uint8_t* xb8 = U8 ? u8.x + (int64_t)b * 3 * H * u8.Wsrc : nullptr;
+  int roll = 0;
+  if (U8 && u8.shift) {
+    roll = u8.shift[b] % u8.Wsrc;
+    if (roll < 0) roll += u8.Wsrc;
+  }
 #pragma unroll 1
   for (int ci = 0; ci < 3; ++ci) {
 #pragma unroll
@@ -335,7 +352,16 @@ stem_conv_silu_kernel(const float* __restrict__ x, const float* __restrict__ w, 
         bool ok = ih >= 0 && ih < H;
         if (CIRC) iw = iw < 0 ? iw + W : (iw >= W ? iw - W : iw);
         else ok = ok && iw >= 0 && iw < W;
-        const float v = ok ? __ldg(xb + ((int64_t)ci * H + ih) * W + iw) : 0.f;
+        float v = 0.f;
+        if (ok) {
+          if (U8) {
+            int ws = iw - roll;                    // torch.roll: out[w] = in[(w - shift) mod Wsrc]
+            if (ws < 0) ws += u8.Wsrc;
+            v = fmaf((float)__ldg(xb8 + ((int64_t)ci * H + ih) * u8.Wsrc + ws), u8.sc[ci], u8.sh[ci]);
+          } else {
+            v = __ldg(xb + ((int64_t)ci * H + ih) * W + iw);
+          }
+        }
         in[ix] = pack_f32x2(v, v);
       }
 #pragma unroll
@@ -532,10 +558,48 @@ extern "C" int ccvpe_stem_conv_silu_nhwc(const float* x, int B, int H, int W, co
   const int pairs = (Wo + 1) / 2;
   const dim3 grid((pairs + 127) / 128, Ho, B);
   cudaStream_t st = (cudaStream_t)stream;
+  StemU8 none;
+  memset(&none, 0, sizeof(none));
   if (circular)
-    stem_conv_silu_kernel<32, true><<<grid, 128, 0, st>>>(x, w, bias, (__nv_bfloat16*)out, H, W, Ho, Wo, in_pad_lo, out_pad_lo, Hp, Wp);
+    stem_conv_silu_kernel<32, true, false><<<grid, 128, 0, st>>>(x, w, bias, (__nv_bfloat16*)out, H, W, Ho, Wo, in_pad_lo, out_pad_lo, Hp, Wp, none);
   else
-    stem_conv_silu_kernel<32, false><<<grid, 128, 0, st>>>(x, w, bias, (__nv_bfloat16*)out, H, W, Ho, Wo, in_pad_lo, out_pad_lo, Hp, Wp);
+    stem_conv_silu_kernel<32, false, false><<<grid, 128, 0, st>>>(x, w, bias, (__nv_bfloat16*)out, H, W, Ho, Wo, in_pad_lo, out_pad_lo, Hp, Wp, none);
+  CCVPE_LAUNCH_CHECK("stem_conv_silu_kernel");
+  return CCVPE_OK;
+}
+
+extern "C" int ccvpe_stem_conv_silu_u8_nhwc(const uint8_t* x, int B, int H, int Wsrc, int crop_w, const int32_t* shift,
+                                            const float* mean_host, const float* std_host, const float* w, const float* bias,
+                                            int CO, void* out, int in_pad_lo, int in_pad_hi, int out_pad_lo, int out_pad_hi,
+                                            int circular, void* stream) {
+  using namespace ccvpe;
+  CCVPE_REQUIRE(x && w && bias && out && mean_host && std_host, "ccvpe_stem_conv_silu_u8_nhwc: null pointer");
+  const int W = crop_w;
+  CCVPE_REQUIRE(B > 0 && H >= 3 && W >= 3 && W <= Wsrc && B <= 65535, "ccvpe_stem_conv_silu_u8_nhwc: bad shape B=%d H=%d W=%d Wsrc=%d",
+                B, H, W, Wsrc);
+  CCVPE_REQUIRE(CO == 32, "ccvpe_stem_conv_silu_u8_nhwc: CO=%d unsupported (EfficientNet-B0 stem has 32 channels)", CO);
+  CCVPE_REQUIRE(in_pad_lo >= 0 && in_pad_lo <= 2 && in_pad_hi >= 0 && in_pad_hi <= 2 && out_pad_lo >= 0 && out_pad_hi >= 0,
+                "ccvpe_stem_conv_silu_u8_nhwc: bad padding");
+  CCVPE_REQUIRE(aligned16(out), "ccvpe_stem_conv_silu_u8_nhwc: out must be 16-byte aligned");
+  const int Ho = (H + in_pad_lo + in_pad_hi - 3) / 2 + 1, Wo = (W + in_pad_lo + in_pad_hi - 3) / 2 + 1;
+  CCVPE_REQUIRE(Ho <= 65535, "ccvpe_stem_conv_silu_u8_nhwc: image too tall");
+  CCVPE_REQUIRE(!circular || (out_pad_lo <= Wo && out_pad_hi <= Wo), "ccvpe_stem_conv_silu_u8_nhwc: wrap wider than the image");
+  const int Hp = Ho + out_pad_lo + out_pad_hi, Wp = Wo + out_pad_lo + out_pad_hi;
+  const int pairs = (Wo + 1) / 2;
+  const dim3 grid((pairs + 127) / 128, Ho, B);
+  StemU8 u;
+  u.x = x;
+  u.shift = shift;
+  u.Wsrc = Wsrc;
+  for (int c = 0; c < 3; ++c) {           // (u8 / 255 - mean) / std  ==  u8 * sc + sh
+    u.sc[c] = 1.f / (255.f * std_host[c]);
+    u.sh[c] = -mean_host[c] / std_host[c];
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (circular)
+    stem_conv_silu_kernel<32, true, true><<<grid, 128, 0, st>>>(nullptr, w, bias, (__nv_bfloat16*)out, H, W, Ho, Wo, in_pad_lo, out_pad_lo, Hp, Wp, u);
+  else
+    stem_conv_silu_kernel<32, false, true><<<grid, 128, 0, st>>>(nullptr, w, bias, (__nv_bfloat16*)out, H, W, Ho, Wo, in_pad_lo, out_pad_lo, Hp, Wp, u);
   CCVPE_LAUNCH_CHECK("stem_conv_silu_kernel");
   return CCVPE_OK;
 }

@@ -332,7 +332,7 @@ extern "C" int64_t ccvpe_colsum_workspace_elems(int64_t n_pix, int C, int s) {
   if (n_pix <= 0 || C <= 0 || (s != 1 && s != 2)) return -1;
   int64_t blocks = (n_pix + 255) / 256;
   if (blocks > 4LL * sm_count()) blocks = 4LL * sm_count();
-  return blocks * s * s * C + 64;
+  return blocks * s * s * C + 64 + 4096;
 }
 
 extern "C" int ccvpe_colsum(const void* x, int dtype, int B, int H, int W, int C, int ld, const float* w, int s,
@@ -343,14 +343,22 @@ extern "C" int ccvpe_colsum(const void* x, int dtype, int B, int H, int W, int C
                 "ccvpe_colsum: bad shape C=%d ld=%d", C, ld);
   CCVPE_REQUIRE(s == 1 || (s == 2 && H % 2 == 0 && W % 2 == 0), "ccvpe_colsum: s must be 1 or 2 (even H, W)");
   CCVPE_REQUIRE(dtype == CCVPE_F32 || dtype == CCVPE_BF16, "ccvpe_colsum: bad dtype");
-  if (C > 512) {   // wide maps (the 1280- / 2048-channel cell descriptors): 512 columns per pass, same workspace
-    CCVPE_REQUIRE(s == 1, "ccvpe_colsum: C=%d > 512 is only supported for s == 1", C);
+  if (C > 512) {   // wide maps (1024-channel transposed convs, 1280- / 2048-channel cell descriptors): 512 columns per pass
     const int esz = dtype == CCVPE_F32 ? 4 : 2;
+    const int buckets = s * s;
+    int64_t blocks_full = ((int64_t)B * H * W + 255) / 256;
+    if (blocks_full > 4LL * sm_count()) blocks_full = 4LL * sm_count();
+    float* tmp = workspace + blocks_full * buckets * 512 + 64;         // behind the partials of one 512-column pass
     for (int c0 = 0; c0 < C; c0 += 512) {
       const int cc = C - c0 < 512 ? C - c0 : 512;
-      const int rc = ccvpe_colsum(static_cast<const uint8_t*>(x) + (int64_t)c0 * esz, dtype, B, H, W, cc, ld, w, 1, out + c0,
-                                  workspace, stream);
+      const int rc = ccvpe_colsum(static_cast<const uint8_t*>(x) + (int64_t)c0 * esz, dtype, B, H, W, cc, ld, w, s,
+                                  buckets == 1 ? out + c0 : tmp, workspace, stream);
       if (rc != CCVPE_OK) return rc;
+      if (buckets > 1) {
+        const cudaError_t e = cudaMemcpy2DAsync(out + c0, (size_t)C * 4, tmp, (size_t)cc * 4, (size_t)cc * 4, buckets,
+                                                cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+        if (e != cudaSuccess) return fail(CCVPE_ERR_CUDA, "ccvpe_colsum: cudaMemcpy2DAsync: %s", cudaGetErrorString(e));
+      }
     }
     return CCVPE_OK;
   }

@@ -194,6 +194,15 @@ int ccvpe_stem_conv_silu_nhwc(const float* x, int B, int H, int W, const float* 
                               void* out, int in_pad_lo, int in_pad_hi, int out_pad_lo, int out_pad_hi, int circular,
                               void* stream);
 
+/* The same stem with the f4 input pipeline fused into its loads: x is the uint8 image batch NCHW [B, 3, H, Wsrc]; every load
+ * applies ToTensor + Normalize ((u8 / 255 - mean[c]) / std[c], evaluated as one FMA), the per-image panorama roll
+ * (torch.roll by shift[b] columns; shift NULL = none) and the limited-FoV crop to the first crop_w columns
+ * (reference train_VIGOR.py:55-70, 272-273; datasets.py:118).  mean_host / std_host: HOST float[3]. */
+int ccvpe_stem_conv_silu_u8_nhwc(const uint8_t* x, int B, int H, int Wsrc, int crop_w, const int32_t* shift,
+                                 const float* mean_host, const float* std_host, const float* w, const float* bias, int CO,
+                                 void* out, int in_pad_lo, int in_pad_hi, int out_pad_lo, int out_pad_hi, int circular,
+                                 void* stream);
+
 /* Circular width padding of a padded channels-last bf16 image [B, H+lo+hi, W+lo+hi, C] (pad the same on both axes, as
  * the depthwise convs use it) whose interior is already written: the lo left / hi right padding columns of the interior
  * rows receive the wrapped-around interior columns (the reference's circular-padding patch of the ground encoder,

@@ -99,7 +99,8 @@ def test_wgrad_conv3x3_tcgen05(cuda_device, B, c0, c1, cout, H, W):
     assert rel_err(got, w.grad) < 1e-3, rel_err(got, w.grad)
 
 
-@pytest.mark.parametrize("B,cin,cout,H,with_scale", [(2, 40, 16, 12, True), (1, 160, 80, 8, False), (2, 32, 24, 5, True)])
+@pytest.mark.parametrize("B,cin,cout,H,with_scale", [(2, 40, 16, 12, True), (1, 160, 80, 8, False), (2, 32, 24, 5, True),
+                                                       (1, 64, 1024, 4, True)])      # deconv6: 1024 output channels
 def test_wgrad_deconv_and_colsum(cuda_device, B, cin, cout, H, with_scale):
     """ConvTranspose2d(k2, s2) over [max | x * inv]: weight rows 1.. from ccvpe_wgrad (A = dY as a k2 s2 image, G = x with
     the F.normalize row scale), row 0 (max channel) and the bias from ccvpe_colsum -- vs autograd."""
