@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 
@@ -14,7 +15,7 @@ namespace ccvpe {
 
 // ---- error reporting -------------------------------------------------------------------------------------------
 char* last_error_buffer();          // thread-local, 512 bytes
-int64_t& launch_counter();          // thread-local
+std::atomic<int64_t>& launch_counter();   // process wide
 
 inline int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -30,7 +31,7 @@ inline int fail(int code, const char* fmt, ...) {
   } while (0)
 
 inline int check_launch(const char* what) {
-  launch_counter() += 1;
+  launch_counter().fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(CCVPE_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
   return CCVPE_OK;

@@ -8,8 +8,8 @@ char* last_error_buffer() {
   return buf;
 }
 
-int64_t& launch_counter() {
-  static thread_local int64_t n = 0;
+std::atomic<int64_t>& launch_counter() {
+  static std::atomic<int64_t> n{0};      // process wide: autograd runs the backward kernels on its own thread
   return n;
 }
 
@@ -32,6 +32,6 @@ int sm_count() {
 extern "C" {
 int ccvpe_abi_version(void) { return CCVPE_ABI_VERSION; }
 const char* ccvpe_last_error(void) { return ccvpe::last_error_buffer(); }
-int64_t ccvpe_launch_count(void) { return ccvpe::launch_counter(); }
-void ccvpe_reset_launch_count(void) { ccvpe::launch_counter() = 0; }
+int64_t ccvpe_launch_count(void) { return ccvpe::launch_counter().load(); }
+void ccvpe_reset_launch_count(void) { ccvpe::launch_counter().store(0); }
 }

@@ -169,11 +169,18 @@ class FastEncoder:
             B, _c, H, W = x.shape
             Ho, Wo = (H + lo + hi - 3) // 2 + 1, (W + lo + hi - 3) // 2 + 1
             buf = self._padded(B, 32, Ho, Wo, o0.pad_lo, o0.pad_hi, "dw")
-            cabi.stem_conv_silu_nhwc(x.float().contiguous(), self.stem_w_taps, self.stem_b_f32, buf, lo, hi, o0.pad_lo,
-                                     o0.pad_hi, self.circular)
+            if x.dtype == torch.uint8:
+                # f4: ToTensor + ImageNet Normalize fused into the stem's loads (reference train_VIGOR.py:55-70)
+                cabi.stem_conv_silu_u8_nhwc(x.contiguous(), self.stem_w_taps, self.stem_b_f32, buf, lo, hi, o0.pad_lo,
+                                            o0.pad_hi, self.circular)
+            else:
+                cabi.stem_conv_silu_nhwc(x.float().contiguous(), self.stem_w_taps, self.stem_b_f32, buf, lo, hi, o0.pad_lo,
+                                         o0.pad_hi, self.circular)
             stem_padded = buf.permute(0, 3, 1, 2)
             pre = pre_bias = None
         else:
+            if x.dtype == torch.uint8:
+                raise cabi.CcvpeError("uint8 images are ingested by the CUDA bf16 encoder plan only (models.ingest otherwise)")
             x = x.to(dt).contiguous(memory_format=torch.channels_last)
             if self.circular:
                 x = F.pad(F.pad(x, (lo, hi, 0, 0), mode="circular"), (0, 0, lo, hi))     # 3-channel input: negligible

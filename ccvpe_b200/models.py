@@ -166,11 +166,17 @@ class _CVMBase(nn.Module):
         return cached[1], cached[2]
 
     def _encode(self, grd, sat):
+        """uint8 inputs (an extension over the reference: images as the decoder hands them over) are normalised on the
+        device: fused into the stem kernel's loads on the bf16 plan, through `ingest` otherwise."""
         if self._precision == "bf16" and not self.training:
             ge, se = self._bf16_encoders()
             fg = ge.extract_features(grd)
             fs, multi = se.extract_features_multiscale(sat)
             return fg, fs, multi, torch.bfloat16
+        if grd.dtype == torch.uint8:
+            grd = self.ingest(grd)
+        if sat.dtype == torch.uint8:
+            sat = self.ingest(sat)
         # fp32 means fp32: cuDNN must not silently drop the encoders to TF32 (torch's default for convolutions)
         cudnn = torch.backends.cudnn           # (keep the caller's benchmark / deterministic choices)
         with cudnn.flags(enabled=True, benchmark=cudnn.benchmark, deterministic=cudnn.deterministic, allow_tf32=False):
@@ -273,8 +279,11 @@ class _CVMBase(nn.Module):
         return out
 
     def localize_u8(self, grd_u8, sat_u8, shift=None, crop_w=None):
-        """uint8 images in, poses out: ingest (normalise / roll / crop) + forward + pose decode, all on the device."""
-        return self.localize(self.ingest(grd_u8, shift, crop_w), self.ingest(sat_u8))
+        """uint8 images in, poses out: normalise (/ roll / crop) + forward + pose decode, all on the device.  Without a roll or
+        crop the bf16 plan reads the uint8 images straight from the stem kernel (no fp32 image is ever materialised)."""
+        if shift is None and crop_w is None:
+            return self.localize(grd_u8, sat_u8)
+        return self.localize(self.ingest(grd_u8, shift, crop_w), sat_u8)
 
 
 class CVM_VIGOR(_CVMBase):

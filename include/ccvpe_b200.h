@@ -45,7 +45,7 @@ enum {
 
 int ccvpe_abi_version(void);
 const char* ccvpe_last_error(void);
-/* number of kernels this library has launched on behalf of the calling thread since the last reset */
+/* number of kernels this library has launched (all threads of the process) since the last reset */
 int64_t ccvpe_launch_count(void);
 void ccvpe_reset_launch_count(void);
 

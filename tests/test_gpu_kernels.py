@@ -665,3 +665,25 @@ def test_ingest_u8_matches_torchvision_arithmetic(cuda_device, B, H, W, crop, nh
     out = models.CVM_VIGOR.ingest(src.to(cuda_device), shifts.to(cuda_device) if rolled else None, crop)
     torch.cuda.synchronize()
     assert out.shape == ref.shape and torch.equal(out.cpu(), ref)
+
+
+@pytest.mark.parametrize("B,H,W,crop,circ,rolled", [(2, 32, 64, 64, True, True), (1, 20, 48, 30, False, True),
+                                                     (2, 16, 24, 24, False, False)])
+def test_stem_conv_silu_u8_fused_ingest(cuda_device, B, H, W, crop, circ, rolled):
+    """Stem kernel reading uint8 images (ToTensor + Normalize + roll + crop in the loads) == the fp32 stem kernel on the
+    ingested image (the normalisation is one FMA instead of divide-subtract-divide: 1e-2 of max|ref| after bf16 rounding)."""
+    g = _gen(42)
+    dev = cuda_device
+    img = torch.randint(0, 256, (B, 3, H, W), generator=g, dtype=torch.uint8).to(dev)
+    shifts = torch.randint(-W, W, (B,), generator=g, dtype=torch.int32).to(dev) if rolled else None
+    w = (torch.randn(27, 32, generator=g) * 0.2).to(dev)
+    bias = torch.randn(32, generator=g).to(dev)
+    from ccvpe_b200 import models
+    x32 = models.CVM_VIGOR.ingest(img, shifts, crop)
+    Ho, Wo = (H + 1 - 3) // 2 + 1, (crop + 1 - 3) // 2 + 1
+    ref = torch.zeros(B, Ho + 2, Wo + 2, 32, device=dev, dtype=torch.bfloat16)
+    got = torch.zeros_like(ref)
+    cabi.stem_conv_silu_nhwc(x32, w, bias, ref, 0, 1, 1, 1, circ)
+    cabi.stem_conv_silu_u8_nhwc(img, w, bias, got, 0, 1, 1, 1, circ, crop_w=crop, shift=shifts)
+    torch.cuda.synchronize()
+    assert rel_err(got.float(), ref.float()) < 1e-2
