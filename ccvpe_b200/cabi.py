@@ -632,7 +632,7 @@ def grd_descriptors_bwd(feat: torch.Tensor, heads, dgs, dfeat: torch.Tensor, dw1
     _require_cuda(feat, dfeat, *[t for h in heads for t in h], *dgs, *dw1, *db1, *dw2, *db2)
     arr = lambda ts: (C.c_void_p * n)(*[t.data_ptr() for t in ts])
     cs = (C.c_int32 * n)(*[h[0].shape[0] for h in heads])
-    scratch = torch.empty(n * B * K * W, dtype=torch.float32, device=feat.device)
+    scratch = torch.empty(2 * n * B * K * W, dtype=torch.float32, device=feat.device)
     _check(load().ccvpe_grd_descriptors_bwd(_ptr(feat), dtype_code(feat.dtype), B, K, H, W, sb, sk, sh, sw, n,
                                             arr([h[0] for h in heads]), arr([h[1] for h in heads]),
                                             arr([h[2] for h in heads]), cs, arr(dgs), _ptr(dfeat), arr(dw1), arr(db1),

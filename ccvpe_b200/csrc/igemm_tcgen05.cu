@@ -333,15 +333,17 @@ igemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
 static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 struct TcGeometry {
-  bool cell;        // k2 s2 cell-descriptor gather
-  int tw, th, tb;   // conv tile: tw x th pixels x tb images = 128 rows
+  bool cell;        // k2 s2 gather (aerial cell descriptors; data gradient of the k2 s2 transposed convs)
+  int tw, th, tb;   // conv tile: tw x th pixels x tb images = 128 rows (cell: tw output columns x th (row, image) pairs)
 };
 
 static bool tc_geometry(const ccvpe_igemm_desc& d, TcGeometry* g) {
   if (d.stride == 2 && d.kh == 2 && d.kw == 2 && d.pad == 0) {
-    if (d.Hin != 16 || d.Win != 16 || d.Hout != 8 || d.Wout != 8 || d.c1 != 0) return false;
+    if (d.Hin != 2 * d.Hout || d.Win != 2 * d.Wout || d.c1 != 0 || !is_pow2(d.Wout)) return false;
     g->cell = true;
-    g->tw = g->th = g->tb = 0;
+    g->tw = d.Wout < TC_BM ? d.Wout : TC_BM;
+    g->th = TC_BM / g->tw;
+    g->tb = 0;
     return true;
   }
   if (d.stride != 1 || d.kh != d.kw || !(d.kh == 1 || d.kh == 3) || d.pad != (d.kh - 1) / 2) return false;
@@ -451,23 +453,25 @@ int igemm_tcgen05(const ccvpe_igemm_desc& d, cudaStream_t st, const TcOutPad* ou
   int rc;
   const uint64_t esz = 2;
   if (g.cell) {
-    // [c][dw=2][j=8][dh=2][ib=8*B]
-    uint64_t dims[5] = {(uint64_t)d.c0, 2, 8, 2, (uint64_t)8 * d.B};
+    // [c][dw=2][j=Wout][dh=2][ib=Hout*B]: output pixel (ib, j), tap (dh, dw) reads input pixel (2*ib + dh, 2*j + dw)
+    // (rows of consecutive images are Hin input rows = Hout output rows apart, so (row, image) merge into one axis)
+    const int rows = d.Hout * d.B;
+    uint64_t dims[5] = {(uint64_t)d.c0, 2, (uint64_t)d.Wout, 2, (uint64_t)rows};
     uint64_t str[4] = {(uint64_t)d.ld0 * esz, 2ull * d.ld0 * esz, (uint64_t)d.Win * d.ld0 * esz,
                        2ull * d.Win * d.ld0 * esz};
-    uint32_t box[5] = {(uint32_t)p.kw0, 1, 8, 1, 16};
+    uint32_t box[5] = {(uint32_t)p.kw0, 1, (uint32_t)g.tw, 1, (uint32_t)g.th};
     if ((rc = encode_map(&p.tm_a0, d.a0, 5, dims, str, box, p.kw0)) != CCVPE_OK) return rc;
     p.a_rank = 5;
-    p.tiles[0] = 1; p.tiles[1] = 1; p.tiles[2] = 1; p.tiles[3] = (8 * d.B + 15) / 16;
-    p.box[0] = 1; p.box[1] = 8; p.box[2] = 1; p.box[3] = 16;
+    p.tiles[0] = 1; p.tiles[1] = d.Wout / g.tw; p.tiles[2] = 1; p.tiles[3] = (rows + g.th - 1) / g.th;
+    p.box[0] = 1; p.box[1] = g.tw; p.box[2] = 1; p.box[3] = g.th;
     for (int t = 0; t < 4; ++t) {
       p.tap_off[t][0] = t & 1;   // dw
       p.tap_off[t][1] = 0;
       p.tap_off[t][2] = t >> 1;  // dh
       p.tap_off[t][3] = 0;
     }
-    p.out_stride[0] = 0; p.out_stride[1] = 1; p.out_stride[2] = 0; p.out_stride[3] = 8;
-    p.extent[0] = 1 << 30; p.extent[1] = 8; p.extent[2] = 1 << 30; p.extent[3] = 8 * d.B;
+    p.out_stride[0] = 0; p.out_stride[1] = 1; p.out_stride[2] = 0; p.out_stride[3] = d.Wout;
+    p.extent[0] = 1 << 30; p.extent[1] = d.Wout; p.extent[2] = 1 << 30; p.extent[3] = rows;
   } else if (d.kh == 1) {
     // 1x1 (transposed convs): the M axis is just the flattened pixel index -> 2-D maps, 128 consecutive pixels per tile
     const int64_t M = (int64_t)d.B * d.Hout * d.Wout;

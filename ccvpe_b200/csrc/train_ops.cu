@@ -325,6 +325,17 @@ colsum_partial_kernel(const T* __restrict__ x, int64_t n_pix, int H, int W, int 
   }
 }
 
+// out[e] = sum_blocks ws[block][e]: one WARP per output element (lanes stride over the blocks, then a fixed shuffle tree --
+// deterministic); the column counts here are tiny, so a thread-per-element loop over ~600 partials would be pure latency
+__global__ void colsum_final_kernel(const float* __restrict__ ws, float* __restrict__ out, int n_out, int blocks) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n_out) return;
+  float s = 0.f;
+  for (int k = lane; k < blocks; k += 32) s += ws[(int64_t)k * n_out + warp];
+  s = warp_sum(s);
+  if (lane == 0) out[warp] = s;
+}
+
 }  // namespace ccvpe
 
 extern "C" int64_t ccvpe_colsum_workspace_elems(int64_t n_pix, int C, int s) {
@@ -378,9 +389,9 @@ extern "C" int ccvpe_colsum(const void* x, int dtype, int B, int H, int W, int C
     colsum_partial_kernel<__nv_bfloat16><<<(int)blocks, CS_THREADS, sm, st>>>((const __nv_bfloat16*)x, n_pix, H, W, C, ld, w, s,
                                                                               (int)ppb, workspace);
   CCVPE_LAUNCH_CHECK("colsum_partial_kernel");
-  const int64_t n_out = (int64_t)s * s * C;
-  reduce_splits_kernel<<<(int)((n_out + 255) / 256), 256, 0, st>>>(workspace, out, n_out, (int)blocks);
-  CCVPE_LAUNCH_CHECK("reduce_splits_kernel");
+  const int n_out = s * s * C;
+  colsum_final_kernel<<<(n_out * 32 + 255) / 256, 256, 0, st>>>(workspace, out, n_out, (int)blocks);
+  CCVPE_LAUNCH_CHECK("colsum_final_kernel");
   return CCVPE_OK;
 }
 
@@ -720,9 +731,27 @@ struct RollShifts {
   int s[32];
 };
 
-// dg[b, k] = sum_i sum_tiles T[b, tile, i, (k + base_i) % C]  -  g[b, k] / gn^2 * sum_tiles c_part[b, tile]
+// T_sum[b][e] = sum_tiles t_part[b][tile][e] (e over R*C), tiles in order: one thread per (b, e), coalesced over e
+__global__ void match_bwd_reduce_tiles_kernel(const float* __restrict__ t_part, int tiles, int RC, float* __restrict__ t_sum) {
+  const int b = blockIdx.y;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < RC; e += gridDim.x * blockDim.x) {
+    const float* src = t_part + (int64_t)b * tiles * RC + e;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int tl = 0;
+    for (; tl + 4 <= tiles; tl += 4) {       // four independent chains (fixed association: deterministic)
+      s0 += src[(int64_t)tl * RC];
+      s1 += src[(int64_t)(tl + 1) * RC];
+      s2 += src[(int64_t)(tl + 2) * RC];
+      s3 += src[(int64_t)(tl + 3) * RC];
+    }
+    for (; tl < tiles; ++tl) s0 += src[(int64_t)tl * RC];
+    t_sum[(int64_t)b * RC + e] = (s0 + s1) + (s2 + s3);
+  }
+}
+
+// dg[b, k] = sum_i T_sum[b, i, (k + base_i) % C]  -  g[b, k] / gn^2 * sum_tiles c_part[b, tile]
 // (T already carries the 1 / (n_i gn) of the per-pixel coefficients)
-__global__ void match_bwd_finalize_kernel(const float* __restrict__ t_part, const float* __restrict__ c_part, int tiles,
+__global__ void match_bwd_finalize_kernel(const float* __restrict__ t_sum, const float* __restrict__ c_part, int tiles,
                                           int R, int C, int L, int offset, RollShifts sh, const float* __restrict__ g,
                                           const float* __restrict__ gnorm, float* __restrict__ dg) {
   const int b = blockIdx.y;
@@ -735,7 +764,7 @@ __global__ void match_bwd_finalize_kernel(const float* __restrict__ t_part, cons
       const int base = ((offset + sh.s[i]) % C + C) % C;
       int c = k + base;
       if (c >= C) c -= C;
-      for (int tl = 0; tl < tiles; ++tl) s += t_part[(((int64_t)b * tiles + tl) * R + i) * C + c];
+      s += t_sum[((int64_t)b * R + i) * C + c];
     }
     dg[(int64_t)b * L + k] = s - g[(int64_t)b * L + k] * csum / (gn * gn);
   }
@@ -752,7 +781,7 @@ extern "C" int64_t ccvpe_match_bwd_scratch_elems(int B, int HW, int C, int n_rol
   auto up = [](int64_t v) { return (v + 63) / 64 * 64; };
   const int64_t tiles = (HW + 127) / 128;
   return up((int64_t)B * n_rolls * C) + up((int64_t)n_rolls * C) + up(B) + up((int64_t)B * tiles * n_rolls * C) +
-         up((int64_t)B * tiles) + 256;
+         up((int64_t)B * tiles) + up((int64_t)B * n_rolls * C) + 256;
 }
 
 extern "C" int ccvpe_match_level_bwd(const void* x, int dtype, int B, int HW, int C, const float* g, int L, int offset,
@@ -777,6 +806,7 @@ extern "C" int ccvpe_match_level_bwd(const void* x, int dtype, int B, int HW, in
   float* gnorm = Mw + up((int64_t)n_rolls * C);
   float* t_part = gnorm + up(B);
   float* c_part = t_part + up((int64_t)B * tiles * n_rolls * C);
+  float* t_sum = c_part + up((int64_t)B * tiles);
   const bool windowed = L < C;
   int rc = build_rolled_descriptor_f32(g, B, L, C, offset, shifts_host, n_rolls, G, windowed ? Mw : nullptr, gnorm, st);
   if (rc != CCVPE_OK) return rc;
@@ -795,7 +825,10 @@ extern "C" int ccvpe_match_level_bwd(const void* x, int dtype, int B, int HW, in
   CCVPE_LAUNCH_CHECK("match_level_bwd_kernel");
   RollShifts sh;
   for (int i = 0; i < 32; ++i) sh.s[i] = i < n_rolls ? shifts_host[i] : 0;
-  match_bwd_finalize_kernel<<<dim3((L + 127) / 128, B), 128, 0, st>>>(t_part, c_part, tiles, n_rolls, C, L, offset, sh, g,
+  const int RC = n_rolls * C;
+  match_bwd_reduce_tiles_kernel<<<dim3((RC + 255) / 256, B), 256, 0, st>>>(t_part, tiles, RC, t_sum);
+  CCVPE_LAUNCH_CHECK("match_bwd_reduce_tiles_kernel");
+  match_bwd_finalize_kernel<<<dim3((L + 127) / 128, B), 128, 0, st>>>(t_sum, c_part, tiles, n_rolls, C, L, offset, sh, g,
                                                                       gnorm, dg);
   CCVPE_LAUNCH_CHECK("match_bwd_finalize_kernel");
   return CCVPE_OK;
@@ -1088,26 +1121,63 @@ __global__ void heads_bwd_data_kernel(const HeadsBwdArgs a) {
   }
 }
 
-// dW_l[ch, k], one thread per (l, ch, k): sum over (b, w) of dT * P with P recomputed from F
+// P_l[b, k, w] = sum_h v_l[h] F[b, k, h, w] for all heads (the forward's height-reduced volume): one thread per (b, k, w)
 template <typename T>
-__global__ void heads_bwd_w1_kernel(const HeadsBwdArgs a, int l) {
+__global__ void heads_bwd_reduce_h_kernel(const HeadsBwdArgs a, float* __restrict__ P) {
+  const int64_t total = (int64_t)a.B * a.K * a.W;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int w = (int)(i % a.W);
+    const int k = (int)((i / a.W) % a.K);
+    const int b = (int)(i / ((int64_t)a.W * a.K));
+    float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int h = 0; h < a.H; ++h) {
+      const float f = feat_at<T>(a, b, k, h, w);
+      for (int l = 0; l < a.n_heads; ++l) acc[l] = fmaf(a.w2[l][h], f, acc[l]);
+    }
+    for (int l = 0; l < a.n_heads; ++l) P[(((int64_t)l * a.B + b) * a.K + k) * a.W + w] = acc[l];
+  }
+}
+
+// dW_l[ch, k] = sum_{b, w} dT_l[b, ch, w] * P_l[b, k, w]: one thread per (ch, k), B*W terms
+__global__ void heads_bwd_w1_kernel(const HeadsBwdArgs a, const float* __restrict__ P, int l) {
   const int c = a.c[l];
   const int64_t total = (int64_t)c * a.K;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int k = (int)(i % a.K), ch = (int)(i / a.K);
     float s = 0.f;
-    for (int b = 0; b < a.B; ++b)
-      for (int w = 0; w < a.W; ++w) {
-        float pv = 0.f;
-        for (int h = 0; h < a.H; ++h) pv = fmaf(a.w2[l][h], feat_at<T>(a, b, k, h, w), pv);
-        s = fmaf(a.dg[l][(int64_t)b * a.W * c + w * c + ch], pv, s);
-      }
+    for (int b = 0; b < a.B; ++b) {
+      const float* pr = P + (((int64_t)l * a.B + b) * a.K + k) * a.W;
+      const float* dr = a.dg[l] + (int64_t)b * a.W * c + ch;
+      for (int w = 0; w < a.W; ++w) s = fmaf(dr[(int64_t)w * c], pr[w], s);
+    }
     a.dw1[l][(int64_t)ch * a.K + k] = s;
   }
 }
 
-// db1_l[ch], dv_l[h], db2_l: one block per head; thread-strided partials folded in a fixed order
+// dv_l[h] = sum_{b,k,w} F[b,k,h,w] U_l[b,k,w] (+ the b1 term, added by the small kernel): one block per (l, h)
 template <typename T>
+__global__ void __launch_bounds__(256) heads_bwd_w2_kernel(const HeadsBwdArgs a) {
+  __shared__ float red[256];
+  const int l = blockIdx.x, h = blockIdx.y, t = threadIdx.x;
+  float s = 0.f;
+  const int64_t total = (int64_t)a.B * a.K * a.W;
+  for (int64_t i = t; i < total; i += 256) {
+    const int w = (int)(i % a.W);
+    const int k = (int)((i / a.W) % a.K);
+    const int b = (int)(i / ((int64_t)a.W * a.K));
+    s = fmaf(feat_at<T>(a, b, k, h, w), a.U[(((int64_t)l * a.B + b) * a.K + k) * a.W + w], s);
+  }
+  red[t] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {                 // fixed tree: deterministic
+    if (t < o) red[t] += red[t + o];
+    __syncthreads();
+  }
+  if (t == 0) a.dw2[l][h] = red[0];
+}
+
+// db1_l[ch], db2_l and the b1 term of dv_l: one block per head; thread-strided partials folded in a fixed order
+// (runs AFTER heads_bwd_w2_kernel: it adds the b1 term to dw2)
 __global__ void __launch_bounds__(256) heads_bwd_small_kernel(const HeadsBwdArgs a) {
   __shared__ float red[256];
   const int l = blockIdx.x;
@@ -1115,7 +1185,6 @@ __global__ void __launch_bounds__(256) heads_bwd_small_kernel(const HeadsBwdArgs
   const int t = threadIdx.x;
   float vsum = 0.f;
   for (int h = 0; h < a.H; ++h) vsum += a.w2[l][h];
-  // db1[ch]
   for (int ch = 0; ch < c; ++ch) {
     float s = 0.f;
     for (int i = t; i < a.B * a.W; i += 256) {
@@ -1128,11 +1197,9 @@ __global__ void __launch_bounds__(256) heads_bwd_small_kernel(const HeadsBwdArgs
       float tot = 0.f;
       for (int i = 0; i < 256; ++i) tot += red[i];
       a.db1[l][ch] = tot * vsum;
-      red[0] = tot;
     }
     __syncthreads();
   }
-  // db2 = sum dg, and the b1 term of dv
   float s_dg = 0.f, s_b1 = 0.f;
   for (int i = t; i < a.B * a.W * c; i += 256) {
     const float v = a.dg[l][i];
@@ -1141,32 +1208,18 @@ __global__ void __launch_bounds__(256) heads_bwd_small_kernel(const HeadsBwdArgs
   }
   red[t] = s_dg;
   __syncthreads();
-  float tot_dg = 0.f;
-  if (t == 0) { for (int i = 0; i < 256; ++i) tot_dg += red[i]; a.db2[l][0] = tot_dg; }
+  if (t == 0) {
+    float tot = 0.f;
+    for (int i = 0; i < 256; ++i) tot += red[i];
+    a.db2[l][0] = tot;
+  }
   __syncthreads();
   red[t] = s_b1;
   __syncthreads();
-  __shared__ float b1_term;
-  if (t == 0) { float x = 0.f; for (int i = 0; i < 256; ++i) x += red[i]; b1_term = x; }
-  __syncthreads();
-  // dv[h] = sum_{b,k,w} F[b,k,h,w] U_l[b,k,w] + b1_term
-  for (int h = 0; h < a.H; ++h) {
-    float s = 0.f;
-    const int64_t total = (int64_t)a.B * a.K * a.W;
-    for (int64_t i = t; i < total; i += 256) {
-      const int w = (int)(i % a.W);
-      const int k = (int)((i / a.W) % a.K);
-      const int b = (int)(i / ((int64_t)a.W * a.K));
-      s = fmaf(feat_at<T>(a, b, k, h, w), a.U[(((int64_t)l * a.B + b) * a.K + k) * a.W + w], s);
-    }
-    red[t] = s;
-    __syncthreads();
-    if (t == 0) {
-      float tot = 0.f;
-      for (int i = 0; i < 256; ++i) tot += red[i];
-      a.dw2[l][h] = tot + b1_term;
-    }
-    __syncthreads();
+  if (t == 0) {
+    float x = 0.f;
+    for (int i = 0; i < 256; ++i) x += red[i];
+    for (int h = 0; h < a.H; ++h) a.dw2[l][h] += x;
   }
 }
 
@@ -1197,14 +1250,18 @@ extern "C" int ccvpe_grd_descriptors_bwd(const void* feat, int dtype, int B, int
   if (dtype == CCVPE_F32) heads_bwd_data_kernel<float><<<blocks, 256, 0, st>>>(a);
   else heads_bwd_data_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(a);
   CCVPE_LAUNCH_CHECK("heads_bwd_data_kernel");
+  float* P = scratch + (int64_t)n_heads * B * K * W;
+  if (dtype == CCVPE_F32) heads_bwd_reduce_h_kernel<float><<<blocks, 256, 0, st>>>(a, P);
+  else heads_bwd_reduce_h_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(a, P);
+  CCVPE_LAUNCH_CHECK("heads_bwd_reduce_h_kernel");
   for (int l = 0; l < n_heads; ++l) {
-    const int wb = ew_blocks((int64_t)c[l] * K);
-    if (dtype == CCVPE_F32) heads_bwd_w1_kernel<float><<<wb, 256, 0, st>>>(a, l);
-    else heads_bwd_w1_kernel<__nv_bfloat16><<<wb, 256, 0, st>>>(a, l);
+    heads_bwd_w1_kernel<<<ew_blocks((int64_t)c[l] * K), 256, 0, st>>>(a, P, l);
     CCVPE_LAUNCH_CHECK("heads_bwd_w1_kernel");
   }
-  if (dtype == CCVPE_F32) heads_bwd_small_kernel<float><<<n_heads, 256, 0, st>>>(a);
-  else heads_bwd_small_kernel<__nv_bfloat16><<<n_heads, 256, 0, st>>>(a);
+  if (dtype == CCVPE_F32) heads_bwd_w2_kernel<float><<<dim3(n_heads, H), 256, 0, st>>>(a);
+  else heads_bwd_w2_kernel<__nv_bfloat16><<<dim3(n_heads, H), 256, 0, st>>>(a);
+  CCVPE_LAUNCH_CHECK("heads_bwd_w2_kernel");
+  heads_bwd_small_kernel<<<n_heads, 256, 0, st>>>(a);
   CCVPE_LAUNCH_CHECK("heads_bwd_small_kernel");
   return CCVPE_OK;
 }

@@ -313,7 +313,7 @@ int ccvpe_orientation_loss(const float* ori, const float* gt_ori, const float* g
 
 /* Backward of the ground descriptor heads (models.py:57-97, 152-157); arguments as ccvpe_grd_descriptors plus the incoming
  * dg[l] fp32 [B, W*c[l]].  Outputs: dfeat fp32 [B, K, H, W] contiguous (NCHW), dw1[l] [c, K], db1[l] [c], dw2[l] [H],
- * db2[l] [1].  scratch: fp32, >= n_heads*B*K*W elements. */
+ * db2[l] [1].  scratch: fp32, >= 2*n_heads*B*K*W elements. */
 int ccvpe_grd_descriptors_bwd(const void* feat, int dtype, int B, int K, int H, int W, int64_t sb, int64_t sk, int64_t sh,
                               int64_t sw, int n_heads, const float* const* w1, const float* const* b1,
                               const float* const* w2, const int32_t* c, const float* const* dg, float* dfeat,

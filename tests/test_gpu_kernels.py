@@ -687,3 +687,23 @@ def test_stem_conv_silu_u8_fused_ingest(cuda_device, B, H, W, crop, circ, rolled
     cabi.stem_conv_silu_u8_nhwc(img, w, bias, got, 0, 1, 1, 1, circ, crop_w=crop, shift=shifts)
     torch.cuda.synchronize()
     assert rel_err(got.float(), ref.float()) < 1e-2
+
+
+@pytest.mark.parametrize("B,C,N,Hout,Wout,backend", [
+    (2, 40, 48, 16, 16, cabi.BACKEND_TCGEN05), (3, 16, 48, 64, 64, cabi.BACKEND_TCGEN05),
+    (1, 320, 648, 8, 16, cabi.BACKEND_TCGEN05), (2, 16, 48, 128, 256, cabi.BACKEND_TCGEN05),
+    (2, 40, 48, 16, 16, cabi.BACKEND_SIMT)])
+def test_conv_k2s2_general_shapes(cuda_device, B, C, N, Hout, Wout, backend):
+    """k2 s2 conv of any size (the data gradient of the k2 s2 transposed convs: dX = conv_k2s2(dY, W^T), models.py:109-124)
+    through the 5-D TMA gather on tcgen05 -- the aerial-cell geometry generalised -- vs F.conv2d."""
+    g = _gen(43)
+    dev = cuda_device
+    dt = torch.bfloat16
+    x = torch.randn(B, C, 2 * Hout, 2 * Wout, generator=g).to(dt).float()
+    w = (torch.randn(N, C, 2, 2, generator=g) * 0.1).to(dt).float()
+    ref = F.conv2d(x, w, stride=2)
+    w_kn = w.permute(2, 3, 1, 0).reshape(4, C, N).contiguous().to(dev, dt)
+    w_nk = _nk(w.permute(0, 2, 3, 1).reshape(N, 4, C), [C]).to(dev)
+    out = torch.empty(B, Hout, Wout, N, device=dev, dtype=dt)
+    _igemm(dev, _cl(x, dt, dev), None, Hout, Wout, 2, 2, 0, N, w_kn, None, out, 0, N, backend=backend, w_nk=w_nk)
+    assert rel_err(out.permute(0, 3, 1, 2).float(), ref) < BF16_TOL
