@@ -209,12 +209,20 @@ class _CVMBase(nn.Module):
         from .training import PostEncoderFunction, PostEncoderTrainer
         if self._trainer[0] is None:
             self._trainer[0] = PostEncoderTrainer(self.pipeline)
+        if grd.dtype == torch.uint8:
+            grd = self.ingest(grd)
+        if sat.dtype == torch.uint8:
+            sat = self.ingest(sat)
         with cabi.device_of(grd):
             cudnn = torch.backends.cudnn
-            with cudnn.flags(enabled=True, benchmark=cudnn.benchmark, deterministic=cudnn.deterministic, allow_tf32=False):
+            bf16 = self._precision == "bf16"
+            # fp32: exact fp32 encoders (no TF32); bf16: mixed precision -- fp32 master weights, bf16 autocast for the
+            # encoders' convolutions (BatchNorm statistics stay fp32), bf16 activations / GEMM operands in the CUDA path
+            with cudnn.flags(enabled=True, benchmark=cudnn.benchmark, deterministic=cudnn.deterministic, allow_tf32=False), \
+                    torch.autocast("cuda", dtype=torch.bfloat16, enabled=bf16):
                 fg = self.grd_efficientnet.extract_features(grd)                      # reference models.py:151
                 fs, multi = self.sat_efficientnet.extract_features_multiscale(sat)    # reference models.py:166
-            dtype = torch.bfloat16 if self._precision == "bf16" else torch.float32
+            dtype = torch.bfloat16 if bf16 else torch.float32
             skips = [multi[i] for i in SKIP_BLOCKS]
             params = list(self.pipeline._params().values())
             return PostEncoderFunction.apply(self._trainer[0], dtype, fg, fs, *skips, *skips, *params)

@@ -373,16 +373,23 @@ def test_training_step_fp32_matches_oracle_autograd(cuda_device, train_mode, mon
         if i != 2:
             assert rel_err(a, b) < 1e-3, i
     assert abs(loss.item() - ref_loss) < 1e-4 * abs(ref_loss), (loss.item(), ref_loss)
-    worst = {}
+    # Tolerance per tensor: 2e-3 of max|ref| of that tensor, plus an absolute floor of 2e-6 of the largest gradient entry of
+    # the model for the tensors whose gradient is ZERO in exact arithmetic and pure summation noise on both sides: the bias of
+    # the logits conv (sum over pixels of softmax - labels = 1 - 1) and, in train mode, every bias that is followed by a
+    # batch-statistics BatchNorm (which removes any per-channel constant).
+    gmax = max(float(v.abs().max()) for v in ref_grads.values() if v is not None)
+    bad = {}
     for k, p_ in gpu.named_parameters():
         rg = ref_grads[k]
         if rg is None:
             assert p_.grad is None or float(p_.grad.abs().max()) == 0.0, k       # _fc.* are never used (models.py:151,166)
             continue
         assert p_.grad is not None, k
-        worst[k] = rel_err(p_.grad, rg)
-    bad = {k: v for k, v in worst.items() if not v < 2e-3}
-    assert not bad, sorted(bad.items(), key=lambda kv: -kv[1])[:10]
+        err = float((p_.grad.detach().cpu().double() - rg.double()).abs().max())
+        scale = float(rg.abs().max())
+        if not err <= 2e-3 * scale + 2e-6 * gmax:
+            bad[k] = (err, scale, gmax)
+    assert not bad, sorted(bad.items(), key=lambda kv: -kv[1][0] / (kv[1][1] + 1e-30))[:10]
 
 
 def test_training_step_bf16_close_to_fp32_oracle(cuda_device):
