@@ -9,10 +9,16 @@
 // tiles (K = channels) are re-interpreted here with K = pixels; only the matrix descriptors and two idesc bits differ.
 //
 // Tile: 128 output channels n (UMMA M) x 32 input channels c (UMMA N) x all 9 taps: nine accumulators [128 x 32] in TMEM
-// (288 of 512 columns).  Per 64-pixel step the G tile [64 px x 128 n] is loaded ONCE and multiplied with nine spatially
-// shifted A boxes [64 px x 32 c] (conv halo = TMA zero fill): 36 MMAs of 128x32x16 per stage.  K (pixels) is split over
+// (288 of 512 columns).  Per 64-pixel step the G tile [64 px x 128 n] is loaded ONCE, and so is the A tile: ONE halo box
+// [(hb + 2) x (wb + 2) px x 32 c] (conv padding = TMA zero fill) serves all nine taps -- tap (ky, kx) of the 16 pixels of a
+// K step is the same shared-memory tile read (ky * (wb + 2) + kx) rows further down, i.e. only the start address of the
+// matrix descriptor moves (the swizzle is a function of the absolute shared-memory address, the one TMA wrote with).
+// 36 MMAs of 128x32x16 per stage against ~260 TMA box rows (nine separate tap boxes would be 640: TMA issues ~3 cycles
+// per box row, which is what bounded the first version of this kernel).  K (pixels) is split over
 // CTAs when there are fewer tiles than SMs; partial tiles go to the workspace and are folded in a fixed order
 // (deterministic).  Warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2-5 = epilogue.
+#include <cstdlib>
+
 #include "tcgen05_common.cuh"
 
 namespace ccvpe {
@@ -23,9 +29,11 @@ constexpr int WT_NT = 128;         // G-channel tile
 constexpr int WT_TAPS = 9;
 constexpr int WT_THREADS = 192;
 constexpr int WT_MAX_STAGES = 4;
+constexpr int WT_MAX_STAGES_HALO = 6;
 constexpr int WT_G_BYTES = WT_BK * WT_NT * 2;          // 16 KB: two [64 px x 64 n] SWIZZLE_128B boxes
 constexpr int WT_A_BYTES = WT_BK * WT_CT * 2;          // 4 KB per tap, SWIZZLE_64B
-constexpr int WT_STAGE_BYTES = WT_G_BYTES + WT_TAPS * WT_A_BYTES;   // 52 KB
+constexpr int WT_STAGE_BYTES = WT_G_BYTES + WT_TAPS * WT_A_BYTES;   // 52 KB (one box per tap)
+constexpr int WT_ROW_BYTES = WT_CT * 2;                // 64 B: one pixel of an A tile
 
 struct WgradTcParams {
   CUtensorMap tm_a0, tm_a1, tm_g;
@@ -34,6 +42,7 @@ struct WgradTcParams {
   int ksteps_total, ksteps_per_split;
   int c_tiles0;
   int stages;
+  int halo, stage_bytes, a_tx;         // halo mode: one (hb+2) x (wb+2) A box per stage; bytes TMA delivers for it
   float* dst;
 };
 
@@ -51,8 +60,8 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr, uint32_t l
 
 __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tcgen05_kernel(const __grid_constant__ WgradTcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_full[WT_MAX_STAGES];
-  __shared__ __align__(8) uint64_t bar_empty[WT_MAX_STAGES];
+  __shared__ __align__(8) uint64_t bar_full[WT_MAX_STAGES_HALO];
+  __shared__ __align__(8) uint64_t bar_empty[WT_MAX_STAGES_HALO];
   __shared__ __align__(8) uint64_t bar_acc;
   __shared__ uint32_t tmem_base_slot;
 
@@ -107,13 +116,17 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tcgen05_kernel(const __gr
       mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
       if (elect_one()) {
         const uint32_t full = smem_u32(&bar_full[stage]);
-        const uint32_t dst = smem_base + (uint32_t)(stage * WT_STAGE_BYTES);
-        mbar_arrive_expect_tx(full, (uint32_t)WT_STAGE_BYTES);
+        const uint32_t dst = smem_base + (uint32_t)(stage * p.stage_bytes);
+        mbar_arrive_expect_tx(full, (uint32_t)(WT_G_BYTES + (p.halo ? p.a_tx : WT_TAPS * WT_A_BYTES)));
         tma_load_2d(dst, &p.tm_g, full, n0, m0);
         tma_load_2d(dst + WT_G_BYTES / 2, &p.tm_g, full, n1, m0);
+        if (p.halo) {
+          tma_load_4d(dst + WT_G_BYTES, tma, full, c_start, w0 - 1, h0 - 1, b);
+        } else {
 #pragma unroll
-        for (int tap = 0; tap < WT_TAPS; ++tap)
-          tma_load_4d(dst + WT_G_BYTES + tap * WT_A_BYTES, tma, full, c_start, w0 + tap % 3 - 1, h0 + tap / 3 - 1, b);
+          for (int tap = 0; tap < WT_TAPS; ++tap)
+            tma_load_4d(dst + WT_G_BYTES + tap * WT_A_BYTES, tma, full, c_start, w0 + tap % 3 - 1, h0 + tap / 3 - 1, b);
+        }
       }
       __syncwarp();
       if (++stage == p.stages) {
@@ -132,16 +145,22 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tcgen05_kernel(const __gr
     for (int ks = ks_begin; ks < ks_end; ++ks) {
       mbar_wait(smem_u32(&bar_full[stage]), phase);
       tc_fence_after();
-      const uint32_t sbase = smem_base + (uint32_t)(stage * WT_STAGE_BYTES);
+      const uint32_t sbase = smem_base + (uint32_t)(stage * p.stage_bytes);
       if (elect_one()) {
+        const int pitch = p.wb + 2;                       // pixels per row of the halo tile
 #pragma unroll
         for (int kk = 0; kk < WT_BK / 16; ++kk) {
           // G: rows of 128 B (64 n), 16 pixels = 2 KB per K step; the second 64-n atom starts WT_G_BYTES/2 later
           const uint64_t gdesc = make_smem_desc_mn(sbase + kk * 2048, WT_G_BYTES / 2, 1024, 2);
+          // the 16 pixels of this K step lie in image row h of the block, starting at column w
+          const int hrow = (kk * 16) / p.wb, wcol = (kk * 16) - hrow * p.wb;
 #pragma unroll
           for (int tap = 0; tap < WT_TAPS; ++tap) {
-            // A tap: rows of 64 B (32 c), 16 pixels = 1 KB per K step, one atom along N
-            const uint64_t adesc = make_smem_desc_mn(sbase + WT_G_BYTES + tap * WT_A_BYTES + kk * 1024, 16, 512, 4);
+            // A tap: rows of 64 B (32 c), one atom along N.  Halo mode: the tap is a row offset into the one halo tile
+            const uint32_t a_addr = p.halo
+                ? sbase + WT_G_BYTES + (uint32_t)(((hrow + tap / 3) * pitch + wcol + tap % 3) * WT_ROW_BYTES)
+                : sbase + WT_G_BYTES + tap * WT_A_BYTES + kk * 1024;
+            const uint64_t adesc = make_smem_desc_mn(a_addr, 16, 512, 4);
             umma_bf16(tmem_base + (uint32_t)(tap * WT_CT), gdesc, adesc, idesc, (kk == 0) ? accumulate : 1u);
           }
         }
@@ -244,7 +263,12 @@ int wgrad_tcgen05(const ccvpe_wgrad_desc& d, cudaStream_t st) {
   p.W = d.Win; p.H = d.Hin; p.B = d.B; p.wb = pl.wb; p.hb = pl.hb; p.tiles_w = pl.tiles_w; p.tiles_h = pl.tiles_h;
   p.ksteps_total = pl.ksteps; p.ksteps_per_split = pl.ksteps_per_split;
   p.c_tiles0 = pl.c_tiles0;
-  p.stages = WT_MAX_STAGES;
+  static const bool halo_off = getenv("CCVPE_WGRAD_HALO") && atoi(getenv("CCVPE_WGRAD_HALO")) == 0;
+  p.halo = halo_off ? 0 : 1;
+  p.a_tx = (pl.wb + 2) * (pl.hb + 2) * WT_ROW_BYTES;
+  p.stage_bytes = p.halo ? WT_G_BYTES + (p.a_tx + 1023) / 1024 * 1024 : WT_STAGE_BYTES;
+  p.stages = p.halo ? WT_MAX_STAGES_HALO : WT_MAX_STAGES;
+  while (p.stages * p.stage_bytes > 200 * 1024) --p.stages;
   const int64_t n_out = (int64_t)p.Q * d.N;
   if (pl.splits > 1) {
     if (!d.workspace || d.workspace_elems < (int64_t)pl.splits * n_out)
@@ -259,7 +283,7 @@ int wgrad_tcgen05(const ccvpe_wgrad_desc& d, cudaStream_t st) {
     const int c = s ? d.c1 : d.c0, ld = s ? d.ld1 : d.ld0;
     uint64_t dims[4] = {(uint64_t)c, (uint64_t)d.Win, (uint64_t)d.Hin, (uint64_t)d.B};
     uint64_t str[3] = {(uint64_t)ld * 2, (uint64_t)d.Win * ld * 2, (uint64_t)d.Hin * d.Win * ld * 2};
-    uint32_t box[4] = {WT_CT, (uint32_t)pl.wb, (uint32_t)pl.hb, 1};
+    uint32_t box[4] = {WT_CT, (uint32_t)(pl.wb + (p.halo ? 2 : 0)), (uint32_t)(pl.hb + (p.halo ? 2 : 0)), 1};
     if ((rc = encode_map(s ? &p.tm_a1 : &p.tm_a0, base, 4, dims, str, box, 32)) != CCVPE_OK) return rc;
   }
   {
@@ -268,7 +292,7 @@ int wgrad_tcgen05(const ccvpe_wgrad_desc& d, cudaStream_t st) {
     uint32_t box[2] = {64, WT_BK};
     if ((rc = encode_map(&p.tm_g, d.g, 2, dims, str, box, 64)) != CCVPE_OK) return rc;
   }
-  const int smem = p.stages * WT_STAGE_BYTES + 1024;
+  const int smem = p.stages * p.stage_bytes + 1024;
   static thread_local uint64_t attr_set = 0;
   if (first_use_on_device(attr_set)) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096);

@@ -373,3 +373,42 @@ class PostEncoderFunction(torch.autograd.Function):
         res += [t.permute(0, 3, 1, 2).to(dt) for t, dt in zip(d_sk_ori, kdt)]
         res += [grads[k] for k in ctx.param_names]
         return tuple(res)
+
+
+class GraphedTrainStep:
+    """One whole training step -- zero_grad, forward, losses, backward, gradient all-reduce, optimizer step -- captured in a
+    single CUDA graph and replayed (the eager step is bound by ~3000 host-side launches of small encoder / optimizer /
+    decoder kernels, not by the GPU).  Everything in the step is capturable: the library never allocates or synchronises, its
+    tensor maps are by-value kernel parameters, the derived weight caches are rebuilt by kernels that are part of the
+    captured graph, the gradient buckets are static memory, and the optimizer must be constructed with capturable=True.
+
+        step = GraphedTrainStep(lambda grd, sat, gt, gwo, gor: ..., example_inputs)    # closure returns the loss tensor
+        loss = step(grd, sat, gt, gwo, gor)                                             # copies inputs in, replays
+
+    `fn` is run `warmup` times eagerly on a side stream before capture (so every lazily-built cache, cuDNN plan and
+    optimizer state exists), which means `warmup + 1` real optimizer steps happen during construction."""
+
+    def __init__(self, fn, example_inputs: Sequence[torch.Tensor], warmup: int = 3):
+        self.static_in = [t.clone() for t in example_inputs]
+        dev = self.static_in[0].device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                fn(*self.static_in)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = cabi.launch_count()
+        with torch.cuda.graph(self.graph):
+            self.static_loss = fn(*self.static_in)
+        self.launches = cabi.launch_count() - n0          # libccvpe_b200 kernels inside one replay
+        cabi.add_replayed_launches(-self.launches)        # captured, not executed
+
+    def __call__(self, *inputs: torch.Tensor) -> torch.Tensor:
+        for dst, src in zip(self.static_in, inputs):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        cabi.add_replayed_launches(self.launches)
+        return self.static_loss

@@ -393,8 +393,9 @@ def test_training_step_fp32_matches_oracle_autograd(cuda_device, train_mode, mon
 
 
 def test_training_step_bf16_close_to_fp32_oracle(cuda_device):
-    """bf16 training path (bf16 activations, tcgen05 forward and data-gradient GEMMs, fp32 weight gradients): the loss within
-    2 % of the fp32 oracle's and every gradient tensor with more than 1000 elements has cosine similarity >= 0.98 with it."""
+    """bf16 training path (bf16-autocast encoders, bf16 activations, tcgen05 forward / data-gradient / weight-gradient GEMMs
+    with fp32 accumulation, fp32 master weights): the loss within 2 % of the fp32 oracle's and every head / decoder gradient
+    tensor with more than 1000 elements has cosine similarity >= 0.95 with it (measured: >= 0.96, all but one >= 0.98)."""
     from ccvpe_b200.synthetic import synthetic_pair
     model = build_model("vigor", None, True, 32)
     grd, sat = synthetic_pair(2, (320, 640), seed=62)
@@ -416,9 +417,43 @@ def test_training_step_bf16_close_to_fp32_oracle(cuda_device):
         if rg is None or rg.numel() < 1000 or k.startswith(("grd_efficientnet", "sat_efficientnet")):
             continue
         cs = F.cosine_similarity(p_.grad.flatten().cpu().double(), rg.flatten().double(), dim=0).item()
-        if cs < 0.98:
+        if cs < 0.95:
             low[k] = cs
     assert not low, low
+
+
+def test_graphed_training_step_matches_eager(cuda_device):
+    """training.GraphedTrainStep: the whole step (zero_grad, forward, losses, backward, Adam) captured in one CUDA graph gives
+    the same losses as the same steps run eagerly from the same start (bf16 path, eval-mode BatchNorm so that both runs are
+    deterministic functions of the weights)."""
+    from ccvpe_b200.synthetic import synthetic_pair
+    from ccvpe_b200.training import GraphedTrainStep
+    dev = cuda_device
+    batch = [t.to(dev) for t in synthetic_pair(2, (320, 640), seed=64)] + [t.to(dev) for t in synthetic_ground_truth(2, seed=8)]
+    hist = {}
+    for mode in ("eager", "graph"):
+        model = build_model("vigor", None, True, 34).to(dev).set_precision("bf16").eval()
+        for n_, p_ in model.named_parameters():
+            p_.requires_grad_("._fc." not in n_)
+        opt = torch.optim.Adam([p_ for p_ in model.parameters() if p_.requires_grad], lr=1e-4, fused=True, capturable=True)
+
+        def fn(grd, sat, gt, gwo, gor):
+            opt.zero_grad(set_to_none=False)
+            loss = losses.training_loss(model(grd, sat), gt, gwo, gor)
+            loss.backward()
+            opt.step()
+            return loss.detach()
+
+        if mode == "eager":
+            hist[mode] = [float(fn(*batch)) for _ in range(6)]
+        else:
+            # give .grad static storage before capture (zero_grad(set_to_none=False) keeps it)
+            fn(*batch)
+            step = GraphedTrainStep(fn, batch, warmup=1)            # steps 2 and 3 (warm-up + capture)
+            hist[mode] = [float("nan")] * 3 + [float(step(*batch)) for _ in range(3)]
+    for a, b in zip(hist["eager"][3:], hist["graph"][3:]):
+        assert abs(a - b) <= 1e-3 * abs(a), hist
+    assert hist["eager"][-1] < hist["eager"][0]
 
 
 def test_adam_steps_reduce_the_loss(cuda_device):
