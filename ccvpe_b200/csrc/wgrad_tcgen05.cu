@@ -136,33 +136,42 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tcgen05_kernel(const __gr
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    // D[128 n x 32 c] (+)= G^T[128 n x 16 px] * A_tap[16 px x 32 c]; both operands MN-major (bits 15, 16)
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(WT_CT >> 3) << 17) |
+    // D[128 n x 96 (kx, c)] (+)= G^T[128 n x 16 px] * [A_(ky,0) | A_(ky,1) | A_(ky,2)][16 px x 96]; both operands MN-major
+    // (idesc bits 15, 16).  The three kx taps of a ky row are three 32-channel atoms of ONE B operand: in the halo tile
+    // they are the same rows shifted by one pixel (LBO = 64 B: overlapping atoms), in the per-tap layout 4 KB apart.
+    // One thread issues everything, at ~5 cycles per dependent instruction, so the per-MMA descriptor words are
+    // precomputed: 12 MMAs per stage, two adds each.
+    constexpr int NW = 3 * WT_CT;                          // 96 accumulator columns per MMA
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(NW >> 3) << 17) |
                            ((uint32_t)(WT_NT >> 4) << 24);
+    const int pitch = p.wb + 2;                            // pixels per row of the halo tile
+    uint32_t a_off[WT_BK / 16][3];                         // 16-byte units from the stage base
+#pragma unroll
+    for (int kk = 0; kk < WT_BK / 16; ++kk) {
+      const int hrow = (kk * 16) / p.wb, wcol = (kk * 16) - hrow * p.wb;   // the 16 pixels of K step kk: row hrow, from wcol
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+        a_off[kk][ky] = (uint32_t)(WT_G_BYTES + (p.halo ? ((hrow + ky) * pitch + wcol) * WT_ROW_BYTES
+                                                         : ky * 3 * WT_A_BYTES + kk * 1024)) >> 4;
+    }
+    const uint64_t gdesc0 = make_smem_desc_mn(smem_base, WT_G_BYTES / 2, 1024, 2);
+    const uint64_t adesc0 = make_smem_desc_mn(smem_base, p.halo ? WT_ROW_BYTES : WT_A_BYTES, 512, 4);
+    const uint32_t stage_units = (uint32_t)p.stage_bytes >> 4;
     int stage = 0;
     uint32_t phase = 0;
     uint32_t accumulate = 0;
     for (int ks = ks_begin; ks < ks_end; ++ks) {
       mbar_wait(smem_u32(&bar_full[stage]), phase);
       tc_fence_after();
-      const uint32_t sbase = smem_base + (uint32_t)(stage * p.stage_bytes);
+      const uint32_t soff = (uint32_t)stage * stage_units;
       if (elect_one()) {
-        const int pitch = p.wb + 2;                       // pixels per row of the halo tile
 #pragma unroll
         for (int kk = 0; kk < WT_BK / 16; ++kk) {
-          // G: rows of 128 B (64 n), 16 pixels = 2 KB per K step; the second 64-n atom starts WT_G_BYTES/2 later
-          const uint64_t gdesc = make_smem_desc_mn(sbase + kk * 2048, WT_G_BYTES / 2, 1024, 2);
-          // the 16 pixels of this K step lie in image row h of the block, starting at column w
-          const int hrow = (kk * 16) / p.wb, wcol = (kk * 16) - hrow * p.wb;
+          const uint64_t gdesc = gdesc0 + soff + (uint32_t)(kk * (2048 >> 4));   // 16 pixels of 128-byte rows per K step
 #pragma unroll
-          for (int tap = 0; tap < WT_TAPS; ++tap) {
-            // A tap: rows of 64 B (32 c), one atom along N.  Halo mode: the tap is a row offset into the one halo tile
-            const uint32_t a_addr = p.halo
-                ? sbase + WT_G_BYTES + (uint32_t)(((hrow + tap / 3) * pitch + wcol + tap % 3) * WT_ROW_BYTES)
-                : sbase + WT_G_BYTES + tap * WT_A_BYTES + kk * 1024;
-            const uint64_t adesc = make_smem_desc_mn(a_addr, 16, 512, 4);
-            umma_bf16(tmem_base + (uint32_t)(tap * WT_CT), gdesc, adesc, idesc, (kk == 0) ? accumulate : 1u);
-          }
+          for (int ky = 0; ky < 3; ++ky)
+            umma_bf16(tmem_base + (uint32_t)(ky * NW), gdesc, adesc0 + soff + a_off[kk][ky], idesc,
+                      (kk == 0) ? accumulate : 1u);
         }
         umma_commit(smem_u32(&bar_empty[stage]));
       }

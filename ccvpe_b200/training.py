@@ -386,7 +386,7 @@ class GraphedTrainStep:
         loss = step(grd, sat, gt, gwo, gor)                                             # copies inputs in, replays
 
     `fn` is run `warmup` times eagerly on a side stream before capture (so every lazily-built cache, cuDNN plan and
-    optimizer state exists), which means `warmup + 1` real optimizer steps happen during construction."""
+    optimizer state exists): `warmup` real optimizer steps happen during construction; the capture itself executes nothing."""
 
     def __init__(self, fn, example_inputs: Sequence[torch.Tensor], warmup: int = 3):
         self.static_in = [t.clone() for t in example_inputs]
