@@ -122,6 +122,12 @@ def main(args):
     model = models.CVM_VIGOR("cuda", True)
     fill_deterministic(model.state_dict(), seed=0)          # identical replicas on every rank
     model = model.to(dev).set_precision(args.precision).train()
+    # PyTorch-side tuning of the (PyTorch) encoders: cuDNN autotuning, and optionally channels-last convolutions
+    torch.backends.cudnn.benchmark = True
+    enc_cl = os.environ.get("CCVPE_TRAIN_CL", "0") == "1"
+    if enc_cl:
+        model.grd_efficientnet.to(memory_format=torch.channels_last)
+        model.sat_efficientnet.to(memory_format=torch.channels_last)
     if args.backend == "simt":
         model.set_backend(cabi.BACKEND_SIMT)
     reducer = GradientAllReducer(model)
@@ -130,6 +136,9 @@ def main(args):
                            capturable=use_graph)
     host = [t.pin_memory() for t in _synthetic_batch(Bsz, 200 + rank)]
     resident = [t.to(dev) for t in host]
+    if enc_cl:
+        resident[0] = resident[0].contiguous(memory_format=torch.channels_last)
+        resident[1] = resident[1].contiguous(memory_format=torch.channels_last)
 
     def eager_step(grd, sat, gt, gwo, gor):
         reducer.zero_grad()
@@ -320,6 +329,7 @@ def main(args):
             "config": {"workload": DESC, "workload_key": "train", "batch_per_gpu": Bsz, "global_batch": world * Bsz,
                        "parallelism": "data-parallel x%d (bucketed NCCL gradient all-reduce)" % world,
                        "backend": args.backend, "optimizer": "Adam(lr=1e-4, betas=(0.9, 0.999)), fused",
+                       "encoder_memory_format": "channels_last" if enc_cl else "contiguous", "cudnn_benchmark": True,
                        "cuda_graph": bool(use_graph), **({"cuda_graph_note": graph_note} if graph_note else {}),
                        "precision_note": "fp32 master weights and optimizer; encoders fp32 autograd; decoder activations and GEMM "
                                          "operands in the stated dtype with fp32 accumulation",
