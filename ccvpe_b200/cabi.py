@@ -28,7 +28,7 @@ EXPORTED_SYMBOLS = (
     "ccvpe_ingest_u8", "ccvpe_stem_conv_silu_u8_nhwc",
     # training step (config 5)
     "ccvpe_wgrad_workspace_elems", "ccvpe_wgrad", "ccvpe_wgrad_plan", "ccvpe_colsum_workspace_elems", "ccvpe_colsum",
-    "ccvpe_relu_bwd", "ccvpe_planar_to_cl", "ccvpe_cl_to_planar", "ccvpe_ori_normalize_bwd",
+    "ccvpe_relu_bwd", "ccvpe_scale_rows", "ccvpe_planar_to_cl", "ccvpe_cl_to_planar", "ccvpe_ori_normalize_bwd",
     "ccvpe_match_bwd_scratch_elems", "ccvpe_match_level_bwd", "ccvpe_loss_workspace_elems", "ccvpe_infonce_loss",
     "ccvpe_cross_entropy_loss", "ccvpe_orientation_loss", "ccvpe_grd_descriptors_bwd",
 )
@@ -164,6 +164,8 @@ def load() -> C.CDLL:
                                  C.c_void_p, C.c_void_p, C.c_void_p]
     lib.ccvpe_relu_bwd.restype = C.c_int
     lib.ccvpe_relu_bwd.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p]
+    lib.ccvpe_scale_rows.restype = C.c_int
+    lib.ccvpe_scale_rows.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
     lib.ccvpe_planar_to_cl.restype = C.c_int
     lib.ccvpe_planar_to_cl.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_void_p]
     lib.ccvpe_cl_to_planar.restype = C.c_int
@@ -537,6 +539,17 @@ def relu_bwd(dh: torch.Tensor, h: torch.Tensor):
     if dh.dtype != h.dtype or dh.shape != h.shape or not dh.is_contiguous() or not h.is_contiguous():
         raise CcvpeError("relu_bwd: dh and h must be contiguous tensors of the same shape and dtype")
     _check(load().ccvpe_relu_bwd(_ptr(dh), _ptr(h), dtype_code(dh.dtype), dh.numel(), _stream()), "ccvpe_relu_bwd")
+
+
+def scale_rows(x: torch.Tensor, scale: torch.Tensor, y: torch.Tensor):
+    """y[..., :] = x[..., :] * scale[...] for contiguous channels-last x / y [.., C] and fp32 scale over the leading dims."""
+    _require_cuda(x, scale, y)
+    Cc = x.shape[-1]
+    if not x.is_contiguous() or not y.is_contiguous() or y.shape != x.shape or scale.dtype != torch.float32 or \
+            scale.numel() * Cc != x.numel():
+        raise CcvpeError("scale_rows: x, y contiguous [.., C] of the same shape; scale fp32 with one entry per row")
+    _check(load().ccvpe_scale_rows(_ptr(x), dtype_code(x.dtype), _ptr(scale), _ptr(y), x.numel() // Cc, Cc, _stream()),
+           "ccvpe_scale_rows")
 
 
 def planar_to_cl(src: torch.Tensor, dst: torch.Tensor):

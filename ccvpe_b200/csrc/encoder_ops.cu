@@ -173,9 +173,11 @@ dwconv_bias_silu_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_sb, int64
   // A block owns one image (blockIdx.y), one chunk of CG V-channel groups (blockIdx.z) and a range of strips
   // (blockIdx.x): wide low-resolution layers are split over channels so that every block still has a whole image's worth
   // of pixels to amortise its weight load over.
-  extern __shared__ __align__(16) unsigned long long s_sum[];   // [CG*V] fixed-point channel sums, then the chunk's fp32 weights [K*K][CG*V]
+  // [lanes][CG*V] per-thread fp32 channel sums (folded in lane order at the end: no shared-memory atomics), then the
+  // chunk's fp32 weights [K*K][CG*V]
+  extern __shared__ __align__(16) float s_part[];
   const int CC = CG * V;                             // channels of a full chunk
-  float* s_w = reinterpret_cast<float*>(s_sum + CC);
+  float* s_w = s_part + (blockDim.x / CG) * CC;
   const int G = C / V;
   const int g0 = blockIdx.z * CG;                    // first channel group of this chunk
   const int gn = min(CG, G - g0);                    // groups actually present in it
@@ -211,7 +213,6 @@ dwconv_bias_silu_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_sb, int64
   const int n_strips = Ho * strips_row;
   const int s_lo = blockIdx.x * strips_per_block;
   const int s_hi = min(n_strips, s_lo + strips_per_block);
-  for (int c = threadIdx.x; c < CC; c += blockDim.x) s_sum[c] = 0ull;
   __syncthreads();
   float csum[V];
 #pragma unroll
@@ -289,13 +290,18 @@ dwconv_bias_silu_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_sb, int64
     }
   }
   if (chan_sum) {
-    if (active) {
+    if (pl < lanes) {
 #pragma unroll
-      for (int j = 0; j < V; ++j) atomicAdd(&s_sum[cl * V + j], se_fixed(csum[j]));
+      for (int j = 0; j < V; ++j) s_part[pl * CC + cl * V + j] = active ? csum[j] : 0.f;
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < gn * V; c += blockDim.x)
-      atomicAdd(reinterpret_cast<unsigned long long*>(chan_sum) + (int64_t)b * C + g0 * V + c, s_sum[c]);
+    // one thread per channel folds the lanes in a fixed order (deterministic fp32), then ONE fixed-point atomic per
+    // (block, channel) into the order-independent 64-bit accumulator
+    for (int c = threadIdx.x; c < gn * V; c += blockDim.x) {
+      float tot = 0.f;
+      for (int l = 0; l < lanes; ++l) tot += s_part[l * CC + c];
+      atomicAdd(reinterpret_cast<unsigned long long*>(chan_sum) + (int64_t)b * C + g0 * V + c, se_fixed(tot));
+    }
   }
 }
 
@@ -663,7 +669,7 @@ extern "C" int ccvpe_dwconv_bias_silu_nhwc(const void* x, int64_t x_sb, int64_t 
   blocks_x = (int)((n_strips + spb - 1) / spb);
   CCVPE_REQUIRE(chunks <= 65535 && B <= 65535, "ccvpe_dwconv_bias_silu_nhwc: grid too large");
   const dim3 grid(blocks_x, B, chunks);
-  const size_t sm = (size_t)CG * V * (sizeof(unsigned long long) + sizeof(float) * K * K);
+  const size_t sm = (size_t)CG * V * sizeof(float) * (lanes + K * K);
   CCVPE_REQUIRE(sm <= 96 * 1024, "ccvpe_dwconv_bias_silu_nhwc: K*K*C too large for shared memory");
   static thread_local uint64_t attr_set = 0;
   if (first_use_on_device(attr_set)) {

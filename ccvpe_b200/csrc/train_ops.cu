@@ -464,6 +464,19 @@ __global__ void ori_normalize_bwd_kernel(const TV* __restrict__ v, int ldv, cons
   }
 }
 
+// y[m, :] = x[m, :] * scale[m]      (the F.normalize'd map as an explicit tensor: the G operand of the tensor-core weight
+// gradient of the transposed convs; 4 elements per thread)
+template <typename T>
+__global__ void scale_rows_kernel(const T* __restrict__ x, const float* __restrict__ scale, T* __restrict__ y, int C4,
+                                  int64_t n4) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = load4(x + i * 4);
+    const float s = __ldg(scale + i / C4);
+    v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+    store4(y + i * 4, v);
+  }
+}
+
 inline int ew_blocks(int64_t n) {
   int64_t b = (n + 255) / 256;
   if (b > 16LL * sm_count()) b = 16LL * sm_count();
@@ -481,6 +494,19 @@ extern "C" int ccvpe_relu_bwd(void* dh, const void* h, int dtype, int64_t n, voi
     relu_bwd_kernel<__nv_bfloat16><<<ew_blocks(n / 4), 256, 0, st>>>((__nv_bfloat16*)dh, (const __nv_bfloat16*)h, n / 4);
   else return fail(CCVPE_ERR_BAD_ARGUMENT, "ccvpe_relu_bwd: bad dtype");
   CCVPE_LAUNCH_CHECK("relu_bwd_kernel");
+  return CCVPE_OK;
+}
+
+extern "C" int ccvpe_scale_rows(const void* x, int dtype, const float* scale, void* y, int64_t M, int C, void* stream) {
+  using namespace ccvpe;
+  CCVPE_REQUIRE(x && scale && y && M > 0 && C > 0 && C % 4 == 0 && aligned16(x) && aligned16(y), "ccvpe_scale_rows: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n4 = M * C / 4;
+  if (dtype == CCVPE_F32) scale_rows_kernel<float><<<ew_blocks(n4), 256, 0, st>>>((const float*)x, scale, (float*)y, C / 4, n4);
+  else if (dtype == CCVPE_BF16)
+    scale_rows_kernel<__nv_bfloat16><<<ew_blocks(n4), 256, 0, st>>>((const __nv_bfloat16*)x, scale, (__nv_bfloat16*)y, C / 4, n4);
+  else return fail(CCVPE_ERR_BAD_ARGUMENT, "ccvpe_scale_rows: bad dtype");
+  CCVPE_LAUNCH_CHECK("scale_rows_kernel");
   return CCVPE_OK;
 }
 

@@ -43,6 +43,7 @@ struct WgradTcParams {
   int c_tiles0;
   int stages;
   int halo, stage_bytes, a_tx;         // halo mode: one (hb+2) x (wb+2) A box per stage; bytes TMA delivers for it
+  int k2s2, taps;                      // k2 s2 layers: 4 taps gathered through a 5-D map [c][dw][j][dh][(b, i)]
   float* dst;
 };
 
@@ -109,6 +110,8 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tcgen05_kernel(const __gr
     uint32_t phase = 0;
     const int per_img = p.tiles_w * p.tiles_h;
     for (int ks = ks_begin; ks < ks_end; ++ks) {
+      // 3x3: (image, row block, column block) of the layer;  k2 s2: ((image, output row) block, output column block) --
+      // p.H is then the number of merged (image, row) lines and one "image" covers them all
       const int b = ks / per_img, r = ks - b * per_img;
       const int th = r / p.tiles_w, tw = r - th * p.tiles_w;
       const int h0 = th * p.hb, w0 = tw * p.wb;
@@ -117,10 +120,14 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tcgen05_kernel(const __gr
       if (elect_one()) {
         const uint32_t full = smem_u32(&bar_full[stage]);
         const uint32_t dst = smem_base + (uint32_t)(stage * p.stage_bytes);
-        mbar_arrive_expect_tx(full, (uint32_t)(WT_G_BYTES + (p.halo ? p.a_tx : WT_TAPS * WT_A_BYTES)));
+        mbar_arrive_expect_tx(full, (uint32_t)(WT_G_BYTES + (p.halo ? p.a_tx : p.taps * WT_A_BYTES)));
         tma_load_2d(dst, &p.tm_g, full, n0, m0);
         tma_load_2d(dst + WT_G_BYTES / 2, &p.tm_g, full, n1, m0);
-        if (p.halo) {
+        if (p.k2s2) {
+#pragma unroll
+          for (int tap = 0; tap < 4; ++tap)      // tap = dh * 2 + dw
+            tma_load_5d(dst + WT_G_BYTES + tap * WT_A_BYTES, tma, full, c_start, tap & 1, w0, tap >> 1, h0);
+        } else if (p.halo) {
           tma_load_4d(dst + WT_G_BYTES, tma, full, c_start, w0 - 1, h0 - 1, b);
         } else {
 #pragma unroll
@@ -156,6 +163,9 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tcgen05_kernel(const __gr
     }
     const uint64_t gdesc0 = make_smem_desc_mn(smem_base, WT_G_BYTES / 2, 1024, 2);
     const uint64_t adesc0 = make_smem_desc_mn(smem_base, p.halo ? WT_ROW_BYTES : WT_A_BYTES, 512, 4);
+    // k2 s2: the two dw taps of a dh row are two atoms (4 KB apart) of one N = 64 MMA
+    const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(2 * WT_CT >> 3) << 17) |
+                            ((uint32_t)(WT_NT >> 4) << 24);
     const uint32_t stage_units = (uint32_t)p.stage_bytes >> 4;
     int stage = 0;
     uint32_t phase = 0;
@@ -165,13 +175,25 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tcgen05_kernel(const __gr
       tc_fence_after();
       const uint32_t soff = (uint32_t)stage * stage_units;
       if (elect_one()) {
+        if (p.k2s2) {
 #pragma unroll
-        for (int kk = 0; kk < WT_BK / 16; ++kk) {
-          const uint64_t gdesc = gdesc0 + soff + (uint32_t)(kk * (2048 >> 4));   // 16 pixels of 128-byte rows per K step
+          for (int kk = 0; kk < WT_BK / 16; ++kk) {
+            const uint64_t gdesc = gdesc0 + soff + (uint32_t)(kk * (2048 >> 4));
 #pragma unroll
-          for (int ky = 0; ky < 3; ++ky)
-            umma_bf16(tmem_base + (uint32_t)(ky * NW), gdesc, adesc0 + soff + a_off[kk][ky], idesc,
-                      (kk == 0) ? accumulate : 1u);
+            for (int dh = 0; dh < 2; ++dh)
+              umma_bf16(tmem_base + (uint32_t)(dh * 2 * WT_CT), gdesc,
+                        adesc0 + soff + (uint32_t)((WT_G_BYTES + dh * 2 * WT_A_BYTES + kk * 1024) >> 4), idesc2,
+                        (kk == 0) ? accumulate : 1u);
+          }
+        } else {
+#pragma unroll
+          for (int kk = 0; kk < WT_BK / 16; ++kk) {
+            const uint64_t gdesc = gdesc0 + soff + (uint32_t)(kk * (2048 >> 4));   // 16 pixels of 128-byte rows per K step
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+              umma_bf16(tmem_base + (uint32_t)(ky * NW), gdesc, adesc0 + soff + a_off[kk][ky], idesc,
+                        (kk == 0) ? accumulate : 1u);
+          }
         }
         umma_commit(smem_u32(&bar_empty[stage]));
       }
@@ -191,7 +213,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tcgen05_kernel(const __gr
     mbar_wait(smem_u32(&bar_acc), 0);
     tc_fence_after();
     const bool n_ok = n < p.N && (lg * 32 + lane < 64 || n0 + 64 < p.N);     // (rows 64.. duplicate rows 0.. on a short tile)
-    for (int tap = 0; tap < WT_TAPS; ++tap) {
+    for (int tap = 0; tap < p.taps; ++tap) {
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(tap * WT_CT), v);
       tmem_ld_wait();
@@ -217,16 +239,23 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tcgen05_kernel(const __gr
 
 int launch_reduce_splits(const float* ws, float* out, int64_t n, int splits, cudaStream_t st);   // train_ops.cu
 
+// (3x3 stride-1 pad-1 convs, and k2 s2 convs -- the weight gradients of the transposed convs and of the aerial cell conv)
 struct WgradTcPlan {
+  bool k2s2;
   int wb, hb, tiles_w, tiles_h, ksteps, c_tiles0, c_tiles1, n_tiles, splits, ksteps_per_split;
 };
 
 static bool plan_wgrad_tc(const ccvpe_wgrad_desc& d, WgradTcPlan& pl) {
-  if (d.dtype != CCVPE_BF16 || d.kh != 3 || d.kw != 3 || d.stride != 1 || d.pad != 1 || d.g_row_scale) return false;
-  if (d.Hin != d.Hout || d.Win != d.Wout) return false;
+  if (d.dtype != CCVPE_BF16 || d.g_row_scale) return false;
+  const bool conv3 = d.kh == 3 && d.kw == 3 && d.stride == 1 && d.pad == 1 && d.Hin == d.Hout && d.Win == d.Wout;
+  const bool k2s2 = d.kh == 2 && d.kw == 2 && d.stride == 2 && d.pad == 0 && d.Hin == 2 * d.Hout && d.Win == 2 * d.Wout &&
+                    d.c1 == 0;
+  if (!conv3 && !k2s2) return false;
   if (d.c0 % 8 || d.c1 % 8 || d.ld0 % 8 || (d.c1 && d.ld1 % 8) || d.N % 8 || d.ldg % 8) return false;
   if (!aligned16(d.a0) || (d.c1 && !aligned16(d.a1)) || !aligned16(d.g)) return false;
-  const int W = d.Win, H = d.Hin;
+  pl.k2s2 = k2s2;
+  // pixel blocks of 64: 3x3 -> (wb x hb) pixels of one image; k2 s2 -> wb output columns x hb merged (image, row) lines
+  const int W = d.Wout, H = k2s2 ? d.Hout * d.B : d.Hout;
   if (W >= WT_BK) {
     if (W % WT_BK) return false;
     pl.wb = WT_BK;
@@ -238,7 +267,7 @@ static bool plan_wgrad_tc(const ccvpe_wgrad_desc& d, WgradTcPlan& pl) {
   }
   pl.tiles_w = W / pl.wb;
   pl.tiles_h = H / pl.hb;
-  pl.ksteps = d.B * pl.tiles_w * pl.tiles_h;
+  pl.ksteps = (k2s2 ? 1 : d.B) * pl.tiles_w * pl.tiles_h;
   pl.c_tiles0 = (d.c0 + WT_CT - 1) / WT_CT;
   pl.c_tiles1 = (d.c1 + WT_CT - 1) / WT_CT;
   pl.n_tiles = (d.N + WT_NT - 1) / WT_NT;
@@ -260,7 +289,7 @@ int wgrad_tcgen05_supported(const ccvpe_wgrad_desc& d) {
 int64_t wgrad_tcgen05_workspace_elems(const ccvpe_wgrad_desc& d) {
   WgradTcPlan pl;
   if (!plan_wgrad_tc(d, pl)) return 0;
-  return pl.splits > 1 ? (int64_t)pl.splits * 9 * (d.c0 + d.c1) * d.N : 0;
+  return pl.splits > 1 ? (int64_t)pl.splits * d.kh * d.kw * (d.c0 + d.c1) * d.N : 0;
 }
 
 int wgrad_tcgen05(const ccvpe_wgrad_desc& d, cudaStream_t st) {
@@ -268,15 +297,18 @@ int wgrad_tcgen05(const ccvpe_wgrad_desc& d, cudaStream_t st) {
   if (!plan_wgrad_tc(d, pl)) return fail(CCVPE_ERR_UNSUPPORTED, "wgrad_tcgen05: unsupported shape");
   static thread_local WgradTcParams p;
   memset(&p, 0, sizeof(p));
-  p.c0 = d.c0; p.c1 = d.c1; p.ctot = d.c0 + d.c1; p.N = d.N; p.Q = 9 * p.ctot;
-  p.W = d.Win; p.H = d.Hin; p.B = d.B; p.wb = pl.wb; p.hb = pl.hb; p.tiles_w = pl.tiles_w; p.tiles_h = pl.tiles_h;
+  p.k2s2 = pl.k2s2 ? 1 : 0;
+  p.taps = pl.k2s2 ? 4 : WT_TAPS;
+  p.c0 = d.c0; p.c1 = d.c1; p.ctot = d.c0 + d.c1; p.N = d.N; p.Q = p.taps * p.ctot;
+  p.W = d.Wout; p.H = pl.k2s2 ? d.Hout * d.B : d.Hout; p.B = pl.k2s2 ? 1 : d.B;
+  p.wb = pl.wb; p.hb = pl.hb; p.tiles_w = pl.tiles_w; p.tiles_h = pl.tiles_h;
   p.ksteps_total = pl.ksteps; p.ksteps_per_split = pl.ksteps_per_split;
   p.c_tiles0 = pl.c_tiles0;
   static const bool halo_off = getenv("CCVPE_WGRAD_HALO") && atoi(getenv("CCVPE_WGRAD_HALO")) == 0;
-  p.halo = halo_off ? 0 : 1;
+  p.halo = (halo_off || pl.k2s2) ? 0 : 1;
   p.a_tx = (pl.wb + 2) * (pl.hb + 2) * WT_ROW_BYTES;
-  p.stage_bytes = p.halo ? WT_G_BYTES + (p.a_tx + 1023) / 1024 * 1024 : WT_STAGE_BYTES;
-  p.stages = p.halo ? WT_MAX_STAGES_HALO : WT_MAX_STAGES;
+  p.stage_bytes = p.halo ? WT_G_BYTES + (p.a_tx + 1023) / 1024 * 1024 : WT_G_BYTES + p.taps * WT_A_BYTES;
+  p.stages = (p.halo || pl.k2s2) ? WT_MAX_STAGES_HALO : WT_MAX_STAGES;
   while (p.stages * p.stage_bytes > 200 * 1024) --p.stages;
   const int64_t n_out = (int64_t)p.Q * d.N;
   if (pl.splits > 1) {
@@ -287,7 +319,14 @@ int wgrad_tcgen05(const ccvpe_wgrad_desc& d, cudaStream_t st) {
     p.dst = d.out;
   }
   int rc;
-  for (int s = 0; s < (d.c1 ? 2 : 1); ++s) {
+  if (pl.k2s2) {
+    // [c][dw = 2][j = Wout][dh = 2][(b, i) = B * Hout]: output pixel ((b, i), j), tap (dh, dw) reads input pixel (2i + dh, 2j + dw)
+    uint64_t dims[5] = {(uint64_t)d.c0, 2, (uint64_t)d.Wout, 2, (uint64_t)d.Hout * d.B};
+    uint64_t str[4] = {(uint64_t)d.ld0 * 2, 2ull * d.ld0 * 2, (uint64_t)d.Win * d.ld0 * 2, 2ull * d.Win * d.ld0 * 2};
+    uint32_t box[5] = {WT_CT, 1, (uint32_t)pl.wb, 1, (uint32_t)pl.hb};
+    if ((rc = encode_map(&p.tm_a0, d.a0, 5, dims, str, box, 32)) != CCVPE_OK) return rc;
+  }
+  for (int s = 0; s < ((d.c1 ? 2 : 1) * (pl.k2s2 ? 0 : 1)); ++s) {
     const void* base = s ? d.a1 : d.a0;
     const int c = s ? d.c1 : d.c0, ld = s ? d.ld1 : d.ld0;
     uint64_t dims[4] = {(uint64_t)c, (uint64_t)d.Win, (uint64_t)d.Hin, (uint64_t)d.B};

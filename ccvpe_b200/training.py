@@ -167,6 +167,15 @@ class PostEncoderTrainer:
         H, W = H2 // 2, W2 // 2
         geom = (B, H2, W2, H, W, 2, 2, 0)
         pw = torch.empty_like(self.p._params()[pname + ".weight"], dtype=torch.float32)      # [Cin, Cout, 2, 2]
+        if row_scale is not None and dtype == torch.bfloat16 and self.p.backend != cabi.BACKEND_SIMT:
+            # tensor-core weight gradient: its G operand is the normalised map itself (one small HBM-bound pass)
+            scaled = []
+            for src, n_real, row0 in srcs:
+                xh = torch.empty_like(src)
+                self.p._op("scale_rows_kernel:scale_rows|" + name, src.numel(), 2.0 * src.numel() * src.element_size(),
+                           lambda s_=src, o_=xh: cabi.scale_rows(s_, row_scale, o_))
+                scaled.append((xh, n_real, row0))
+            srcs, row_scale = scaled, None
         for src, n_real, row0 in srcs:
             ld = src.shape[-1]
             dw = self._wgrad("wgrad|" + name, d_up, cout, None, 0, geom, src.view(B * H * W, ld), ld, row_scale, dtype)

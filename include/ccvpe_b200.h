@@ -274,6 +274,9 @@ int64_t ccvpe_colsum_workspace_elems(int64_t n_pix, int C, int s);
 int ccvpe_colsum(const void* x, int dtype, int B, int H, int W, int C, int ld, const float* w, int s, float* out,
                  float* workspace, void* stream);
 
+/* y[m, :] = x[m, :] * scale[m] over a channels-last matrix [M, C] (C % 4 == 0): the L2-normalised aerial map as an explicit
+ * tensor (models.py:205), the G operand of the tensor-core weight gradient of the transposed convs. */
+int ccvpe_scale_rows(const void* x, int dtype, const float* scale, void* y, int64_t M, int C, void* stream);
 /* ReLU backward in place: dh[i] = h[i] > 0 ? dh[i] : 0 (models.py:45).  n % 4 == 0. */
 int ccvpe_relu_bwd(void* dh, const void* h, int dtype, int64_t n, void* stream);
 /* planar fp32 [B, N, HW] -> channels-last (dtype) [B, HW, ld], channels >= N zero filled (incoming d logits) */

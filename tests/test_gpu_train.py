@@ -129,6 +129,33 @@ def test_wgrad_deconv_and_colsum(cuda_device, B, cin, cout, H, with_scale):
     assert rel_err(bsum[0], bias.grad) < TOL
 
 
+@pytest.mark.parametrize("B,cin,cout,H,W", [(2, 64, 32, 8, 8), (3, 1280, 1024, 8, 8), (1, 40, 16, 64, 64),
+                                             (2, 80, 40, 32, 128), (2, 1280, 72, 8, 8)])
+def test_wgrad_k2s2_tcgen05(cuda_device, B, cin, cout, H, W):
+    """Weight gradient of a k2 s2 transposed conv on tensor cores: A = dY gathered with stride 2 through a 5-D tensor map
+    (four taps), G = the layer input; vs autograd on the same bf16-rounded inputs (1e-3 of max|ref|)."""
+    g = _gen(40)
+    dev = cuda_device
+    dt = torch.bfloat16
+    x = torch.randn(B, cin, H, W, generator=g).to(dt).float()
+    dy = torch.randn(B, cout, 2 * H, 2 * W, generator=g).to(dt).float()
+    w = torch.zeros(cin, cout, 2, 2, requires_grad=True)
+    (F.conv_transpose2d(x, w, stride=2) * dy).sum().backward()
+    out = _wgrad_call(_cl(dy, dt, dev), None, (B, 2 * H, 2 * W, H, W, 2, 2, 0), _cl(x, dt, dev).view(B * H * W, cin), cin, None,
+                      backend=cabi.BACKEND_TCGEN05)
+    got = out.view(2, 2, cout, cin).permute(3, 2, 0, 1)
+    assert rel_err(got, w.grad) < 1e-3, rel_err(got, w.grad)
+
+
+def test_scale_rows(cuda_device):
+    g = _gen(44)
+    x = torch.randn(3, 5, 7, 40, generator=g).to(cuda_device, torch.bfloat16)
+    sc = torch.rand(3, 5, 7, generator=g).to(cuda_device)
+    y = torch.empty_like(x)
+    cabi.scale_rows(x, sc, y)
+    assert torch.equal(y, (x.float() * sc[..., None]).to(torch.bfloat16))
+
+
 def test_wgrad_cell(cuda_device):
     """Linear(5120 -> D) over 2x2 cells == conv k2 s2: dW vs autograd of the oracle's cell loop."""
     g = _gen(33)
