@@ -292,24 +292,38 @@ colsum_partial_kernel(const T* __restrict__ x, int64_t n_pix, int H, int W, int 
 #pragma unroll
   for (int k = 0; k < 4; ++k) acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.f;
   if (pl < lanes) {
-    for (int64_t p = p_lo + pl; p < p_hi; p += lanes) {
-      float4 v = load4(x + p * ld + cg * 4);
-      int bucket = 0;
-      float wt = 1.f;
-      if (s == 2 || w) {
-        const int64_t b = p / ((int64_t)H * W);
-        const int r = (int)(p - b * H * W);
-        const int y = r / W, xx = r - y * W;
-        if (s == 2) bucket = (y & 1) * 2 + (xx & 1);
-        if (w) wt = __ldg(w + (b * (H / s) + y / s) * (W / s) + xx / s);
+    constexpr int U = 4;                               // independent loads in flight per thread (the loop is latency bound)
+    for (int64_t p0 = p_lo + pl; p0 < p_hi; p0 += (int64_t)lanes * U) {
+      float4 v[U];
+      float wt[U];
+      int bucket[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t p = p0 + (int64_t)u * lanes;
+        bucket[u] = -1;
+        wt[u] = 1.f;
+        if (p < p_hi) {
+          v[u] = load4(x + p * ld + cg * 4);
+          bucket[u] = 0;
+          if (s == 2 || w) {
+            const int64_t b = p / ((int64_t)H * W);
+            const int r = (int)(p - b * H * W);
+            const int y = r / W, xx = r - y * W;
+            if (s == 2) bucket[u] = (y & 1) * 2 + (xx & 1);
+            if (w) wt[u] = __ldg(w + (b * (H / s) + y / s) * (W / s) + xx / s);
+          }
+        }
       }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (k == bucket) {
-          acc[k][0] = fmaf(wt, v.x, acc[k][0]);
-          acc[k][1] = fmaf(wt, v.y, acc[k][1]);
-          acc[k][2] = fmaf(wt, v.z, acc[k][2]);
-          acc[k][3] = fmaf(wt, v.w, acc[k][3]);
+      for (int u = 0; u < U; ++u) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (k == bucket[u]) {
+            acc[k][0] = fmaf(wt[u], v[u].x, acc[k][0]);
+            acc[k][1] = fmaf(wt[u], v[u].y, acc[k][1]);
+            acc[k][2] = fmaf(wt[u], v[u].z, acc[k][2]);
+            acc[k][3] = fmaf(wt[u], v[u].w, acc[k][3]);
+          }
         }
       }
     }

@@ -44,6 +44,57 @@ def _nk(per_tap_rows: torch.Tensor, splits: Sequence[int]) -> torch.Tensor:
     return out.contiguous()
 
 
+_SIDE_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
+
+
+class Fork:
+    """Runs a block of launches on a side stream that forks from / joins into the current stream, so that two independent
+    kernel sequences (localisation vs orientation decoder, ground vs aerial encoder) execute concurrently.  Matters at small
+    batches, where single kernels do not fill the 148 SMs; inside a CUDA-graph capture the fork / join become graph edges.
+
+        fork = Fork(device, enabled)
+        with fork:            # launches in here go to the side stream
+            ...
+        ...                   # launches on the main stream, concurrent with the block above
+        fork.join(t1, t2)     # main waits for the side stream; tensors produced there are handed over to main
+
+    Tensors allocated in the block belong to the side stream's pool: pass the ones that outlive the call to `join`
+    (outside graph capture they are `record_stream`-ed on the main stream; main-stream tensors read in the block are kept
+    alive by the caller until `join`)."""
+
+    def __init__(self, device, enabled: bool = True):
+        self.enabled = bool(enabled)
+        self.device = device
+        if self.enabled:
+            idx = device.index if device.index is not None else torch.cuda.current_device()
+            if idx not in _SIDE_STREAMS:
+                _SIDE_STREAMS[idx] = torch.cuda.Stream(device=device)
+            self.side = _SIDE_STREAMS[idx]
+            self.main = torch.cuda.current_stream(device)
+            self._ctx = None
+
+    def __enter__(self):
+        if self.enabled:
+            self.side.wait_stream(self.main)
+            self._ctx = torch.cuda.stream(self.side)
+            self._ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.enabled:
+            self._ctx.__exit__(*exc)
+        return False
+
+    def join(self, *tensors):
+        if not self.enabled:
+            return
+        self.main.wait_stream(self.side)
+        if not torch.cuda.is_current_stream_capturing():
+            for t in tensors:
+                if t is not None:
+                    t.record_stream(self.main)
+
+
 class OpTimer:
     """Optional per-operator CUDA-event timer (bench.py): events are recorded on torch's current stream, which is the
     stream every kernel of the pipeline is launched on.  `flops` / `nbytes` are the ALGORITHMIC work of the call."""
@@ -77,6 +128,7 @@ class PostEncoderPipeline:
         self.spec = spec
         self.ori_noise = ori_noise
         self.backend = cabi.BACKEND_AUTO
+        self.concurrent = True           # run independent branches (orientation / localisation decoder) on forked streams
         self._cache: Dict[torch.dtype, dict] = {}
         self._sig = None
         self.timer: Optional[OpTimer] = None
@@ -258,6 +310,39 @@ class PostEncoderPipeline:
         if save is not None:
             save.update(dtype=dtype, B=B, grd_feat=grd_feat, fs=fs, skips=skips, g=g, loc=[], ori=[])
 
+        # The orientation decoder only needs level 1 (score volume + normalised map) and the skips: it runs on a forked side
+        # stream, concurrently with levels 2..6 of the localisation decoder (per-operator timing runs them back to back)
+        fork = Fork(dev, enabled=self.timer is None and self.concurrent)
+
+        def orientation_decoder():
+            # a11 -- orientation decoder (no matching inside; input = [scores_1, normalize(x_1)], models.py:323)
+            o = None
+            for l in range(6):
+                ow = w["ori"][l]
+                nm = "ori%d" % (6 - l)
+                o_in = o
+                if l == 0:
+                    o = self._deconv(ow["deconv"], scores_cl, SCORES_CL_PAD, xhat, D, dtype, name=nm)
+                else:
+                    o = self._deconv(ow["deconv"], o, o.shape[-1], None, 0, dtype, name=nm)
+                o_up = o
+                if l < 5:
+                    o = self._conv3(ow["conv_a"], o, skips[l], dtype, relu=True, name=nm + "a")
+                    o_h = o
+                    o = self._conv3(ow["conv_b"], o, None, dtype, relu=False, name=nm + "b")
+                else:
+                    o = self._conv3(ow["conv_a"], o, None, dtype, relu=True, name=nm + "a")
+                    o_h = o
+                    o = self._conv3(ow["conv_b"], o, None, dtype, relu=False, out_f32=True, name=nm + "b")  # fp32 [B,512,512,2]
+                if save is not None:
+                    save["ori"].append(dict(inp=o_in, up=o_up, h=o_h))
+            Ho, Wo = o.shape[1], o.shape[2]
+            ori_ = torch.empty((B, 2, Ho, Wo), dtype=f32, device=dev)
+            self._op("ori_normalize_kernel:ori_normalize|", 6.0 * B * Ho * Wo, 2.0 * B * Ho * Wo * (o.element_size() + 4),
+                     lambda: cabi.ori_normalize(o, ori_))                                   # a12
+            return o, ori_
+
+        o_raw = ori = None
         loc_rolls = loc_roll_indices(spec, self.ori_noise)
         scores_out: List[torch.Tensor] = []
         scores_cl = xhat = None
@@ -300,6 +385,9 @@ class PostEncoderPipeline:
                 xhat=xhat if l == 0 else None, scratch=scratch,
                 backend=cabi.BACKEND_SIMT if self.backend == cabi.BACKEND_SIMT else cabi.BACKEND_AUTO))
             scores_out.append(scores)
+            if l == 0:
+                with fork:
+                    o_raw, ori = orientation_decoder()
             lw = w["loc"][l]
             nm = "loc%d" % (6 - l)
             x_level = x
@@ -322,34 +410,10 @@ class PostEncoderPipeline:
         sm_scratch = torch.empty(cabi.softmax_scratch_elems(B, Hh * Wh), dtype=f32, device=dev)
         self._op("softmax_finish_kernel:softmax|", 5.0 * B * Hh * Wh, 2.0 * B * Hh * Wh * 4,
                  lambda: cabi.softmax_heatmap(logits_flat, heatmap.view(B, Hh * Wh), sm_scratch))
-
-        # a11 -- orientation decoder (no matching inside; input = [scores_1, normalize(x_1)], models.py:323)
-        o = None
-        for l in range(6):
-            ow = w["ori"][l]
-            nm = "ori%d" % (6 - l)
-            o_in = o
-            if l == 0:
-                o = self._deconv(ow["deconv"], scores_cl, SCORES_CL_PAD, xhat, D, dtype, name=nm)
-            else:
-                o = self._deconv(ow["deconv"], o, o.shape[-1], None, 0, dtype, name=nm)
-            o_up = o
-            if l < 5:
-                o = self._conv3(ow["conv_a"], o, skips[l], dtype, relu=True, name=nm + "a")
-                o_h = o
-                o = self._conv3(ow["conv_b"], o, None, dtype, relu=False, name=nm + "b")
-            else:
-                o = self._conv3(ow["conv_a"], o, None, dtype, relu=True, name=nm + "a")
-                o_h = o
-                o = self._conv3(ow["conv_b"], o, None, dtype, relu=False, out_f32=True, name=nm + "b")  # fp32 [B,512,512,2]
-            if save is not None:
-                save["ori"].append(dict(inp=o_in, up=o_up, h=o_h))
-        ori = torch.empty((B, 2, Hh, Wh), dtype=f32, device=dev)
+        side_saved = [t for rec in save["ori"] for t in rec.values()] if save is not None else []
+        fork.join(ori, o_raw, *side_saved)
         if save is not None:
-            save.update(o_raw=o, scores_cl=scores_cl, xhat=xhat)
-        o_in = o
-        self._op("ori_normalize_kernel:ori_normalize|", 6.0 * B * Hh * Wh, 2.0 * B * Hh * Wh * (o.element_size() + 4),
-                 lambda: cabi.ori_normalize(o_in, ori))                                   # a12
+            save.update(o_raw=o_raw, scores_cl=scores_cl, xhat=xhat)
         return (logits_flat, heatmap, ori, *scores_out)
 
 

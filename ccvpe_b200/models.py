@@ -20,7 +20,7 @@ import torch
 from torch import nn
 
 from . import cabi
-from .decoder import PostEncoderPipeline, decode_pose
+from .decoder import Fork, PostEncoderPipeline, decode_pose
 from .efficientnet import EfficientNetB0
 from .fast_encoder import FastEncoder
 from .specs import KITTI, OXFORD, SKIP_BLOCKS, SKIP_CHANNELS, VIGOR, VariantSpec
@@ -170,8 +170,12 @@ class _CVMBase(nn.Module):
         device: fused into the stem kernel's loads on the bf16 plan, through `ingest` otherwise."""
         if self._precision == "bf16" and not self.training:
             ge, se = self._bf16_encoders()
-            fg = ge.extract_features(grd)
+            # the two encoders are independent: the ground one runs on a forked side stream (small batches do not fill the GPU)
+            fork = Fork(grd.device, enabled=self.pipeline.concurrent and self.pipeline.timer is None)
+            with fork:
+                fg = ge.extract_features(grd)
             fs, multi = se.extract_features_multiscale(sat)
+            fork.join(fg)
             return fg, fs, multi, torch.bfloat16
         if grd.dtype == torch.uint8:
             grd = self.ingest(grd)

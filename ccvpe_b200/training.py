@@ -21,7 +21,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 
 from . import cabi
-from .decoder import SCORES_CL_PAD, PostEncoderPipeline, _cl, _nk
+from .decoder import SCORES_CL_PAD, Fork, PostEncoderPipeline, _cl, _nk
 from .specs import ENCODER_CHANNELS, SKIP_BLOCKS
 
 GRAD_PAD = 8      # incoming 1- / 2-channel gradients (logits, orientation field) are zero padded to 8 channels
@@ -236,39 +236,42 @@ class PostEncoderTrainer:
         D = spec.sat_dim
 
         # ---- orientation decoder (reference models.py:322-341), output -> bottleneck ----
-        d_sk_ori: List[Optional[torch.Tensor]] = [None] * 5
-        dY = torch.empty((B, Hh, Wh, GRAD_PAD), dtype=dtype, device=dev)
-        if d_ori is None:
-            dY.zero_()
-        else:
-            do = d_ori.contiguous().float()
-            p._op("ori_normalize_bwd_kernel:ori_normalize_bwd|", 12.0 * B * Hh * Wh, B * Hh * Wh * (16 + 8 * dY.element_size()),
-                  lambda: cabi.ori_normalize_bwd(sv["o_raw"], do, dY))
-        d_ori_in = None
-        for l in range(5, -1, -1):
-            rec, wl = sv["ori"][l], wb.ori[l]
-            n = 6 - l
-            nm = "ori%d" % n
-            h, up = rec["h"], rec["up"]
-            n_real = 2 if l == 5 else spec.ori_conv_out[l]
-            dh = self._conv_bwd(nm + "b", wl["conv_b"], h, None, dY, n_real, dtype, grads, "conv%d_ori.2" % n)
-            p._op("relu_bwd_kernel:relu_bwd|" + nm, dh.numel(), 3.0 * dh.numel() * dh.element_size(),
-                  lambda: cabi.relu_bwd(dh, h))
-            skip = skips[l] if l < 5 else None
-            dcat = self._conv_bwd(nm + "a", wl["conv_a"], up, skip, dh, h.shape[-1], dtype, grads, "conv%d_ori.0" % n)
-            cout = up.shape[-1]
-            if skip is not None:
-                d_sk_ori[l] = dcat[..., cout:]
-            d_up = dcat[..., :cout]
-            if l == 0:
-                srcs = [(sv["scores_cl"], spec.n_rolls, 0), (sv["xhat"], D, spec.n_rolls)]
+        # (on a forked side stream: independent of the localisation decoder's backward until the bottleneck level)
+        fork = Fork(dev, enabled=p.timer is None and p.concurrent)
+        with fork:
+            d_sk_ori: List[Optional[torch.Tensor]] = [None] * 5
+            dY = torch.empty((B, Hh, Wh, GRAD_PAD), dtype=dtype, device=dev)
+            if d_ori is None:
+                dY.zero_()
             else:
-                srcs = [(rec["inp"], rec["inp"].shape[-1], 0)]
-            d_in = self._deconv_bwd(nm, wl["deconv"], srcs, d_up, cout, dtype, grads, "deconv%d_ori" % n)
-            if l == 0:
-                d_ori_in = d_in                               # [B, 8, 8, 32 + D]: d scores_1 | d xhat_1
-            else:
-                dY = d_in
+                do = d_ori.contiguous().float()
+                p._op("ori_normalize_bwd_kernel:ori_normalize_bwd|", 12.0 * B * Hh * Wh, B * Hh * Wh * (16 + 8 * dY.element_size()),
+                      lambda: cabi.ori_normalize_bwd(sv["o_raw"], do, dY))
+            d_ori_in = None
+            for l in range(5, -1, -1):
+                rec, wl = sv["ori"][l], wb.ori[l]
+                n = 6 - l
+                nm = "ori%d" % n
+                h, up = rec["h"], rec["up"]
+                n_real = 2 if l == 5 else spec.ori_conv_out[l]
+                dh = self._conv_bwd(nm + "b", wl["conv_b"], h, None, dY, n_real, dtype, grads, "conv%d_ori.2" % n)
+                p._op("relu_bwd_kernel:relu_bwd|" + nm, dh.numel(), 3.0 * dh.numel() * dh.element_size(),
+                      lambda: cabi.relu_bwd(dh, h))
+                skip = skips[l] if l < 5 else None
+                dcat = self._conv_bwd(nm + "a", wl["conv_a"], up, skip, dh, h.shape[-1], dtype, grads, "conv%d_ori.0" % n)
+                cout = up.shape[-1]
+                if skip is not None:
+                    d_sk_ori[l] = dcat[..., cout:]
+                d_up = dcat[..., :cout]
+                if l == 0:
+                    srcs = [(sv["scores_cl"], spec.n_rolls, 0), (sv["xhat"], D, spec.n_rolls)]
+                else:
+                    srcs = [(rec["inp"], rec["inp"].shape[-1], 0)]
+                d_in = self._deconv_bwd(nm, wl["deconv"], srcs, d_up, cout, dtype, grads, "deconv%d_ori" % n)
+                if l == 0:
+                    d_ori_in = d_in                               # [B, 8, 8, 32 + D]: d scores_1 | d xhat_1
+                else:
+                    dY = d_in
 
         # ---- localisation decoder (reference models.py:186-320), output -> bottleneck ----
         d_sk_loc: List[Optional[torch.Tensor]] = [None] * 5
@@ -307,6 +310,8 @@ class PostEncoderTrainer:
             ds = ds.contiguous().float() if ds is not None else None
             d2 = d_in.view(B * H * W, C + GRAD_PAD)
             ds_cl = dxh2 = None
+            if l == 0:      # the orientation decoder's gradients are needed from here on
+                fork.join(d_ori_in, *[t for t in d_sk_ori if t is not None], *[grads[k] for k in grads if "_ori" in k])
             if l == 0 and d_ori_in is not None:
                 o2 = d_ori_in.view(B * H * W, SCORES_CL_PAD + D)
                 ds_cl, dxh2 = o2, o2[:, SCORES_CL_PAD:]
