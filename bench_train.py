@@ -218,10 +218,16 @@ def main(args):
     barrier()
     w0 = time.time()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ncu_range = bool(os.environ.get("CCVPE_NCU_RANGE"))       # `ncu --profile-from-start off`: capture exactly these steps
+    if ncu_range:
+        torch.cuda.profiler.start()
     ev0.record()
     for _ in range(args.steps):
         loss = step(resident)
     ev1.record()
+    if ncu_range:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     barrier()
     sampler.window(w0, time.time())
     launches = cabi.launch_count()
@@ -355,4 +361,11 @@ def main(args):
                     f.write("%-72s %9.4f %10.2f %10.1f %9.3f\n" % (tag, r["ms"] / args.steps, r["flops"] / sec / 1e12,
                                                                    r["bytes"] / sec / 1e9, ideal / sec))
     if dist is not None:
-        dist.destroy_process_group()
+        # The captured training graph holds NCCL work: tearing the communicator down underneath it can block forever, so the
+        # ranks meet at a barrier, flush and leave without running the process-group destructor.
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)

@@ -18,6 +18,6 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:matc
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:wgrad_tcgen05 -s 60 -c 1 -o gpurun_out/${TAG}_prof_wgrad \
   python bench.py --workload train --steps 1 --warmup 3 --no-cuda-graph $COMMON > gpurun_out/${TAG}_ncu_wgrad.log 2>&1
 # (5) launch list of one training step
-timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -s 12000 -c 4000 --csv --log-file gpurun_out/${TAG}_launches_train.csv \
+CCVPE_NCU_RANGE=1 timeout 1200 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/${TAG}_launches_train.csv \
   python bench.py --workload train --steps 1 --warmup 3 --no-cuda-graph $COMMON > gpurun_out/${TAG}_ncu_train.log 2>&1
 ls -la gpurun_out/${TAG}_* | tail -12
