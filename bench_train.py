@@ -124,10 +124,9 @@ def main(args):
     model = model.to(dev).set_precision(args.precision).train()
     # PyTorch-side tuning of the (PyTorch) encoders: cuDNN autotuning, and optionally channels-last convolutions
     torch.backends.cudnn.benchmark = True
-    enc_cl = os.environ.get("CCVPE_TRAIN_CL", "0") == "1"
-    if enc_cl:
-        model.grd_efficientnet.to(memory_format=torch.channels_last)
-        model.sat_efficientnet.to(memory_format=torch.channels_last)
+    # channels-last INPUTS make cuDNN / ATen run the encoders' convolutions and train-mode BatchNorms in NHWC (the parameters
+    # keep their layout: the flat gradient buckets and the fused optimizer want dense contiguous tensors)
+    enc_cl = os.environ.get("CCVPE_TRAIN_CL", "1") == "1"
     if args.backend == "simt":
         model.set_backend(cabi.BACKEND_SIMT)
     reducer = GradientAllReducer(model)
