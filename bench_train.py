@@ -124,8 +124,8 @@ def main(args):
     model = model.to(dev).set_precision(args.precision).train()
     # PyTorch-side tuning of the (PyTorch) encoders: cuDNN autotuning, and optionally channels-last convolutions
     torch.backends.cudnn.benchmark = True
-    # channels-last INPUTS make cuDNN / ATen run the encoders' convolutions and train-mode BatchNorms in NHWC (the parameters
-    # keep their layout: the flat gradient buckets and the fused optimizer want dense contiguous tensors)
+    # (the model itself feeds its bf16-autocast encoders channels-last inputs; CCVPE_TRAIN_CL=1 additionally keeps the resident
+    # input buffers channels-last so that conversion is free)
     enc_cl = os.environ.get("CCVPE_TRAIN_CL", "1") == "1"
     if args.backend == "simt":
         model.set_backend(cabi.BACKEND_SIMT)

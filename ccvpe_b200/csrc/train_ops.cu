@@ -306,11 +306,11 @@ colsum_partial_kernel(const T* __restrict__ x, int64_t n_pix, int H, int W, int 
           v[u] = load4(x + p * ld + cg * 4);
           bucket[u] = 0;
           if (s == 2 || w) {
-            const int64_t b = p / ((int64_t)H * W);
-            const int r = (int)(p - b * H * W);
-            const int y = r / W, xx = r - y * W;
-            if (s == 2) bucket[u] = (y & 1) * 2 + (xx & 1);
-            if (w) wt[u] = __ldg(w + (b * (H / s) + y / s) * (W / s) + xx / s);
+            const uint32_t pp = (uint32_t)p, hw = (uint32_t)(H * W);      // (n_pix < 2^31: checked on the host)
+            const uint32_t b = pp / hw, r = pp - b * hw;
+            const uint32_t y = r / (uint32_t)W, xx = r - y * (uint32_t)W;
+            if (s == 2) bucket[u] = (int)((y & 1u) * 2u + (xx & 1u));
+            if (w) wt[u] = __ldg(w + ((int64_t)b * (H / s) + y / s) * (W / s) + xx / s);
           }
         }
       }
@@ -355,9 +355,7 @@ __global__ void colsum_final_kernel(const float* __restrict__ ws, float* __restr
 extern "C" int64_t ccvpe_colsum_workspace_elems(int64_t n_pix, int C, int s) {
   using namespace ccvpe;
   if (n_pix <= 0 || C <= 0 || (s != 1 && s != 2)) return -1;
-  int64_t blocks = (n_pix + 255) / 256;
-  if (blocks > 4LL * sm_count()) blocks = 4LL * sm_count();
-  return blocks * s * s * C + 64 + 4096;
+  return 4LL * sm_count() * s * s * C + 64 + 4096;      // at most 4 blocks per SM, each one partial row per bucket
 }
 
 extern "C" int ccvpe_colsum(const void* x, int dtype, int B, int H, int W, int C, int ld, const float* w, int s,
@@ -371,9 +369,7 @@ extern "C" int ccvpe_colsum(const void* x, int dtype, int B, int H, int W, int C
   if (C > 512) {   // wide maps (1024-channel transposed convs, 1280- / 2048-channel cell descriptors): 512 columns per pass
     const int esz = dtype == CCVPE_F32 ? 4 : 2;
     const int buckets = s * s;
-    int64_t blocks_full = ((int64_t)B * H * W + 255) / 256;
-    if (blocks_full > 4LL * sm_count()) blocks_full = 4LL * sm_count();
-    float* tmp = workspace + blocks_full * buckets * 512 + 64;         // behind the partials of one 512-column pass
+    float* tmp = workspace + 4LL * sm_count() * buckets * 512 + 64;    // behind the partials of one 512-column pass
     for (int c0 = 0; c0 < C; c0 += 512) {
       const int cc = C - c0 < 512 ? C - c0 : 512;
       const int rc = ccvpe_colsum(static_cast<const uint8_t*>(x) + (int64_t)c0 * esz, dtype, B, H, W, cc, ld, w, s,
@@ -388,9 +384,11 @@ extern "C" int ccvpe_colsum(const void* x, int dtype, int B, int H, int W, int C
     return CCVPE_OK;
   }
   const int64_t n_pix = (int64_t)B * H * W;
-  int64_t blocks = (n_pix + 255) / 256;
-  if (blocks > 4LL * sm_count()) blocks = 4LL * sm_count();
+  CCVPE_REQUIRE(n_pix < (1LL << 31), "ccvpe_colsum: too many pixels");
   const int lanes = CS_THREADS / (C / 4);
+  int64_t blocks = (n_pix + 4 * lanes - 1) / (4 * lanes);     // >= 4 pixels per lane, up to 4 blocks per SM
+  if (blocks > 4LL * sm_count()) blocks = 4LL * sm_count();
+  if (blocks < 1) blocks = 1;
   int64_t ppb = (n_pix + blocks - 1) / blocks;
   ppb = (ppb + lanes - 1) / lanes * lanes;
   blocks = (n_pix + ppb - 1) / ppb;
@@ -601,6 +599,7 @@ struct MatchBwdArgs {
   float* t_part;                                             // [B, tiles, R, C] partial T
   float* c_part;                                             // [B, tiles] partial sum_p sum_i dS_i s_i
   int tiles;
+  int csplits, chunks_per_split;                             // pass B (dx, T) is split over channel ranges (blockIdx.z)
 };
 
 template <typename T, bool WINDOWED>
@@ -721,13 +720,17 @@ __global__ void __launch_bounds__(MB_TILE) match_level_bwd_kernel(const MatchBwd
     float v = warp_sum(cpart);
     if ((t & 31) == 0) red[t >> 5] = v;
     __syncthreads();
-    if (t == 0) a.c_part[(int64_t)b * a.tiles + tile] = (red[0] + red[1]) + (red[2] + red[3]);
+    if (t == 0 && blockIdx.z == 0) a.c_part[(int64_t)b * a.tiles + tile] = (red[0] + red[1]) + (red[2] + red[3]);
   }
   __syncthreads();
   // ---- pass B: dx and the partial T ----
   T* dxo = static_cast<T*>(a.dx) + ((int64_t)b * a.HW + p0) * C;
   float* tp = a.t_part + ((int64_t)b * a.tiles + tile) * R * C;
-  for (int c0 = 0; c0 < C; c0 += MB_CHUNK) {
+  // small maps have few pixel tiles: the channel axis of this pass is split over blockIdx.z (pass A above is cheap and is
+  // simply repeated by every split)
+  const int cb_begin = blockIdx.z * a.chunks_per_split * MB_CHUNK;
+  const int cb_end = min(C, cb_begin + a.chunks_per_split * MB_CHUNK);
+  for (int c0 = cb_begin; c0 < cb_end; c0 += MB_CHUNK) {
     stage(c0, true);
     __syncthreads();
     // (1) T[i][c0 + cc] partial: R x 32 outputs, each a 128-term dot product over the tile's pixels
@@ -857,7 +860,13 @@ extern "C" int ccvpe_match_level_bwd(const void* x, int dtype, int B, int HW, in
   a.d_max = d_max; a.ld_dmax = ld_dmax; a.d_xhat = d_xhat; a.ld_dxhat = ld_dxhat;
   a.d_xhat2 = d_xhat2; a.ld_dxhat2 = ld_dxhat2; a.d_scores_cl = d_scores_cl; a.ld_dscl = ld_dscl;
   a.dx = dx; a.t_part = t_part; a.c_part = c_part; a.tiles = tiles;
-  const dim3 grid(tiles, B);
+  const int chunks = (C + MB_CHUNK - 1) / MB_CHUNK;
+  int csplits = (2 * sm_count() + tiles * B - 1) / (tiles * B);
+  if (csplits > chunks) csplits = chunks;
+  if (csplits < 1) csplits = 1;
+  a.chunks_per_split = (chunks + csplits - 1) / csplits;
+  a.csplits = (chunks + a.chunks_per_split - 1) / a.chunks_per_split;
+  const dim3 grid(tiles, B, a.csplits);
 #define CCVPE_MB(TT, WW) match_level_bwd_kernel<TT, WW><<<grid, MB_TILE, 0, st>>>(a)
   if (dtype == CCVPE_F32) { if (windowed) CCVPE_MB(float, true); else CCVPE_MB(float, false); }
   else { if (windowed) CCVPE_MB(__nv_bfloat16, true); else CCVPE_MB(__nv_bfloat16, false); }

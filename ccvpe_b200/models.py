@@ -220,6 +220,11 @@ class _CVMBase(nn.Module):
         with cabi.device_of(grd):
             cudnn = torch.backends.cudnn
             bf16 = self._precision == "bf16"
+            if bf16:
+                # channels-last inputs make cuDNN / ATen run the encoders' convolutions and train-mode BatchNorms in NHWC
+                # (measured: 51.8 -> 41.9 ms per B=8 training step); parameters keep their layout
+                grd = grd.contiguous(memory_format=torch.channels_last)
+                sat = sat.contiguous(memory_format=torch.channels_last)
             # fp32: exact fp32 encoders (no TF32); bf16: mixed precision -- fp32 master weights, bf16 autocast for the
             # encoders' convolutions (BatchNorm statistics stay fp32), bf16 activations / GEMM operands in the CUDA path
             with cudnn.flags(enabled=True, benchmark=cudnn.benchmark, deterministic=cudnn.deterministic, allow_tf32=False), \

@@ -20,6 +20,7 @@ for w in $what; do
     bench_train_fp32) timeout 900 python bench.py --workload train --precision fp32 --steps 3 --warmup 3 --no-cpu --layers gpurun_out/${tag}_layers_train_fp32.txt > gpurun_out/${tag}_bench_train_fp32.json 2> gpurun_out/${tag}_bench_train_fp32.err; head -c 500 gpurun_out/${tag}_bench_train_fp32.json; echo; tail -5 gpurun_out/${tag}_bench_train_fp32.err;;
     bench_train_nocl) CCVPE_TRAIN_CL=0 timeout 900 python bench.py --workload train --steps 5 --warmup 3 --no-cpu > gpurun_out/${tag}_bench_train_nocl.json 2> gpurun_out/${tag}_bench_train_nocl.err; head -c 300 gpurun_out/${tag}_bench_train_nocl.json; echo; tail -3 gpurun_out/${tag}_bench_train_nocl.err;;
     bench_train_cl) CCVPE_TRAIN_CL=1 timeout 900 python bench.py --workload train --steps 5 --warmup 3 --no-cpu > gpurun_out/${tag}_bench_train_cl.json 2> gpurun_out/${tag}_bench_train_cl.err; head -c 300 gpurun_out/${tag}_bench_train_cl.json; echo; tail -3 gpurun_out/${tag}_bench_train_cl.err;;
+    profile_train) timeout 600 python scripts/profile_train.py > gpurun_out/${tag}_profile_train.txt 2>&1; head -40 gpurun_out/${tag}_profile_train.txt | cut -c1-200;;
     bench_dw) timeout 300 python scripts/bench_dwconv.py fast > gpurun_out/${tag}_bench_dw.txt 2>&1; tail -2 gpurun_out/${tag}_bench_dw.txt;;
     wgrad_halo) CCVPE_WGRAD_HALO=1 timeout 300 python -m pytest tests/test_gpu_train.py -m gpu -q -k "wgrad_conv3x3_tcgen05" 2>&1 | tail -3; CCVPE_WGRAD_HALO=0 timeout 300 python -m pytest tests/test_gpu_train.py -m gpu -q -k "wgrad_conv3x3_tcgen05" 2>&1 | tail -3;;
     *) echo "unknown step $w";;
