@@ -73,11 +73,19 @@ class SamePadConv2d(nn.Conv2d):
     def forward(self, x):
         lo, hi = self._pad_lo, self._pad_hi
         if lo or hi:
+            # (pure data movement, so any formulation is bit-identical to the reference's F.pad calls; this one keeps a
+            # channels-last input channels-last -- F.pad(mode="circular") would hand back an NCHW tensor and push the
+            # convolution and the BatchNorm behind it onto the slow NCHW kernels in training)
+            cl = x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous()
             if self._circular:
-                x = F.pad(x, (lo, hi, 0, 0), mode="circular")
+                w = x.shape[3]
+                parts = ([x[..., w - lo:]] if lo else []) + [x] + ([x[..., :hi]] if hi else [])
+                x = torch.cat(parts, dim=3) if len(parts) > 1 else x
                 x = F.pad(x, (0, 0, lo, hi))
             else:
                 x = F.pad(x, (lo, hi, lo, hi))
+            if cl and not x.is_contiguous(memory_format=torch.channels_last):
+                x = x.contiguous(memory_format=torch.channels_last)
         return F.conv2d(x, self.weight, self.bias, self.stride, 0, self.dilation, self.groups)
 
 
