@@ -243,18 +243,21 @@ def main(args):
     # ---- all-reduce: alone vs exposed ----
     ar = {"bytes": int(reducer.n_params) * 4, "buckets": reducer.bucket_bytes, "world": world}
     if world > 1:
+        for _ in range(2):                          # (first eager collectives of these sizes: protocol / channel set-up)
+            reducer.all_reduce_alone()
         barrier()
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a0.record()
-        for _ in range(3):
+        for _ in range(5):
             reducer.all_reduce_alone()
         a1.record()
         torch.cuda.synchronize()
-        ar["alone_ms"] = round(a0.elapsed_time(a1) / 3, 3)
+        ar["alone_ms"] = round(a0.elapsed_time(a1) / 5, 3)
+        ar["alone_busbw_gbs"] = round(2.0 * (world - 1) / world * ar["bytes"] / (ar["alone_ms"] * 1e-3) / 1e9, 1)
         # exposed: time from the end of backward to all buckets reduced
         grd, sat, gt, gwo, gor = resident
         exp = []
-        for _ in range(3):
+        for _ in range(4):
             reducer.zero_grad()
             out = model(grd, sat)
             l_ = losses.training_loss(out, gt, gwo, gor)
