@@ -1,0 +1,58 @@
+"""Collects the bench.py JSON lines recorded under gpurun_out/ in round 2 into profiles/r02_bench_lines.md (profiles tool)."""
+import json
+import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+RUNS = [
+    ("vigor_b64 (default workload), 1 GPU", "r02v_bench.json"),
+    ("kitti_b32, 1 GPU", "r02v_bench_kitti_b32.json"),
+    ("vigor_prior72_fov180, 1 GPU", "r02v_bench_vigor_prior72_fov180.json"),
+    ("vigor_prior72_fov108, 1 GPU", "r02v_bench_vigor_prior72_fov108.json"),
+    ("oxford_b1 (batch-1 sequential frames), 1 GPU", "r02v_bench_oxford_b1.json"),
+    ("train, B=8 bf16, one CUDA graph per step, 1 GPU", "r02v_bench_train.json"),
+    ("train, B=8 fp32 parity path (eager), 1 GPU", "r02f_bench_train_fp32.json"),
+    ("2 GPUs, weak (64 pairs per GPU)", "r02m_n2_weak.json"),
+    ("2 GPUs, strong (one batch of 64)", "r02m_n2_strong.json"),
+    ("2 GPUs, train (graph)", "r02m_n2_train.json"),
+    ("8 GPUs, weak (64 pairs per GPU)", "r02s_n8_weak.json"),
+    ("8 GPUs, strong (one batch of 64: 8 pairs per GPU)", "r02s_n8_strong.json"),
+    ("8 GPUs, train (B=8 per GPU, graph)", "r02t_n8_train.json"),
+]
+
+
+def load(name):
+    try:
+        return json.loads(open(os.path.join(ROOT, "gpurun_out", name)).read().strip().splitlines()[-1])
+    except Exception:
+        return None
+
+
+out = ["# Bench lines recorded in round 2 (B200; the full JSON lines live under gpurun_out/, which is not tracked)", ""]
+for tag, f in RUNS:
+    d = load(f)
+    if not d:
+        continue
+    out.append("## %s  (%s)" % (tag, f))
+    out.append("value %.1f %s, %.3f ms/step; e2e %.1f (%s); gpu_launches %s; clocks %s" % (
+        d["value"], d["unit"], d["ms_per_step"], d["e2e"]["value"], d["e2e"].get("input", "host tensors"), d.get("gpu_launches"),
+        d.get("clocks")))
+    if "fp32_host_images" in d["e2e"]:
+        out.append("e2e with fp32 host images: %.1f" % d["e2e"]["fp32_host_images"]["value"])
+    if d.get("roofline"):
+        out.append("roofline: %s" % {k: d["roofline"][k] for k in ("kernel", "bound", "achieved", "peak", "unit", "frac")})
+    if d.get("kernels"):
+        out.append("kernels (ms/step, frac of peak): %s" % {k: (v["ms_per_step"], v["frac"]) for k, v in d["kernels"].items()})
+    if d.get("cpu_baseline"):
+        c = d["cpu_baseline"]
+        out.append("cpu_baseline: %.2f %s on %d cores (%s)" % (c["value"], c["unit"], c["cores"], c["kind"]))
+    if d.get("torch_gpu_baseline"):
+        out.append("torch_gpu_baseline: %s" % {k: v for k, v in d["torch_gpu_baseline"].items() if k != "sample"})
+    if d.get("parity"):
+        out.append("parity: %s" % d["parity"])
+    if d.get("allreduce"):
+        out.append("allreduce: %s" % d["allreduce"])
+    if d.get("latency_ms_per_frame"):
+        out.append("latency: %s" % d["latency_ms_per_frame"])
+    out.append("")
+open(os.path.join(ROOT, "profiles", "r02_bench_lines.md"), "w").write("\n".join(out))
+print("\n".join(out))

@@ -303,6 +303,31 @@ def test_bf16_full_size_batches_against_oracle(cuda_device, variant, shape_key, 
     assert agree_decided == len(decided) and len(decided) >= 1, rec["argmax"]
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_uint8_images_are_ingested_on_the_device(cuda_device, precision):
+    """forward(uint8 images) == forward(ToTensor + ImageNet Normalize of the same pixels): bit-identical on the fp32 path
+    (ccvpe_ingest_u8 reproduces torchvision's arithmetic), within bf16 noise on the bf16 plan (the stem kernel normalises
+    with one FMA in its loads).  Odd batch size on purpose."""
+    model = build_model("vigor", None, True, 12).to(cuda_device).set_precision(precision)
+    g = torch.Generator().manual_seed(6)
+    grd8 = torch.randint(0, 256, (3, 3, 320, 640), generator=g, dtype=torch.uint8)
+    sat8 = torch.randint(0, 256, (3, 3, 512, 512), generator=g, dtype=torch.uint8)
+    mean = torch.tensor(cabi.IMAGENET_MEAN).view(1, 3, 1, 1)
+    std = torch.tensor(cabi.IMAGENET_STD).view(1, 3, 1, 1)
+    grd = ((grd8.float().div(255) - mean) / std).to(cuda_device)
+    sat = ((sat8.float().div(255) - mean) / std).to(cuda_device)
+    with torch.no_grad():
+        a = model(grd8.to(cuda_device), sat8.to(cuda_device))
+        b = model(grd, sat)
+        pose = model.localize_u8(grd8.to(cuda_device), sat8.to(cuda_device))
+    for i, n in enumerate(OUT_NAMES):
+        if precision == "fp32":
+            assert torch.equal(a[i], b[i]), n
+        elif n != "ori":
+            assert rel_err(a[i], b[i]) < 4e-2, (n, rel_err(a[i], b[i]))
+    assert pose["idx"].tolist() == [int(a[1][i].flatten().argmax()) for i in range(3)]
+
+
 def test_model_follows_its_tensors_device(cuda_device):
     """a model moved to cuda:1 while the current device is cuda:0 must launch on cuda:1 (kernel attributes,
     stream and tensor maps are per device)."""

@@ -356,7 +356,7 @@ def test_grd_descriptors_bwd(cuda_device, B, H, W, cs):
 # ---------------------------------------------------------------------------------------------------------------
 # the whole training step
 # ---------------------------------------------------------------------------------------------------------------
-def _oracle_step(model, grd, sat, gts, train_mode, seed):
+def _oracle_step(model, grd, sat, gts, train_mode, seed, variant="vigor"):
     """Loss and gradients of the reference training step (train_VIGOR.py:120-150) through autograd of the CPU oracle."""
     ref = copy.deepcopy(model).cpu()
     ref.train(train_mode)
@@ -364,7 +364,7 @@ def _oracle_step(model, grd, sat, gts, train_mode, seed):
         p_.requires_grad_(True)
     params = dict(ref.named_parameters())
     torch.manual_seed(seed)
-    out = orc.forward_full("vigor", params, ref.grd_efficientnet, ref.sat_efficientnet, grd, sat)
+    out = orc.forward_full(variant, params, ref.grd_efficientnet, ref.sat_efficientnet, grd, sat)
     loss = orc.training_loss(out, *gts)
     loss.backward()
     return loss.item(), {k: (v.grad.clone() if v.grad is not None else None) for k, v in params.items()}, [t.detach() for t in out]
@@ -417,6 +417,47 @@ def test_training_step_fp32_matches_oracle_autograd(cuda_device, train_mode, mon
         if not err <= 2e-3 * scale + 2e-6 * gmax:
             bad[k] = (err, scale, gmax)
     assert not bad, sorted(bad.items(), key=lambda kv: -kv[1][0] / (kv[1][1] + 1e-30))[:10]
+
+
+@pytest.mark.parametrize("variant,shape_key,n_bins", [("kitti", "kitti", 16), ("oxford", "oxford", 20)])
+def test_training_step_fp32_other_classes(cuda_device, variant, shape_key, n_bins):
+    """The same step for CVM_KITTI (16 orientations, windowed matching with wrap-around, reference train_KITTI.py:121-155) and
+    CVM_OxfordRobotCar (centred windows, train_OxfordRobotCar.py:100-136), batch 1, eval-mode BatchNorm: loss and every
+    gradient vs autograd through the oracle (same tolerances as the VIGOR test)."""
+    from ccvpe_b200.synthetic import GROUND_SHAPES, synthetic_pair
+    model = build_model(variant, None, None, 35)
+    grd, sat = synthetic_pair(1, GROUND_SHAPES[shape_key], seed=65)
+    gts = synthetic_ground_truth(1, seed=9, n_bins=n_bins)
+    ref_loss, ref_grads, ref_out = _oracle_step(model, grd, sat, gts, False, seed=3, variant=variant)
+    dev = cuda_device
+    gpu = copy.deepcopy(model).to(dev).eval()
+    for p_ in gpu.parameters():
+        p_.requires_grad_(True)
+    out = gpu(grd.to(dev), sat.to(dev))
+    loss = losses.training_loss(out, *[t.to(dev) for t in gts])
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(loss.item() - ref_loss) < 1e-4 * abs(ref_loss), (loss.item(), ref_loss)
+    gmax = max(float(v.abs().max()) for v in ref_grads.values() if v is not None)
+    bad = {}
+    for k, p_ in gpu.named_parameters():
+        rg = ref_grads[k]
+        if rg is None:
+            continue
+        err = float((p_.grad.detach().cpu().double() - rg.double()).abs().max())
+        if not err <= 2e-3 * float(rg.abs().max()) + 2e-6 * gmax:
+            bad[k] = (err, float(rg.abs().max()))
+    assert not bad, sorted(bad.items(), key=lambda kv: -kv[1][0])[:10]
+
+
+def test_losses_and_model_refuse_cpu_tensors():
+    """No CPU fallback on the training path either."""
+    with pytest.raises(cabi.CcvpeError):
+        losses.infoNCELoss(torch.zeros(1, 8), torch.zeros(1, 8))
+    with pytest.raises(cabi.CcvpeError):
+        losses.cross_entropy_loss(torch.zeros(1, 8), torch.zeros(1, 8))
+    with pytest.raises(cabi.CcvpeError):
+        losses.orientation_loss(torch.zeros(1, 2, 4, 4), torch.zeros(1, 2, 4, 4), torch.zeros(1, 1, 4, 4))
 
 
 def test_training_step_bf16_close_to_fp32_oracle(cuda_device):
