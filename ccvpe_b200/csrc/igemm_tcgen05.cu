@@ -34,8 +34,14 @@ struct TcParams {
   int pad_w, pad_h, pad_wp, pad_hp, pad_lo;   // MODE 3 only: rows are written into the interior of a padded image
   int epi_off;                                // byte offset of the epilogue staging tile behind the pipeline stages
   int w_resident, w_off, w_blk;               // weights loaded once per CTA: offset of / bytes per K-block B tile
+  // halo mode (3x3 convs of the shallow levels): ONE A box [(th+2) x (tw+2) px x kw ch] per K block serves all nine taps
+  // (tile = 8 x 16 pixels, so a UMMA 8-row group is one image row and the group stride is the halo pitch); the nine
+  // weight tiles stream through the ordinary stage ring
+  int halo, a_slots, a_slot_bytes, b_off, halo_pitch, halo_tx0, halo_tx1;
   EpiParams e;
 };
+
+constexpr int TC_HALO_SLOTS = 4;
 
 // ---- kernel ------------------------------------------------------------------------------------------------------
 template <bool LIGHT, int MODE, bool HAS_R1, bool OUT_F32>
@@ -52,6 +58,8 @@ igemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
   __shared__ __align__(8) uint64_t bar_tmem_full[2];
   __shared__ __align__(8) uint64_t bar_tmem_empty[2];
   __shared__ __align__(8) uint64_t bar_weights;
+  __shared__ __align__(8) uint64_t bar_a_full[TC_HALO_SLOTS];
+  __shared__ __align__(8) uint64_t bar_a_empty[TC_HALO_SLOTS];
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(16) float s_bias[2][TC_MAX_N];
   __shared__ __align__(16) float s_r1w[2][TC_MAX_N];
@@ -73,6 +81,10 @@ igemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
       mbar_init(smem_u32(&bar_tmem_empty[a]), EPI_WARPS);
     }
     mbar_init(smem_u32(&bar_weights), 1);
+    for (int s2 = 0; s2 < TC_HALO_SLOTS; ++s2) {
+      mbar_init(smem_u32(&bar_a_full[s2]), 1);
+      mbar_init(smem_u32(&bar_a_empty[s2]), 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0 && lane == 0) {
@@ -129,6 +141,8 @@ igemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
       }
       int stage = 0;
       uint32_t phase = 0;
+      int aslot = 0;
+      uint32_t aphase = 0;
       for (int tile = t0; tile < tend; tile += tstep) {
         int mt = fixed_n ? tile : tile / p.n_tiles_n;
         const int nt = fixed_n ? cta_nt : tile - mt * p.n_tiles_n;
@@ -139,6 +153,44 @@ igemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
           mt >>= p.tile_shift[d];
         }
         const int n0 = nt * p.block_n;
+        if (p.halo) {
+          // per K block: one halo box of the activations, then the nine tap tiles of the weights
+          for (int src = 0; src < 2; ++src) {
+            const int nb = src ? p.nb1 : p.nb0;
+            const int kw = src ? p.kw1 : p.kw0;
+            const CUtensorMap* tm = src ? &p.tm_a1 : &p.tm_a0;
+            const CUtensorMap* tmb = src ? &p.tm_b1 : &p.tm_b0;
+            const uint32_t txb = (uint32_t)(p.block_n * kw * 2);
+            for (int cb = 0; cb < nb; ++cb) {
+              mbar_wait(smem_u32(&bar_a_empty[aslot]), aphase ^ 1u);
+              if (elect_one()) {
+                const uint32_t full = smem_u32(&bar_a_full[aslot]);
+                mbar_arrive_expect_tx(full, (uint32_t)(src ? p.halo_tx1 : p.halo_tx0));
+                tma_load_4d(smem_base + aslot * p.a_slot_bytes, tm, full, cb * kw, base[0] - 1, base[1] - 1, base[2]);
+              }
+              __syncwarp();
+              if (++aslot == p.a_slots) {
+                aslot = 0;
+                aphase ^= 1u;
+              }
+              for (int tap = 0; tap < 9; ++tap) {
+                const int kbase = tap * (p.kpad0 + p.kpad1) + (src ? p.kpad0 : 0);
+                mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+                if (elect_one()) {
+                  const uint32_t full = smem_u32(&bar_full[stage]);
+                  mbar_arrive_expect_tx(full, txb);
+                  tma_load_2d(smem_base + p.b_off + stage * stage_bytes, tmb, full, kbase + cb * kw, n0);
+                }
+                __syncwarp();
+                if (++stage == p.stages) {
+                  stage = 0;
+                  phase ^= 1u;
+                }
+              }
+            }
+          }
+          continue;
+        }
         for (int tap = 0; tap < p.taps; ++tap) {
           const int c1 = base[0] + p.tap_off[tap][0], c2 = base[1] + p.tap_off[tap][1];
           const int c3 = base[2] + p.tap_off[tap][2], c4 = base[3] + p.tap_off[tap][3];
@@ -193,6 +245,11 @@ igemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      int aslot = 0;
+      uint32_t aphase = 0;
+      // halo mode: A descriptors address the halo tile (group stride = halo pitch), B descriptors the weight ring
+      const uint32_t lo_bring = ((((smem_base + (uint32_t)p.b_off) & 0x3FFFFu) >> 4) | (1u << 16));
+      const uint32_t lo_aslot = (uint32_t)p.a_slot_bytes >> 4;
       for (int tile = t0; tile < tend; tile += tstep, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
@@ -201,6 +258,53 @@ igemm_tcgen05_kernel(const __grid_constant__ TcParams p) {
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.block_n);
         uint32_t accumulate = 0;
         uint32_t b_res = lo_w;                     // resident B tile of the next K block
+        if (p.halo) {
+#pragma unroll 1
+          for (int src = 0; src < 2; ++src) {
+            const int nb = src ? p.nb1 : p.nb0;
+            const int kw = src ? p.kw1 : p.kw0;
+            const uint32_t hib = src ? hi1 : hi0;
+            const uint32_t row_units = (uint32_t)(kw * 2) >> 4;                       // one pixel of the halo tile
+            const uint32_t hia = (hib & ~0x3FFFu) | ((uint32_t)p.halo_pitch * row_units);   // SBO = one halo row of pixels
+            const uint32_t pitch_units = (uint32_t)p.halo_pitch * row_units;
+            const int nfull = src ? full1 : full0, ntail = src ? tail1 : tail0;
+#pragma unroll 1
+            for (int cb = 0; cb < nb; ++cb) {
+              const int nk16 = (cb == nb - 1) ? ntail : nfull;
+              mbar_wait(smem_u32(&bar_a_full[aslot]), aphase);
+              tc_fence_after();
+              const uint32_t a_lo0 = lo_base + (uint32_t)aslot * lo_aslot;
+#pragma unroll
+              for (int tap = 0; tap < 9; ++tap) {
+                mbar_wait(smem_u32(&bar_full[stage]), phase);
+                tc_fence_after();
+                const uint64_t adesc = ((uint64_t)hia << 32) | (a_lo0 + (uint32_t)(tap / 3) * pitch_units + (uint32_t)(tap % 3) * row_units);
+                const uint64_t bdesc = ((uint64_t)hib << 32) | (lo_bring + (uint32_t)stage * lo_stage);
+                if (elect_one()) {
+                  umma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);
+                  if (nk16 > 1) umma_bf16(tmem_d, adesc + 2, bdesc + 2, idesc, 1u);
+                  if (nk16 > 2) umma_bf16(tmem_d, adesc + 4, bdesc + 4, idesc, 1u);
+                  if (nk16 > 3) umma_bf16(tmem_d, adesc + 6, bdesc + 6, idesc, 1u);
+                  umma_commit(smem_u32(&bar_empty[stage]));
+                  if (tap == 8) umma_commit(smem_u32(&bar_a_empty[aslot]));          // the halo tile is free again
+                }
+                accumulate = 1;
+                __syncwarp();
+                if (++stage == p.stages) {
+                  stage = 0;
+                  phase ^= 1u;
+                }
+              }
+              if (++aslot == p.a_slots) {
+                aslot = 0;
+                aphase ^= 1u;
+              }
+            }
+          }
+          if (elect_one()) umma_commit(smem_u32(&bar_tmem_full[acc]));
+          __syncwarp();
+          continue;
+        }
         for (int tap = 0; tap < p.taps; ++tap) {
 #pragma unroll 1
           for (int src = 0; src < 2; ++src) {
@@ -334,13 +438,22 @@ static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 struct TcGeometry {
   bool cell;        // k2 s2 gather (aerial cell descriptors; data gradient of the k2 s2 transposed convs)
+  bool halo;        // 3x3 conv with one halo A box per K block (8 x 16 pixel tiles)
   int tw, th, tb;   // conv tile: tw x th pixels x tb images = 128 rows (cell: tw output columns x th (row, image) pairs)
 };
+
+// CCVPE_IGEMM_HALO: 0 = never, 1 = whenever the geometry allows, unset = the shallow 3x3 layers (N <= 160), which are bound by
+// TMA's per-box-row issue rate when every tap loads its own 128-row A box (9 x 128 rows per K block vs 180 for the halo box)
+static int halo_policy() {
+  static const int v = getenv("CCVPE_IGEMM_HALO") ? atoi(getenv("CCVPE_IGEMM_HALO")) : -1;
+  return v;
+}
 
 static bool tc_geometry(const ccvpe_igemm_desc& d, TcGeometry* g) {
   if (d.stride == 2 && d.kh == 2 && d.kw == 2 && d.pad == 0) {
     if (d.Hin != 2 * d.Hout || d.Win != 2 * d.Wout || d.c1 != 0 || !is_pow2(d.Wout)) return false;
     g->cell = true;
+    g->halo = false;
     g->tw = d.Wout < TC_BM ? d.Wout : TC_BM;
     g->th = TC_BM / g->tw;
     g->tb = 0;
@@ -350,11 +463,21 @@ static bool tc_geometry(const ccvpe_igemm_desc& d, TcGeometry* g) {
   if (d.Hin != d.Hout || d.Win != d.Wout) return false;
   if (d.kh == 1) {   // 1x1: flattened pixel tiles, any spatial size
     g->cell = false;
+    g->halo = false;
     g->tw = TC_BM;
     g->th = g->tb = 1;
     return true;
   }
   if (!is_pow2(d.Wout) || !is_pow2(d.Hout)) return false;
+  g->halo = false;
+  if (d.Wout >= 8 && d.Hout >= 16 && halo_policy() != 0 && (halo_policy() == 1 || d.N <= 160)) {
+    g->cell = false;
+    g->halo = true;
+    g->tw = 8;
+    g->th = 16;
+    g->tb = 1;
+    return true;
+  }
   int tw = d.Wout < TC_BM ? d.Wout : TC_BM;
   int th = TC_BM / tw;
   if (th > d.Hout) th = d.Hout;
@@ -444,8 +567,26 @@ int igemm_tcgen05(const ccvpe_igemm_desc& d, cudaStream_t st, const TcOutPad* ou
   }
   int stages = (light ? light_budget - w_bytes : TC_SMEM_BUDGET) / stage_bytes;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+  if (g.halo) {
+    // one CTA per SM: a ring of halo A tiles + a deep ring of weight tiles (weights stream: nine tiles per K block)
+    light = false;
+    p.w_resident = 0;
+    w_bytes = 0;
+    p.halo = 1;
+    p.halo_pitch = g.tw + 2;
+    p.halo_tx0 = (g.tw + 2) * (g.th + 2) * p.kw0 * 2;
+    p.halo_tx1 = (g.tw + 2) * (g.th + 2) * p.kw1 * 2;
+    p.a_slot_bytes = ((g.tw + 2) * (g.th + 2) * kw_max * 2 + 1023) / 1024 * 1024;
+    p.a_slots = 3;
+    p.b_off = p.a_slots * p.a_slot_bytes;
+    stage_bytes = (block_n * kw_max * 2 + 1023) / 1024 * 1024;
+    p.stage_bytes = stage_bytes;
+    stages = (TC_SMEM_BUDGET - p.b_off) / stage_bytes;
+    if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+    if (stages < 3) return fail(CCVPE_ERR_UNSUPPORTED, "ccvpe_igemm(tcgen05): halo mode does not fit shared memory");
+  }
   p.stages = stages;
-  p.w_off = stages * stage_bytes;
+  p.w_off = (g.halo ? p.b_off : 0) + stages * stage_bytes;
   p.epi_off = p.w_off + w_bytes;
   const bool staged = light && staged_out;
   const int64_t ktot = (int64_t)p.taps * (p.kpad0 + p.kpad1);
@@ -499,7 +640,7 @@ int igemm_tcgen05(const ccvpe_igemm_desc& d, cudaStream_t st, const TcOutPad* ou
       uint64_t dims[4] = {(uint64_t)c, (uint64_t)d.Win, (uint64_t)d.Hin, (uint64_t)d.B};
       uint64_t str[3] = {(uint64_t)ld * esz, (uint64_t)d.Win * ld * esz, (uint64_t)d.Hin * d.Win * ld * esz};
       const int kw = s ? p.kw1 : p.kw0;
-      uint32_t box[4] = {(uint32_t)kw, (uint32_t)g.tw, (uint32_t)g.th, (uint32_t)g.tb};
+      uint32_t box[4] = {(uint32_t)kw, (uint32_t)(g.tw + (g.halo ? 2 : 0)), (uint32_t)(g.th + (g.halo ? 2 : 0)), (uint32_t)g.tb};
       if ((rc = encode_map(s ? &p.tm_a1 : &p.tm_a0, base, 4, dims, str, box, kw)) != CCVPE_OK) return rc;
     }
     p.tiles[0] = d.Wout / g.tw; p.tiles[1] = d.Hout / g.th; p.tiles[2] = (d.B + g.tb - 1) / g.tb; p.tiles[3] = 1;
@@ -542,7 +683,7 @@ int igemm_tcgen05(const ccvpe_igemm_desc& d, cudaStream_t st, const TcOutPad* ou
     p.pad_w = d.Wout; p.pad_h = d.Hout; p.pad_wp = out_pad->Wp; p.pad_hp = out_pad->Hp; p.pad_lo = out_pad->lo;
   }
 
-  const int smem = stages * stage_bytes + w_bytes + (staged ? (TC_EPI_WARPS * EPI_WARP_STAGE_BYTES) : 0) + 1024;
+  const int smem = (g.halo ? p.b_off : 0) + stages * stage_bytes + w_bytes + (staged ? (TC_EPI_WARPS * EPI_WARP_STAGE_BYTES) : 0) + 1024;
   const int max_grid = (light ? 2 : 1) * sm_count();
   int grid = p.total_tiles < max_grid ? p.total_tiles : max_grid;
   if (p.w_resident) {   // whole groups of n_tiles_n CTAs, one per N tile

@@ -22,6 +22,7 @@ for w in $what; do
     bench_train_cl) CCVPE_TRAIN_CL=1 timeout 900 python bench.py --workload train --steps 5 --warmup 3 --no-cpu > gpurun_out/${tag}_bench_train_cl.json 2> gpurun_out/${tag}_bench_train_cl.err; head -c 300 gpurun_out/${tag}_bench_train_cl.json; echo; tail -3 gpurun_out/${tag}_bench_train_cl.err;;
     profile_train) timeout 600 python scripts/profile_train.py > gpurun_out/${tag}_profile_train.txt 2>&1; head -40 gpurun_out/${tag}_profile_train.txt | cut -c1-200;;
     bench_dw) timeout 300 python scripts/bench_dwconv.py fast > gpurun_out/${tag}_bench_dw.txt 2>&1; tail -2 gpurun_out/${tag}_bench_dw.txt;;
+    igemm_halo) for h in 1 0; do CCVPE_IGEMM_HALO=$h timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_train.py -m gpu -q -k "conv3x3 or deconv or training_step_bf16" 2>&1 | tail -4; done;;
     wgrad_halo) CCVPE_WGRAD_HALO=1 timeout 300 python -m pytest tests/test_gpu_train.py -m gpu -q -k "wgrad_conv3x3_tcgen05" 2>&1 | tail -3; CCVPE_WGRAD_HALO=0 timeout 300 python -m pytest tests/test_gpu_train.py -m gpu -q -k "wgrad_conv3x3_tcgen05" 2>&1 | tail -3;;
     *) echo "unknown step $w";;
   esac
