@@ -23,6 +23,7 @@ for w in $what; do
     profile_train) timeout 600 python scripts/profile_train.py > gpurun_out/${tag}_profile_train.txt 2>&1; head -40 gpurun_out/${tag}_profile_train.txt | cut -c1-200;;
     bench_dw) timeout 300 python scripts/bench_dwconv.py fast > gpurun_out/${tag}_bench_dw.txt 2>&1; tail -2 gpurun_out/${tag}_bench_dw.txt;;
     igemm_halo) for h in 1 0; do CCVPE_IGEMM_HALO=$h timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_train.py -m gpu -q -k "conv3x3 or deconv or training_step_bf16" 2>&1 | tail -4; done;;
+    ncu_igemm_halo) timeout 600 ncu --set full --clock-control none --import-source on -k regex:igemm_tcgen05 -s 6 -c 1 -o gpurun_out/${tag}_prof_igemm_halo python scripts/bench_igemm.py conv 16 160 40 160 64 > gpurun_out/${tag}_ncu_igemm_halo.log 2>&1; tail -3 gpurun_out/${tag}_ncu_igemm_halo.log | cut -c1-200;;
     wgrad_halo) CCVPE_WGRAD_HALO=1 timeout 300 python -m pytest tests/test_gpu_train.py -m gpu -q -k "wgrad_conv3x3_tcgen05" 2>&1 | tail -3; CCVPE_WGRAD_HALO=0 timeout 300 python -m pytest tests/test_gpu_train.py -m gpu -q -k "wgrad_conv3x3_tcgen05" 2>&1 | tail -3;;
     *) echo "unknown step $w";;
   esac

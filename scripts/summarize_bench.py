@@ -4,12 +4,12 @@ import os
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 RUNS = [
-    ("vigor_b64 (default workload), 1 GPU", "r02v_bench.json"),
-    ("kitti_b32, 1 GPU", "r02v_bench_kitti_b32.json"),
-    ("vigor_prior72_fov180, 1 GPU", "r02v_bench_vigor_prior72_fov180.json"),
-    ("vigor_prior72_fov108, 1 GPU", "r02v_bench_vigor_prior72_fov108.json"),
-    ("oxford_b1 (batch-1 sequential frames), 1 GPU", "r02v_bench_oxford_b1.json"),
-    ("train, B=8 bf16, one CUDA graph per step, 1 GPU", "r02v_bench_train.json"),
+    ("vigor_b64 (default workload), 1 GPU", "r02x_bench.json"),
+    ("kitti_b32, 1 GPU", "r02x_bench_kitti_b32.json"),
+    ("vigor_prior72_fov180, 1 GPU", "r02x_bench_vigor_prior72_fov180.json"),
+    ("vigor_prior72_fov108, 1 GPU", "r02x_bench_vigor_prior72_fov108.json"),
+    ("oxford_b1 (batch-1 sequential frames), 1 GPU", "r02x_bench_oxford_b1.json"),
+    ("train, B=8 bf16, one CUDA graph per step, 1 GPU", "r02x_bench_train.json"),
     ("train, B=8 fp32 parity path (eager), 1 GPU", "r02f_bench_train_fp32.json"),
     ("2 GPUs, weak (64 pairs per GPU)", "r02m_n2_weak.json"),
     ("2 GPUs, strong (one batch of 64)", "r02m_n2_strong.json"),
