@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = (
     "ccvpe_grd_descriptor", "ccvpe_grd_descriptors", "ccvpe_igemm", "ccvpe_igemm_plan", "ccvpe_match_scratch_elems", "ccvpe_match_plan", "ccvpe_match_level",
     "ccvpe_softmax_scratch_elems", "ccvpe_softmax_heatmap", "ccvpe_ori_normalize",
     "ccvpe_pose_scratch_bytes", "ccvpe_pose_decode", "ccvpe_bias_silu_nhwc", "ccvpe_dwconv_bias_silu_nhwc",
-    "ccvpe_pointwise_silu_nhwc", "ccvpe_stem_conv_silu_nhwc", "ccvpe_se_gate_scale",
+    "ccvpe_pointwise_silu_nhwc", "ccvpe_stem_conv_silu_nhwc", "ccvpe_se_gate_scale", "ccvpe_mbconv_project_nhwc",
     "ccvpe_wrap_columns_nhwc",
     "ccvpe_ingest_u8", "ccvpe_stem_conv_silu_u8_nhwc",
     # training step (config 5)
@@ -146,6 +146,8 @@ def load() -> C.CDLL:
                                                  C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.ccvpe_se_gate_scale.restype = C.c_int
     lib.ccvpe_se_gate_scale.argtypes = [C.c_void_p, C.c_float] + [C.c_void_p] * 6 + [C.c_int] * 4 + [C.c_void_p]
+    lib.ccvpe_mbconv_project_nhwc.restype = C.c_int
+    lib.ccvpe_mbconv_project_nhwc.argtypes = [C.c_void_p] * 6 + [C.c_int] * 4 + [C.c_void_p]
     lib.ccvpe_wrap_columns_nhwc.restype = C.c_int
     lib.ccvpe_wrap_columns_nhwc.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.ccvpe_ingest_u8.restype = C.c_int
@@ -489,6 +491,31 @@ def se_gate_scale(chan_sum: torch.Tensor, inv_hw: float, w_red: torch.Tensor, b_
         raise CcvpeError("se_gate_scale: shape / dtype mismatch")
     _check(load().ccvpe_se_gate_scale(_ptr(chan_sum), C.c_float(inv_hw), _ptr(w_red), _ptr(b_red), _ptr(w_se), _ptr(b_se),
                                       _ptr(w_proj), _ptr(wg), B, mid, R, cout, _stream()), "ccvpe_se_gate_scale")
+
+
+def mbconv_project_nhwc(d: torch.Tensor, wg: torch.Tensor, residual: Optional[torch.Tensor], out: torch.Tensor,
+                        bias: Optional[torch.Tensor] = None, out_biased: Optional[torch.Tensor] = None):
+    """out[b] = d[b] @ wg[b]^T (+ residual[b]); optionally out_biased = out + bias (the decoder's skip copy).
+    d: contiguous bf16 [B, HW, mid] (or [B, H, W, mid]); wg: [B, cout, mid]; residual / out / out_biased: [B, HW, cout]
+    (or [B, H, W, cout]); bias: [cout]."""
+    _require_cuda(d, wg, out)
+    B, cout, mid = wg.shape
+    tensors = [d, wg, out] + [t for t in (residual, bias, out_biased) if t is not None]
+    for t in tensors:
+        if t.dtype != torch.bfloat16 or not t.is_contiguous():
+            raise CcvpeError("mbconv_project_nhwc: operands must be contiguous bf16")
+    if d.shape[0] != B or d.shape[-1] != mid or d.numel() % (B * mid) != 0:
+        raise CcvpeError("mbconv_project_nhwc: d must be [B, HW, mid]")
+    HW = d.numel() // (B * mid)
+    for t in (residual, out, out_biased):
+        if t is not None and (t.shape[0] != B or t.shape[-1] != cout or t.numel() != B * HW * cout):
+            raise CcvpeError("mbconv_project_nhwc: residual / out / out_biased must be [B, HW, cout]")
+    if out_biased is not None and (bias is None or bias.numel() != cout):
+        raise CcvpeError("mbconv_project_nhwc: out_biased needs a bias of cout elements")
+    _check(load().ccvpe_mbconv_project_nhwc(_ptr(d), _ptr(wg), _ptr(residual) if residual is not None else None,
+                                            _ptr(bias) if bias is not None else None, _ptr(out),
+                                            _ptr(out_biased) if out_biased is not None else None, B, HW, mid, cout,
+                                            _stream()), "ccvpe_mbconv_project_nhwc")
 
 
 def wrap_columns_nhwc(buf: torch.Tensor, H: int, W: int, pad_lo: int, pad_hi: int):

@@ -20,6 +20,7 @@ constexpr int RING_EPI_THREADS = 128;
 constexpr int RING_MAX_DEPTH = 8;
 constexpr int RING_HALO_W = TC_BM + 2;
 constexpr int RING_SMEM_BUDGET = 208 * 1024;
+constexpr int RING_MAX_STEPS = 4;     // K16 slices per tap of the unrolled issue path (4 x 16 = 64 padded input channels)
 
 struct RingParams {
   CUtensorMap tm_a0, tm_a1, tm_b0, tm_b1;
@@ -29,20 +30,21 @@ struct RingParams {
   int a_blk0, a_blk1, row_bytes;      // ring slot geometry
   int w_blk0, w_blk1, w_tap_bytes;    // resident weight geometry
   int tx_row, tx_weights;
+  // Unrolled issue path (NS > 0): one entry per K16 slice of a tap, precomputed on the host so that the single MMA-issuing
+  // thread forms every descriptor with one add from the constant bank: descriptor high word (swizzle mode + group stride),
+  // A offset of (slice, dx) inside a ring row and B offset of (tap, slice) inside the resident weights, all in 16-byte
+  // descriptor units.
+  int n_steps;
+  uint32_t st_hi[RING_MAX_STEPS], st_adx[RING_MAX_STEPS][3], st_wt[9][RING_MAX_STEPS];
   EpiParams e;
 };
 
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
-          dst),
-      "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
 
 // STAGE_OUT: bf16 rows leave through per-warp staging tiles (tiles of >= 32 columns; for 16-column tiles the direct
 // 32-byte stores measure faster, and compiling both paths into one kernel spills).
-template <int MODE, bool HAS_R1, bool OUT_F32, bool STAGE_OUT>
+// NS > 0: the layer's taps have exactly NS K16 slices and the MMA issue sequence of an output row is straight-line code
+// (see the issuer below); NS == 0: generic loops.
+template <int MODE, bool HAS_R1, bool OUT_F32, bool STAGE_OUT, int NS = 0>
 __global__ void __launch_bounds__(RING_THREADS, 3) conv_ring_tcgen05_kernel(const __grid_constant__ RingParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[RING_MAX_DEPTH];
@@ -199,7 +201,32 @@ __global__ void __launch_bounds__(RING_THREADS, 3) conv_ring_tcgen05_kernel(cons
           mbar_wait(bar_te0 + 8u * acc, (((uint32_t)it >> 1) & 1u) ^ 1u);
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + acc * (uint32_t)p.block_n;
-          if (simple) {
+          if (NS > 0) {
+            // Measured (ncu source view of the generic loop on the 40 -> 40 level-2 conv): the issuing warp executed 465
+            // instructions per output row for 27 MMAs and was never waiting -- its own instruction stream was the
+            // kernel's clock (3000 cycles per row).  Here the (dy, slice, dx) nest is fully unrolled and every
+            // descriptor is one add of a constant-bank entry to a per-row base.
+            if (elect_one()) {
+              uint32_t accumulate = 0;
+#pragma unroll
+              for (int dy = 0; dy < 3; ++dy) {
+                const int sl = dy == 0 ? s_prev : (dy == 1 ? s_cur : s_next);
+                if (sl >= 0) {
+                  const uint32_t a_row = ring16 + (uint32_t)sl * row16;
+#pragma unroll
+                  for (int j = 0; j < NS; ++j) {
+                    const uint64_t hi = (uint64_t)p.st_hi[j] << 32;
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) {
+                      umma_bf16(tmem_d, hi | (a_row + p.st_adx[j][dx]), hi | (w16 + p.st_wt[dy * 3 + dx][j]), idesc, accumulate);
+                      accumulate = 1;
+                    }
+                  }
+                }
+              }
+            }
+            __syncwarp();
+          } else if (simple) {
             // one 16-channel K block (the 512^2 level): nine MMAs, every descriptor word precomputed
             if (elect_one()) {
               uint32_t accumulate = 0;
@@ -340,6 +367,28 @@ static bool ring_plan(const ccvpe_igemm_desc& d, RingParams* p) {
   p->w_blk0 = round1k(p->block_n * p->kw0 * 2);
   p->w_blk1 = round1k(p->block_n * p->kw1 * 2);
   p->w_tap_bytes = p->nb0 * p->w_blk0 + p->nb1 * p->w_blk1;
+  {
+    int j = 0;
+    uint32_t ao = 0, wo = 0;
+    bool fits = true;
+    for (int g = 0; g < p->nb0 + p->nb1 && fits; ++g) {
+      const bool s1 = g >= p->nb0;
+      const int kw = s1 ? p->kw1 : p->kw0, cb = s1 ? g - p->nb0 : g, c = s1 ? d.c1 : d.c0, nb = s1 ? p->nb1 : p->nb0;
+      const int nk16 = (cb == nb - 1) ? (c - cb * kw + 15) / 16 : kw / 16;
+      for (int k = 0; k < nk16; ++k, ++j) {
+        if (j >= RING_MAX_STEPS) {
+          fits = false;
+          break;
+        }
+        p->st_hi[j] = (uint32_t)(make_smem_desc(0, kw) >> 32);
+        for (int dx = 0; dx < 3; ++dx) p->st_adx[j][dx] = ((ao + 32u * k) >> 4) + (uint32_t)dx * ((uint32_t)(kw * 2) >> 4);
+        for (int t = 0; t < 9; ++t) p->st_wt[t][j] = ((uint32_t)t * (uint32_t)p->w_tap_bytes + wo + 32u * k) >> 4;
+      }
+      ao += s1 ? p->a_blk1 : p->a_blk0;
+      wo += s1 ? p->w_blk1 : p->w_blk0;
+    }
+    p->n_steps = fits ? j : 0;
+  }
   p->tx_row = (p->nb0 * p->kw0 + p->nb1 * p->kw1) * RING_HALO_W * 2;
   p->tx_weights = 9 * (p->nb0 * p->kw0 + p->nb1 * p->kw1) * p->block_n * 2;
   const int avail = RING_SMEM_BUDGET - 9 * p->w_tap_bytes;
@@ -419,8 +468,25 @@ int conv_ring_tcgen05(const ccvpe_igemm_desc& d, cudaStream_t st) {
     if (stage_out) conv_ring_tcgen05_kernel<MODE, R1, F32, !(F32) && MODE != 2><<<grid, RING_THREADS, smem, st>>>(p); \
     else conv_ring_tcgen05_kernel<MODE, R1, F32, false><<<grid, RING_THREADS, smem, st>>>(p);                     \
   } while (0)
+#define CCVPE_LAUNCH_RING_NS(NSV)                                                                                \
+  do {                                                                                                           \
+    static thread_local uint64_t attr = 0;                                                                       \
+    if (first_use_on_device(attr))                                                                               \
+      attr_err = cudaFuncSetAttribute(conv_ring_tcgen05_kernel<0, false, false, true, NSV>,                      \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, RING_SMEM_BUDGET + 2048);     \
+    conv_ring_tcgen05_kernel<0, false, false, true, NSV><<<grid, RING_THREADS, smem, st>>>(p);                    \
+  } while (0)
   const bool stage_out = ring_stages_output(d);
-  CCVPE_EPI_SWITCH(epi_variant(p.e), CCVPE_LAUNCH_RING)
+  // the plain bf16 channels-last convs with 2..4 K16 slices per tap (levels 2 and 3) take the unrolled issue path
+  static const bool unroll_off = getenv("CCVPE_RING_UNROLL") && atoi(getenv("CCVPE_RING_UNROLL")) == 0;   // development switch
+  if (!unroll_off && epi_variant(p.e) == 0 && stage_out && p.n_steps >= 2 && p.n_steps <= 4) {
+    if (p.n_steps == 2) CCVPE_LAUNCH_RING_NS(2);
+    else if (p.n_steps == 3) CCVPE_LAUNCH_RING_NS(3);
+    else CCVPE_LAUNCH_RING_NS(4);
+  } else {
+    CCVPE_EPI_SWITCH(epi_variant(p.e), CCVPE_LAUNCH_RING)
+  }
+#undef CCVPE_LAUNCH_RING_NS
 #undef CCVPE_LAUNCH_RING
   if (attr_err != cudaSuccess) return fail(CCVPE_ERR_CUDA, "cudaFuncSetAttribute(ring): %s", cudaGetErrorString(attr_err));
   return check_launch("conv_ring_tcgen05_kernel");

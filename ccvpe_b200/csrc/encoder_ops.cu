@@ -306,6 +306,232 @@ dwconv_bias_silu_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_sb, int64
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Stride-1 depthwise convolution, shared-memory tiled version (same arithmetic and summation order as the kernel above,
+// so y is bit-identical to it).  The streaming kernel above is bound by load latency at 128 registers per thread and
+// by the LSU (every input vector is fetched K times, every fp32 weight vector once per four outputs); here
+//   * a persistent CTA walks (image, 64-channel block, spatial tile) work items; the haloed input tile and the tile's
+//     K*K x 64 bf16 weights arrive through cp.async into one of two stages, so the next item's loads are in flight during
+//     the current item's arithmetic and cost no registers;
+//   * a thread owns 4 channels (8-byte shared loads: the 16 lanes of a half warp read one pixel's 128 bytes, conflict
+//     free) and a 2 x 8 output micro tile: (K+1) x (K+7) input vectors and K*K packed weights feed 16 outputs, i.e.
+//     7.6 (5x5) shared loads per output instead of 22.5 -- the FMA pipe, not the LSU, is the limit.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int DWT_THREADS = 256;
+constexpr int DWT_CB = 64;          // channels per work item
+constexpr int DWT_PT = 16;          // pixel threads per work item (x 16 channel lanes = 256 threads)
+constexpr int DWT_TW = 8, DWT_TH = 2;
+constexpr int DWT_SCRATCH = DWT_PT * DWT_CB * 4;      // per-thread channel sums of one item
+constexpr int DWT_STAGE_LIMIT = 55 * 1024;
+
+struct DwTileParams {
+  const __nv_bfloat16* x;
+  int64_t x_sb, x_sh, x_sw;
+  int Hp, Wp;
+  const __nv_bfloat16* w;
+  const __nv_bfloat16* bias;
+  __nv_bfloat16* y;
+  int Ho, Wo, C;
+  int ptw, pth, otw, oth, itw, ith;
+  int tiles_w, tiles_h, cblocks, total_items, stage_bytes;
+  long long* chan_sum;
+};
+
+__device__ __forceinline__ void dwt_cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ uint2 dwt_lds64(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+
+template <int K>
+__global__ void __launch_bounds__(DWT_THREADS, 2) dwconv_tile_kernel(const __grid_constant__ DwTileParams p) {
+  constexpr int TW = DWT_TW, TH = DWT_TH, IW = TW + K - 1, IH = TH + K - 1;
+  extern __shared__ __align__(128) uint8_t dwt_smem[];
+  float* s_part = reinterpret_cast<float*>(dwt_smem);
+  const uint32_t stage0 = (uint32_t)__cvta_generic_to_shared(dwt_smem) + DWT_SCRATCH;
+  const int tid = threadIdx.x;
+  const int cg = tid & 15, pt = tid >> 4;
+  const int pw = pt % p.ptw, ph = pt / p.ptw;
+  const int n_pix = p.ith * p.itw;
+
+  auto decode = [&](int item, int& tw_i, int& th_i, int& cb, int& b) {
+    tw_i = item % p.tiles_w;
+    item /= p.tiles_w;
+    th_i = item % p.tiles_h;
+    item /= p.tiles_h;
+    cb = item % p.cblocks;
+    b = item / p.cblocks;
+  };
+  // loads of one work item: thread = (16-byte chunk of the pixel's 128 bytes, every 32nd pixel)
+  auto issue = [&](int item, int stage) {
+    int tw_i, th_i, cb, b;
+    decode(item, tw_i, th_i, cb, b);
+    const int c0 = cb * DWT_CB;
+    const int nch = min(8, (p.C - c0) >> 3);
+    const int ch = tid & 7;
+    if (ch < nch) {
+      const uint32_t sw = stage0 + (uint32_t)(stage * p.stage_bytes), sx = sw + K * K * 128;
+      const __nv_bfloat16* xb = p.x + (int64_t)b * p.x_sb + c0 + ch * 8;
+      const int gh0 = th_i * p.oth, gw0 = tw_i * p.otw;
+      int pix = tid >> 3;
+      int ih = pix / p.itw, iw = pix - ih * p.itw;
+      for (; pix < n_pix; pix += 32) {
+        // (rows / columns past the padded image only feed outputs that are never stored: clamp to stay in bounds)
+        const int gh = min(gh0 + ih, p.Hp - 1), gw = min(gw0 + iw, p.Wp - 1);
+        dwt_cp_async16(sx + (uint32_t)pix * 128u + (uint32_t)ch * 16u, xb + gh * p.x_sh + gw * p.x_sw);
+        iw += 32;
+        while (iw >= p.itw) {
+          iw -= p.itw;
+          ++ih;
+        }
+      }
+      for (int tap = tid >> 3; tap < K * K; tap += 32)
+        dwt_cp_async16(sw + (uint32_t)tap * 128u + (uint32_t)ch * 16u, p.w + (int64_t)tap * p.C + c0 + ch * 8);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  int item = blockIdx.x;
+  if (item < p.total_items) issue(item, 0);
+  for (int it = 0; item < p.total_items; item += gridDim.x, ++it) {
+    const int nxt = item + gridDim.x;
+    if (nxt < p.total_items) {
+      issue(nxt, (it + 1) & 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    int tw_i, th_i, cb, b;
+    decode(item, tw_i, th_i, cb, b);
+    const int c0 = cb * DWT_CB;
+    const bool active = (c0 + cg * 4 < p.C) && ph < p.pth;
+    float csum[4] = {0.f, 0.f, 0.f, 0.f};
+    if (active) {
+      const uint32_t sw = stage0 + (uint32_t)((it & 1) * p.stage_bytes) + (uint32_t)cg * 8u;
+      const uint32_t sx = sw + K * K * 128 + (uint32_t)((ph * TH) * p.itw + pw * TW) * 128u;
+      const uint32_t row_pitch = (uint32_t)p.itw * 128u;
+      uint64_t bv[2];
+      {
+        const uint2 bq = __ldg(reinterpret_cast<const uint2*>(p.bias + c0 + cg * 4));
+        bv[0] = bf16x2_to_f32x2(bq.x);
+        bv[1] = bf16x2_to_f32x2(bq.y);
+      }
+      uint64_t acc[TH][TW][2];
+#pragma unroll
+      for (int r = 0; r < TH; ++r)
+#pragma unroll
+        for (int t = 0; t < TW; ++t) {
+          acc[r][t][0] = bv[0];
+          acc[r][t][1] = bv[1];
+        }
+#pragma unroll
+      for (int ir = 0; ir < IH; ++ir) {
+        uint2 xin[IW];
+#pragma unroll
+        for (int ix = 0; ix < IW; ++ix) xin[ix] = dwt_lds64(sx + (uint32_t)ir * row_pitch + (uint32_t)ix * 128u);
+        uint64_t xf[IW][2];
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) {
+#pragma unroll
+          for (int t = 0; t < TW; ++t)
+            if (kx == 0 || t == TW - 1) {              // first use of input column t + kx
+              xf[t + kx][0] = bf16x2_to_f32x2(xin[t + kx].x);
+              xf[t + kx][1] = bf16x2_to_f32x2(xin[t + kx].y);
+            }
+#pragma unroll
+          for (int r = 0; r < TH; ++r) {
+            const int ky = ir - r;                     // input row ir is row ky of output row r's window
+            if (ky >= 0 && ky < K) {
+              const uint2 wq = dwt_lds64(sw + (uint32_t)(ky * K + kx) * 128u);
+              const uint64_t w0 = bf16x2_to_f32x2(wq.x), w1 = bf16x2_to_f32x2(wq.y);
+#pragma unroll
+              for (int t = 0; t < TW; ++t) {
+                acc[r][t][0] = ffma2(xf[t + kx][0], w0, acc[r][t][0]);
+                acc[r][t][1] = ffma2(xf[t + kx][1], w1, acc[r][t][1]);
+              }
+            }
+          }
+        }
+      }
+      const int ho0 = th_i * p.oth + ph * TH, wo0 = tw_i * p.otw + pw * TW;
+#pragma unroll
+      for (int r = 0; r < TH; ++r) {
+        const int ho = ho0 + r;
+        if (ho < p.Ho) {
+          __nv_bfloat16* yrow = p.y + (((int64_t)b * p.Ho + ho) * p.Wo) * p.C + c0 + cg * 4;
+#pragma unroll
+          for (int t = 0; t < TW; ++t) {
+            const int wo = wo0 + t;
+            if (wo < p.Wo) {
+              uint2 q;
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                float a0, a1;
+                unpack_f32x2(acc[r][t][j], a0, a1);
+                a0 *= 0.5f;                             // SiLU(a) = h + h * tanh(h), h = a / 2 (one MUFU)
+                a1 *= 0.5f;
+                a0 = fmaf(a0, dw_tanh(a0), a0);
+                a1 = fmaf(a1, dw_tanh(a1), a1);
+                h[j] = __floats2bfloat162_rn(a0, a1);
+                const float2 rr = __bfloat1622float2(h[j]);
+                csum[2 * j] += rr.x;
+                csum[2 * j + 1] += rr.y;
+              }
+              *reinterpret_cast<uint2*>(yrow + (int64_t)wo * p.C) = q;
+            }
+          }
+        }
+      }
+    }
+    if (p.chan_sum) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s_part[pt * DWT_CB + cg * 4 + j] = csum[j];
+    }
+    __syncthreads();   // the stage is free for the item after next; the per-thread sums are visible
+    if (p.chan_sum && tid < DWT_CB && c0 + tid < p.C) {
+      // fixed-order fp32 fold of the 16 pixel threads, then one order-independent fixed-point atomic per (item, channel)
+      float tot = 0.f;
+#pragma unroll
+      for (int l = 0; l < DWT_PT; ++l) tot += s_part[l * DWT_CB + tid];
+      atomicAdd(reinterpret_cast<unsigned long long*>(p.chan_sum) + (int64_t)b * p.C + c0 + tid, se_fixed(tot));
+    }
+  }
+}
+
+// picks the micro-tile arrangement (ptw x pth pixel threads, each 2 rows x 8 columns) of the tiled kernel; false if no
+// arrangement fits the stage budget
+static bool dwt_plan(int K, int Ho, int Wo, int C, int B, DwTileParams* p) {
+  double best = 1e30;
+  bool found = false;
+  for (int ptw = 1; ptw <= DWT_PT; ++ptw) {
+    const int pth = DWT_PT / ptw;
+    const int otw = ptw * DWT_TW, oth = pth * DWT_TH;
+    const int itw = otw + K - 1, ith = oth + K - 1;
+    const int stage = (K * K + ith * itw) * 128;
+    if (stage > DWT_STAGE_LIMIT) continue;
+    const int tiles_w = (Wo + otw - 1) / otw, tiles_h = (Ho + oth - 1) / oth;
+    // cost of the layer ~ items x (bytes staged + the fixed arithmetic of a full item)
+    const double cost = (double)tiles_w * tiles_h * (ith * itw + 2.0 * DWT_PT * DWT_TW * DWT_TH);
+    if (cost < best) {
+      best = cost;
+      found = true;
+      p->ptw = ptw; p->pth = pth; p->otw = otw; p->oth = oth; p->itw = itw; p->ith = ith;
+      p->tiles_w = tiles_w; p->tiles_h = tiles_h; p->stage_bytes = stage;
+    }
+  }
+  if (!found) return false;
+  p->cblocks = (C + DWT_CB - 1) / DWT_CB;
+  const int64_t total = (int64_t)p->tiles_w * p->tiles_h * p->cblocks * B;
+  if (total > (1LL << 30)) return false;
+  p->total_items = (int)total;
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Encoder stem: 3x3 stride-2 convolution over the fp32 NCHW image (3 channels, TensorFlow-"same" zero padding, optionally
 // circular along the width for panoramas) + folded-BN bias + SiLU, written as bf16 channels-last into the interior of the
 // first depthwise convolution's padded input image (wrap columns included for the circular encoder).  Replaces: dtype /
@@ -643,6 +869,32 @@ extern "C" int ccvpe_dwconv_bias_silu_nhwc(const void* x, int64_t x_sb, int64_t 
   CCVPE_REQUIRE(x_sb % 8 == 0 && x_sh % 8 == 0 && x_sw % 8 == 0, "ccvpe_dwconv_bias_silu_nhwc: input strides must be multiples of 8");
   CCVPE_REQUIRE(x_sw > 0 && x_sw * 16 < (1LL << 31), "ccvpe_dwconv_bias_silu_nhwc: pixel stride out of range");
   const int Ho = (Hp - K) / S + 1, Wo = (Wp - K) / S + 1;
+  // Measured per layer (B=64, scripts/bench_dwconv.py): the tiled kernel wins wherever the window is 5x5 (1.2-1.5x) and
+  // for the deep 3x3 layers (>= 240 channels); the shallow 3x3 layers (32 / 144 channels on large images) stay on the
+  // streaming kernel.  CCVPE_DW_TILED = 0 / 2 forces streaming / tiled (development switch).
+  static const int use_tiled = getenv("CCVPE_DW_TILED") ? atoi(getenv("CCVPE_DW_TILED")) : 1;
+  if (S == 1 && (use_tiled == 2 || (use_tiled == 1 && (K == 5 || C >= 240)))) {
+    DwTileParams tp;
+    memset(&tp, 0, sizeof(tp));
+    if (dwt_plan(K, Ho, Wo, C, B, &tp)) {
+      tp.x = (const __nv_bfloat16*)x; tp.x_sb = x_sb; tp.x_sh = x_sh; tp.x_sw = x_sw; tp.Hp = Hp; tp.Wp = Wp;
+      tp.w = (const __nv_bfloat16*)w; tp.bias = (const __nv_bfloat16*)bias; tp.y = (__nv_bfloat16*)y;
+      tp.Ho = Ho; tp.Wo = Wo; tp.C = C;
+      tp.chan_sum = reinterpret_cast<long long*>(chan_sum);
+      const int smem = DWT_SCRATCH + 2 * tp.stage_bytes;
+      static thread_local uint64_t tiled_attr = 0;
+      if (first_use_on_device(tiled_attr)) {
+        cudaFuncSetAttribute(dwconv_tile_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, DWT_SCRATCH + 2 * DWT_STAGE_LIMIT);
+        cudaFuncSetAttribute(dwconv_tile_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, DWT_SCRATCH + 2 * DWT_STAGE_LIMIT);
+      }
+      const int max_grid = 2 * sm_count();
+      const int grid = tp.total_items < max_grid ? tp.total_items : max_grid;
+      if (K == 3) dwconv_tile_kernel<3><<<grid, DWT_THREADS, smem, (cudaStream_t)stream>>>(tp);
+      else dwconv_tile_kernel<5><<<grid, DWT_THREADS, smem, (cudaStream_t)stream>>>(tp);
+      CCVPE_LAUNCH_CHECK("dwconv_tile_kernel");
+      return CCVPE_OK;
+    }
+  }
   // V = channels per thread
   static const int force_v = getenv("CCVPE_DW_V") ? atoi(getenv("CCVPE_DW_V")) : 0;
   const int V = force_v ? force_v : 8;   // (measured: 4 channels per thread gains nothing, the loop is issue-bound)

@@ -74,6 +74,13 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm,
       ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          dst),
+      "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
@@ -113,7 +120,7 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 // K-major swizzled shared-memory matrix descriptor.  A K block of kw bf16 channels is one swizzle row of 2*kw bytes
 // (kw = 64 -> SWIZZLE_128B, 32 -> SWIZZLE_64B, 16 -> SWIZZLE_32B); 8 rows form a group, groups are 16*kw bytes apart.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, int kw) {
+__host__ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, int kw) {
   const uint64_t layout = kw == 64 ? 2 : (kw == 32 ? 4 : 6);
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);  // start address, 16-byte units
@@ -455,7 +462,14 @@ inline int encode_map(CUtensorMap* tm, const void* base, int rank, const uint64_
 // K-block width (bf16 channels) used for a source with c channels; one block is one swizzle row of 2*width bytes.
 // Narrow sources get narrow blocks so TMA neither over-fetches nor zero-fills most of the tile (include/ccvpe_b200.h
 // documents the same rule for the w_nk weight layout).
-inline int tc_block_width(int c) { return c <= 16 ? 16 : (c < 64 ? 32 : 64); }
+// 33..63 channels take ONE 64-wide block rather than two 32-wide ones: the padded K extent (64), the shared-memory
+// footprint and the number of K16 MMA slices are the same, but TMA walks half as many box rows (its cost is per box row).
+inline int tc_block_width(int c) {
+  static const bool old_rule = getenv("CCVPE_KW_OLD") != nullptr;   // development switch: A/B against the round-1 rule
+  return c <= 16 ? 16 : (c < (old_rule ? 64 : 33) ? 32 : 64);
+}
+// the matching kernel's norm warps were tuned against the original rule
+inline int tc_block_width_match(int c) { return c <= 16 ? 16 : (c < 64 ? 32 : 64); }
 
 inline void fill_epi(EpiParams& e, const ccvpe_igemm_desc& d) {
   e.N = d.N;

@@ -256,6 +256,16 @@ class FastEncoder:
                 sq = (sums / float(Ho * Wo)).to(dt)                                  # [B, mid]
                 g = torch.sigmoid(F.linear(F.silu(F.linear(sq, o.w_red, o.b_red)), o.w_se, o.b_se))   # [B, mid]
                 wg = o.w_proj.unsqueeze(0) * g.unsqueeze(1)                          # [B, cout, mid]
+            if fused_dw:
+                # batched per-image-weight GEMM on tcgen05: the identity skip is added in the epilogue, and the copy the
+                # decoder reads (cur + pending bias) is a second output of the same pass
+                cur = torch.empty((Bo, Ho, Wo, o.cout), dtype=dt, device=d.device)
+                want = keep_blocks and len(outs) in self.keep
+                kept = torch.empty_like(cur) if want else None
+                cabi.mbconv_project_nhwc(d, wg, block_in if o.residual else None, cur, o.b_proj if want else None, kept)
+                if keep_blocks:
+                    outs.append(kept.permute(0, 3, 1, 2) if want else None)
+                continue
             dm = d.reshape(Bo, Ho * Wo, o.mid)
             if o.residual:                                                           # residual add = beta 1 of the GEMM
                 y = torch.baddbmm(block_in.reshape(Bo, Ho * Wo, o.cout), dm, wg.transpose(1, 2))

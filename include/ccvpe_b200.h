@@ -226,6 +226,16 @@ int ccvpe_se_gate_scale(const int64_t* chan_sum, float inv_hw, const void* w_red
 int ccvpe_pointwise_silu_nhwc(const void* x, int B, int H, int W, int K, int ldx, const void* w_nk, const float* bias,
                               int N, void* out, int pad_lo, int pad_hi, void* stream);
 
+/* f2  MBConv projection -- reference efficientnet_pytorch/model.py:115-131 (squeeze-excite multiply, _project_conv + _bn2,
+ * identity skip), batched over images because the gate is folded into PER-IMAGE weights wg = W_proj . diag(gate[b])
+ * (ccvpe_se_gate_scale):
+ *   out[b, p, n] = sum_k d[b, p, k] * wg[b, n, k]  (+ residual[b, p, n])          fp32 accumulation, rounded once to bf16
+ *   out_biased[b, p, n] = bf16(out[b, p, n]) + bias[n]                              (optional; the decoder's skip tensor)
+ * d: bf16 [B, HW, mid]; wg: bf16 [B, cout, mid]; residual: bf16 [B, HW, cout] or NULL; bias: bf16 [cout] (required iff
+ * out_biased); out / out_biased: bf16 [B, HW, cout].  mid % 8 == cout % 8 == 0; all pointers 16-byte aligned. */
+int ccvpe_mbconv_project_nhwc(const void* d, const void* wg, const void* residual, const void* bias, void* out,
+                              void* out_biased, int B, int HW, int mid, int cout, void* stream);
+
 /* f4  Input pipeline after image decoding -- reference train_VIGOR.py:55-70 (ToTensor + Normalize), datasets.py:118
  * (random panorama roll: torch.roll(grd, shift, dims=2)), train_VIGOR.py:272-273 (limited-FoV crop of the panorama):
  *   dst[b, c, h, w] = (src[b, c, h, (w - shift[b]) mod W] / 255 - mean[c]) / std[c]        for w < crop_w

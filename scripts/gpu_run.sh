@@ -24,6 +24,14 @@ for w in $what; do
     bench_dw) timeout 300 python scripts/bench_dwconv.py fast > gpurun_out/${tag}_bench_dw.txt 2>&1; tail -2 gpurun_out/${tag}_bench_dw.txt;;
     igemm_halo) for h in 1 0; do CCVPE_IGEMM_HALO=$h timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_train.py -m gpu -q -k "conv3x3 or deconv or training_step_bf16" 2>&1 | tail -4; done;;
     ncu_igemm_halo) timeout 600 ncu --set full --clock-control none --import-source on -k regex:igemm_tcgen05 -s 6 -c 1 -o gpurun_out/${tag}_prof_igemm_halo python scripts/bench_igemm.py conv 16 160 40 160 64 > gpurun_out/${tag}_ncu_igemm_halo.log 2>&1; tail -3 gpurun_out/${tag}_ncu_igemm_halo.log | cut -c1-200;;
+    ncu_ring2b) timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_ring -s 6 -c 1 -o gpurun_out/${tag}_prof_ring2b python scripts/bench_igemm.py conv 16 40 0 40 256 > gpurun_out/${tag}_ncu_ring2b.log 2>&1; tail -3 gpurun_out/${tag}_ncu_ring2b.log | cut -c1-200;;
+    bench_ring) for a in "16 40 0 40 256" "16 40 16 40 256" "16 32 16 32 256" "16 32 0 32 256" "16 16 0 16 512" "16 80 24 80 128" "16 80 0 80 128"; do timeout 120 python scripts/bench_igemm.py conv $a 2>&1 | tail -1; done | tee gpurun_out/${tag}_bench_ring.txt;;
+    test_conv) timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q -k "conv3x3 or deconv or k2s2" 2>&1 | tail -4;;
+    test_dw) timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_fast_encoder.py -m gpu -q -k "dwconv or encoder" 2>&1 | tail -4;;
+    ring_dbg) for dbg in 0 1 2 3; do echo "dbg=$dbg"; for a in "16 40 0 40 256" "16 64 0 48 256" "16 48 0 48 256" "16 32 0 48 256" "16 16 0 48 256"; do CCVPE_RING_DBG=$dbg timeout 120 python scripts/bench_igemm.py conv $a 2>&1 | tail -1; done; done | tee gpurun_out/${tag}_ring_dbg.txt;;
+    kw_ab) for old in 1 0; do echo "CCVPE_KW_OLD=$old"; for a in "conv 16 40 0 40 256" "conv 16 40 16 40 256" "conv 16 160 40 160 64" "conv 16 48 0 48 256" "deconv 16 40 16 256"; do if [ $old = 1 ]; then CCVPE_KW_OLD=1 timeout 120 python scripts/bench_igemm.py $a 2>&1 | tail -1; else timeout 120 python scripts/bench_igemm.py $a 2>&1 | tail -1; fi; done; done | tee gpurun_out/${tag}_kw_ab.txt;;
+    probe2) timeout 120 scripts/tma_probe2.bin 2>&1 | tee gpurun_out/${tag}_tma_probe2.txt;;
+    test_proj) timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_fast_encoder.py tests/test_gpu_forward.py -m gpu -q -x -k "mbconv_project or encoder or bit_reproducible or bf16" 2>&1 | tail -6;;
     wgrad_halo) CCVPE_WGRAD_HALO=1 timeout 300 python -m pytest tests/test_gpu_train.py -m gpu -q -k "wgrad_conv3x3_tcgen05" 2>&1 | tail -3; CCVPE_WGRAD_HALO=0 timeout 300 python -m pytest tests/test_gpu_train.py -m gpu -q -k "wgrad_conv3x3_tcgen05" 2>&1 | tail -3;;
     *) echo "unknown step $w";;
   esac

@@ -526,7 +526,11 @@ def test_grd_descriptors_all_heads(cuda_device, B, H, W, cs, layout, dtype):
 
 
 @pytest.mark.parametrize("B,H,W,C,K,S", [(2, 33, 47, 96, 3, 1), (2, 32, 48, 144, 5, 2), (1, 64, 64, 32, 3, 2),
-                                         (3, 16, 16, 1152, 5, 1), (2, 17, 9, 240, 3, 1)])
+                                         (3, 16, 16, 1152, 5, 1), (2, 17, 9, 240, 3, 1),
+                                         # shared-memory tiled stride-1 kernel: half-filled / partial 64-channel blocks,
+                                         # several tiles per image with ragged right / bottom edges
+                                         (2, 64, 64, 32, 3, 1), (1, 40, 80, 144, 5, 1), (2, 20, 40, 672, 5, 1),
+                                         (1, 50, 70, 8, 5, 1), (2, 10, 20, 1152, 3, 1)])
 def test_dwconv_bias_silu_nhwc(cuda_device, B, H, W, C, K, S):
     """fused depthwise conv + bias + SiLU + SE channel sums over a pre-padded buffer vs torch (fp32 math on bf16 data)."""
     g = _gen(15)
@@ -625,6 +629,37 @@ def test_se_gate_scale(cuda_device, B, mid, R, cout):
                        w_proj.to(dev), wg)
     torch.cuda.synchronize()
     assert rel_err(wg.float(), ref) < 1e-2
+
+
+@pytest.mark.parametrize("B,HW,mid,cout,res,biased", [
+    (2, 300, 144, 24, True, True),      # several tiles per image, ragged last tile, 64 + 64 + 16 channel K blocks
+    (3, 200, 1152, 320, True, False),   # two N tiles, 18 K blocks (deeper than the stage ring)
+    (2, 130, 32, 16, False, True),      # one narrow K block (SWIZZLE_64B), no residual (first block of the encoder)
+    (1, 128, 96, 24, False, False),     # exactly one full tile
+    (2, 77, 672, 192, True, True),      # less than one tile per image
+    (5, 257, 240, 40, True, True),      # one pixel past two tiles; 48-channel tail block
+    (2, 1024, 480, 112, False, True),
+    (160, 50, 96, 16, True, False),     # more work items than SMs: persistent loop + accumulator double buffering
+])
+def test_mbconv_project_nhwc(cuda_device, B, HW, mid, cout, res, biased):
+    """batched per-image-weight projection GEMM (+ residual, + biased copy) on tcgen05 vs torch (fp32 math on bf16 data);
+    the biased copy must be exactly bf16(out) + bias as torch computes it."""
+    g = _gen(23)
+    dev = cuda_device
+    d = torch.randn(B, HW, mid, generator=g).to(torch.bfloat16)
+    wg = (torch.randn(B, cout, mid, generator=g) / math.sqrt(mid)).to(torch.bfloat16)
+    r = torch.randn(B, HW, cout, generator=g).to(torch.bfloat16) if res else None
+    bias = torch.randn(cout, generator=g).to(torch.bfloat16)
+    ref = torch.bmm(d.float(), wg.float().transpose(1, 2))
+    if res:
+        ref = ref + r.float()
+    out = torch.full((B, HW, cout), 7.0, device=dev, dtype=torch.bfloat16)
+    out2 = torch.full((B, HW, cout), 7.0, device=dev, dtype=torch.bfloat16) if biased else None
+    cabi.mbconv_project_nhwc(d.to(dev), wg.to(dev), r.to(dev) if res else None, out, bias.to(dev) if biased else None, out2)
+    torch.cuda.synchronize()
+    assert rel_err(out.float().cpu(), ref) < 1e-2
+    if biased:
+        assert torch.equal(out2, out + bias.to(dev))
 
 
 @pytest.mark.parametrize("B,H,W,C,lo,hi", [(2, 9, 20, 96, 1, 1), (1, 5, 7, 32, 2, 2), (3, 4, 16, 240, 0, 1), (2, 6, 5, 8, 1, 2)])
