@@ -34,7 +34,7 @@ struct RingParams {
   // thread forms every descriptor with one add from the constant bank: descriptor high word (swizzle mode + group stride),
   // A offset of (slice, dx) inside a ring row and B offset of (tap, slice) inside the resident weights, all in 16-byte
   // descriptor units.
-  int n_steps;
+  int n_steps, unrolled;
   uint32_t st_hi[RING_MAX_STEPS], st_adx[RING_MAX_STEPS][3], st_wt[9][RING_MAX_STEPS];
   EpiParams e;
 };
@@ -44,8 +44,10 @@ struct RingParams {
 // 32-byte stores measure faster, and compiling both paths into one kernel spills).
 // NS > 0: the layer's taps have exactly NS K16 slices and the MMA issue sequence of an output row is straight-line code
 // (see the issuer below); NS == 0: generic loops.
+// These variants also run TWO epilogue groups of four warps, one per TMEM accumulator stage (even / odd output rows): with
+// the issue stream shortened, a single group's ~340 dependent instructions per row were the next limit.
 template <int MODE, bool HAS_R1, bool OUT_F32, bool STAGE_OUT, int NS = 0>
-__global__ void __launch_bounds__(RING_THREADS, 3) conv_ring_tcgen05_kernel(const __grid_constant__ RingParams p) {
+__global__ void __launch_bounds__(NS > 0 ? RING_THREADS + RING_EPI_THREADS : RING_THREADS, NS > 0 ? 2 : 3) conv_ring_tcgen05_kernel(const __grid_constant__ RingParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[RING_MAX_DEPTH];
   __shared__ __align__(8) uint64_t bar_empty[RING_MAX_DEPTH];
@@ -58,8 +60,9 @@ __global__ void __launch_bounds__(RING_THREADS, 3) conv_ring_tcgen05_kernel(cons
   __shared__ int s_off[TC_MAX_N / 8];
   // bf16 rows leave through per-warp staging tiles (coalesced copy-out, see epi_store_row_staged)
   constexpr bool STAGED = STAGE_OUT && !OUT_F32 && MODE != 2;
-  __shared__ __align__(16) uint8_t s_stage[STAGED ? 4 * EPI_WARP_STAGE_BYTES : 16];
-  __shared__ int32_t s_rowbase[STAGED ? TC_BM : 1];
+  constexpr int EPI_GROUPS = NS > 0 ? 2 : 1;
+  __shared__ __align__(16) uint8_t s_stage[STAGED ? EPI_GROUPS * 4 * EPI_WARP_STAGE_BYTES : 16];
+  __shared__ int32_t s_rowbase[STAGED ? EPI_GROUPS * TC_BM : 1];
   __shared__ __align__(16) uint4 s_blk[4];   // per K block: descriptor offsets (16-byte units) for the MMA issuer
 
   const int warp = threadIdx.x >> 5;
@@ -297,10 +300,13 @@ __global__ void __launch_bounds__(RING_THREADS, 3) conv_ring_tcgen05_kernel(cons
     }
   } else {
     // ===================== epilogue: warps 2..5, warp w owns TMEM lanes 32*(w%4) .. +31 and all column chunks ==========
+    // (NS > 0: a second group, warps 6..9, takes the odd accumulator stage)
     const int ew = warp & 3;
+    const int grp = (warp - 2) >> 2;
+    const int ewi = warp - 2;
     const int row = ew * 32 + lane;
     const int et = threadIdx.x - 64;
-    epi_stage_vectors(p.e, s_bias, s_r1w, s_off, 0, p.block_n, et, RING_EPI_THREADS);
+    epi_stage_vectors(p.e, s_bias, s_r1w, s_off, 0, p.block_n, et, EPI_GROUPS * RING_EPI_THREADS);
     int it = 0;
     for (int unit = blockIdx.x; unit < p.total_units; unit += gridDim.x) {
       const int rc = unit % p.chunks;
@@ -309,6 +315,7 @@ __global__ void __launch_bounds__(RING_THREADS, 3) conv_ring_tcgen05_kernel(cons
       const int y0 = rc * p.R, x0 = xs * TC_BM;
       for (int yo = y0; yo < y0 + p.R; ++yo, ++it) {
         const int acc = it & 1;
+        if (EPI_GROUPS == 2 && acc != grp) continue;
         const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
         const int m_glob = (b * p.H + yo) * p.W + x0 + row;
         float rs = 1.f, r1 = 0.f;
@@ -320,7 +327,7 @@ __global__ void __launch_bounds__(RING_THREADS, 3) conv_ring_tcgen05_kernel(cons
         if (STAGED) {
           epi_store_row_staged<MODE, HAS_R1>(p.e, taddr, 0, 1, p.block_n, 0, true, epi_row_base<MODE>(p.e, m_glob), rs, r1,
                                              s_bias, s_r1w, s_off, smem_u32(&bar_tmem_empty[acc]),
-                                             s_stage + ew * EPI_WARP_STAGE_BYTES, s_rowbase + 32 * ew);
+                                             s_stage + ewi * EPI_WARP_STAGE_BYTES, s_rowbase + 32 * ewi);
         } else {
           epi_store_row<MODE, HAS_R1, OUT_F32>(p.e, taddr, 0, p.block_n, 0, true, m_glob, epi_row_base<MODE>(p.e, m_glob),
                                                rs, r1, s_bias, s_r1w, s_off, 1, smem_u32(&bar_tmem_empty[acc]));
@@ -388,19 +395,25 @@ static bool ring_plan(const ccvpe_igemm_desc& d, RingParams* p) {
       wo += s1 ? p->w_blk1 : p->w_blk0;
     }
     p->n_steps = fits ? j : 0;
+    // the plain bf16 channels-last convs with 2..4 K16 slices per tap (levels 2 and 3) take the unrolled issue path
+    static const bool unroll_off = getenv("CCVPE_RING_UNROLL") && atoi(getenv("CCVPE_RING_UNROLL")) == 0;   // development switch
+    const bool plain = d.relu != 2 && d.out_mode == 0 && d.out_dtype == CCVPE_BF16 && !d.row_r1;            // epilogue variant 0
+    p->unrolled = (!unroll_off && plain && ring_stages_output(d) && p->n_steps >= 2 && p->n_steps <= 4) ? 1 : 0;
   }
   p->tx_row = (p->nb0 * p->kw0 + p->nb1 * p->kw1) * RING_HALO_W * 2;
   p->tx_weights = 9 * (p->nb0 * p->kw0 + p->nb1 * p->kw1) * p->block_n * 2;
-  const int avail = RING_SMEM_BUDGET - 9 * p->w_tap_bytes;
+  // (the second epilogue group's staging tiles are static shared memory: 11 KB less for the ring)
+  const int avail = RING_SMEM_BUDGET - (p->unrolled ? 12 * 1024 : 0) - 9 * p->w_tap_bytes;
   if (avail < 4 * p->row_bytes) return false;
   int depth = avail / p->row_bytes;
   p->depth = depth > RING_MAX_DEPTH ? RING_MAX_DEPTH : depth;
   // prefer a shallower ring if that lets two CTAs (two MMA issuers, two producers, eight epilogue warps) share an SM:
   // the narrow levels are bound by single-thread issue latency, not by pipeline depth
   // static shared memory + alignment slack of one CTA (the bf16 variants carry the epilogue staging tiles)
-  const int static_bytes = ring_stages_output(d) ? 15 * 1024 : 4096;
+  // (the unrolled variants: two epilogue groups -> twice the staging tiles, 320 threads -> at most two CTAs per SM)
+  const int static_bytes = p->unrolled ? 28 * 1024 : (ring_stages_output(d) ? 15 * 1024 : 4096);
   bool placed = false;
-  for (int ctas = 3; ctas >= 2 && !placed; --ctas) {
+  for (int ctas = p->unrolled ? 2 : 3; ctas >= 2 && !placed; --ctas) {
     for (int dd = p->depth; dd >= 4; --dd) {
       if (ctas * (9 * p->w_tap_bytes + dd * p->row_bytes + static_bytes) <= 224 * 1024) {
         p->depth = dd;
@@ -448,9 +461,9 @@ int conv_ring_tcgen05(const ccvpe_igemm_desc& d, cudaStream_t st) {
   }
   fill_epi(p.e, d);
   const int smem = 9 * p.w_tap_bytes + p.depth * p.row_bytes + 1024;
-  int ctas_per_sm = (224 * 1024) / (smem + 3072);          // shared memory (+ static) ...
+  int ctas_per_sm = (224 * 1024) / (smem + (p.unrolled ? 26 * 1024 : 3072));   // shared memory (+ static) ...
   if (ctas_per_sm > 512 / p.tmem_cols) ctas_per_sm = 512 / p.tmem_cols;   // ... TMEM columns ...
-  if (ctas_per_sm > 3) ctas_per_sm = 3;                                  // ... registers (launch bounds: 96 regs)
+  if (ctas_per_sm > (p.unrolled ? 2 : 3)) ctas_per_sm = p.unrolled ? 2 : 3;   // ... registers / threads (launch bounds)
   if (ctas_per_sm < 1) ctas_per_sm = 1;
   const int max_grid = ctas_per_sm * sm_count();
   const int grid = p.total_units < max_grid ? p.total_units : max_grid;
@@ -473,13 +486,11 @@ int conv_ring_tcgen05(const ccvpe_igemm_desc& d, cudaStream_t st) {
     static thread_local uint64_t attr = 0;                                                                       \
     if (first_use_on_device(attr))                                                                               \
       attr_err = cudaFuncSetAttribute(conv_ring_tcgen05_kernel<0, false, false, true, NSV>,                      \
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, RING_SMEM_BUDGET + 2048);     \
-    conv_ring_tcgen05_kernel<0, false, false, true, NSV><<<grid, RING_THREADS, smem, st>>>(p);                    \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, RING_SMEM_BUDGET - 10 * 1024); \
+    conv_ring_tcgen05_kernel<0, false, false, true, NSV><<<grid, RING_THREADS + RING_EPI_THREADS, smem, st>>>(p); \
   } while (0)
   const bool stage_out = ring_stages_output(d);
-  // the plain bf16 channels-last convs with 2..4 K16 slices per tap (levels 2 and 3) take the unrolled issue path
-  static const bool unroll_off = getenv("CCVPE_RING_UNROLL") && atoi(getenv("CCVPE_RING_UNROLL")) == 0;   // development switch
-  if (!unroll_off && epi_variant(p.e) == 0 && stage_out && p.n_steps >= 2 && p.n_steps <= 4) {
+  if (p.unrolled) {
     if (p.n_steps == 2) CCVPE_LAUNCH_RING_NS(2);
     else if (p.n_steps == 3) CCVPE_LAUNCH_RING_NS(3);
     else CCVPE_LAUNCH_RING_NS(4);

@@ -32,6 +32,10 @@ for w in $what; do
     kw_ab) for old in 1 0; do echo "CCVPE_KW_OLD=$old"; for a in "conv 16 40 0 40 256" "conv 16 40 16 40 256" "conv 16 160 40 160 64" "conv 16 48 0 48 256" "deconv 16 40 16 256"; do if [ $old = 1 ]; then CCVPE_KW_OLD=1 timeout 120 python scripts/bench_igemm.py $a 2>&1 | tail -1; else timeout 120 python scripts/bench_igemm.py $a 2>&1 | tail -1; fi; done; done | tee gpurun_out/${tag}_kw_ab.txt;;
     probe2) timeout 120 scripts/tma_probe2.bin 2>&1 | tee gpurun_out/${tag}_tma_probe2.txt;;
     test_proj) timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_fast_encoder.py tests/test_gpu_forward.py -m gpu -q -x -k "mbconv_project or encoder or bit_reproducible or bf16" 2>&1 | tail -6;;
+    ncu_dwtile) timeout 600 ncu --set full --clock-control none --import-source on -k regex:dwconv_tile -s 2 -c 1 -o gpurun_out/${tag}_prof_dwtile python scripts/prof_dwconv.py > gpurun_out/${tag}_ncu_dwtile.log 2>&1; tail -3 gpurun_out/${tag}_ncu_dwtile.log | cut -c1-200;;
+    launches) CCVPE_NCU_RANGE=1 timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 1 --warmup 3 --no-cpu --no-parity --no-torch-gpu-baseline > gpurun_out/${tag}_ncu_bench.log 2>&1; python scripts/launch_shares.py gpurun_out/${tag}_launches.csv | tee gpurun_out/${tag}_launch_shares.txt | head -32;;
+    bench_pw) timeout 300 python scripts/bench_pointwise.py 64 2>&1 | tee gpurun_out/${tag}_bench_pw.txt | tail -26;;
+    ncu_pw) timeout 600 ncu --set full --clock-control none --import-source on -k regex:igemm_tcgen05 -s 2 -c 1 -o gpurun_out/${tag}_prof_pw python scripts/bench_pointwise.py 64 0 > gpurun_out/${tag}_ncu_pw.log 2>&1; tail -3 gpurun_out/${tag}_ncu_pw.log | cut -c1-200;;
     wgrad_halo) CCVPE_WGRAD_HALO=1 timeout 300 python -m pytest tests/test_gpu_train.py -m gpu -q -k "wgrad_conv3x3_tcgen05" 2>&1 | tail -3; CCVPE_WGRAD_HALO=0 timeout 300 python -m pytest tests/test_gpu_train.py -m gpu -q -k "wgrad_conv3x3_tcgen05" 2>&1 | tail -3;;
     *) echo "unknown step $w";;
   esac
