@@ -14,7 +14,7 @@ import torch
 from . import build as _build
 
 F32, BF16 = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 SE_SUM_SCALE = 1048576.0    # CCVPE_SE_SUM_SCALE: the squeeze-excite channel sums are int64 fixed point (order independent)
 BACKEND_AUTO, BACKEND_SIMT, BACKEND_TCGEN05 = 0, 1, 2
 
@@ -145,7 +145,7 @@ def load() -> C.CDLL:
                                                  C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p, C.c_void_p, C.c_int,
                                                  C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.ccvpe_se_gate_scale.restype = C.c_int
-    lib.ccvpe_se_gate_scale.argtypes = [C.c_void_p, C.c_float] + [C.c_void_p] * 6 + [C.c_int] * 4 + [C.c_void_p]
+    lib.ccvpe_se_gate_scale.argtypes = [C.c_void_p, C.c_float] + [C.c_void_p] * 6 + [C.c_int] * 5 + [C.c_void_p] * 2
     lib.ccvpe_mbconv_project_nhwc.restype = C.c_int
     lib.ccvpe_mbconv_project_nhwc.argtypes = [C.c_void_p] * 6 + [C.c_int] * 4 + [C.c_void_p]
     lib.ccvpe_wrap_columns_nhwc.restype = C.c_int
@@ -476,21 +476,28 @@ def stem_conv_silu_u8_nhwc(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor,
 
 
 def se_gate_scale(chan_sum: torch.Tensor, inv_hw: float, w_red: torch.Tensor, b_red: torch.Tensor, w_se: torch.Tensor,
-                  b_se: torch.Tensor, w_proj: torch.Tensor, wg: torch.Tensor):
+                  b_se: torch.Tensor, w_proj: torch.Tensor, wg: torch.Tensor, gate_ws: Optional[torch.Tensor] = None,
+                  rep: int = 1):
     """wg[b] = w_proj * diag(sigmoid(w_se^T SiLU(w_red mean_b + b_red) + b_se)), mean_b = chan_sum[b] * inv_hw.
     chan_sum int64 fixed point [B, mid]; w_red [R, mid]; w_se [R, mid] (the excite weights transposed); contiguous bf16;
-    wg contiguous bf16 [B, cout, mid]."""
+    wg contiguous bf16 [B, rep*cout, rep*mid] (rep > 1: block diagonal, `rep` pixels packed into one GEMM row);
+    gate_ws: optional fp32 [B, mid] workspace (required for rep > 1; enables the two-launch form for the deep blocks)."""
     _require_cuda(chan_sum, w_red, b_red, w_se, b_se, w_proj, wg)
     B, mid = chan_sum.shape
     R, cout = w_red.shape[0], w_proj.shape[0]
     for t in (w_red, b_red, w_se, b_se, w_proj, wg):
         if t.dtype != torch.bfloat16 or not t.is_contiguous():
             raise CcvpeError("se_gate_scale: weights, biases and wg must be contiguous bf16")
-    if chan_sum.dtype != torch.int64 or not chan_sum.is_contiguous() or tuple(wg.shape) != (B, cout, mid) \
+    if chan_sum.dtype != torch.int64 or not chan_sum.is_contiguous() or tuple(wg.shape) != (B, rep * cout, rep * mid) \
             or tuple(w_red.shape) != (R, mid) or tuple(w_se.shape) != (R, mid) or tuple(w_proj.shape) != (cout, mid):
         raise CcvpeError("se_gate_scale: shape / dtype mismatch")
+    if gate_ws is not None:
+        _require_cuda(gate_ws)
+        if gate_ws.dtype != torch.float32 or not gate_ws.is_contiguous() or gate_ws.numel() < B * mid:
+            raise CcvpeError("se_gate_scale: gate_ws must be contiguous fp32 with at least B * mid elements")
     _check(load().ccvpe_se_gate_scale(_ptr(chan_sum), C.c_float(inv_hw), _ptr(w_red), _ptr(b_red), _ptr(w_se), _ptr(b_se),
-                                      _ptr(w_proj), _ptr(wg), B, mid, R, cout, _stream()), "ccvpe_se_gate_scale")
+                                      _ptr(w_proj), _ptr(wg), B, mid, R, cout, int(rep),
+                                      _ptr(gate_ws) if gate_ws is not None else None, _stream()), "ccvpe_se_gate_scale")
 
 
 def mbconv_project_nhwc(d: torch.Tensor, wg: torch.Tensor, residual: Optional[torch.Tensor], out: torch.Tensor,

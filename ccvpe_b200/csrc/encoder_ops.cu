@@ -712,6 +712,80 @@ se_gate_scale_kernel(const long long* __restrict__ chan_sum, float inv_hw, const
   }
 }
 
+// Two-kernel form of the same operator for the deep blocks (measured: the fused kernel spends 42 us per launch at
+// mid = 1152 -- every block first recomputes the gate, a chain of dependent L2 loads, before it may scale its rows):
+// se_gate_kernel computes g[b, :] once per image, se_scale_kernel is a flat grid-stride pass over all of wg.  `rep` > 1
+// writes the block-diagonal weights of `rep` pixels packed into one GEMM row,
+//   wg[b][r * cout + c][r' * mid + m] = (r == r') ? w_proj[c][m] * g[b][m] : 0,
+// which lets the projection GEMM of the shallow first block (mid = 32: 64-byte pixels) read full 128-byte rows.
+__global__ void __launch_bounds__(512)
+se_gate_kernel(const long long* __restrict__ chan_sum, float inv_hw, const __nv_bfloat16* __restrict__ w_red,
+               const __nv_bfloat16* __restrict__ b_red, const __nv_bfloat16* __restrict__ w_se_t,
+               const __nv_bfloat16* __restrict__ b_se, float* __restrict__ gate, int mid, int R) {
+  extern __shared__ __align__(16) float s_se[];
+  float* s_mean = s_se;
+  float* s_h = s_se + mid;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int m = tid; m < mid; m += blockDim.x) s_mean[m] = __ll2float_rn(chan_sum[(int64_t)b * mid + m]) * (inv_hw * (1.f / kSeFixedScale));
+  __syncthreads();
+  const int n_warps = blockDim.x >> 5;
+  for (int r = warp; r < R; r += n_warps) {
+    const __nv_bfloat16* wr = w_red + (int64_t)r * mid;
+    float acc = 0.f;
+    for (int m0 = lane * 8; m0 < mid; m0 += 256) {
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(wr + m0));
+      const __nv_bfloat162* hq = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(hq[j]);
+        acc = fmaf(f.x, s_mean[m0 + 2 * j], acc);
+        acc = fmaf(f.y, s_mean[m0 + 2 * j + 1], acc);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      const float v = acc + __bfloat162float(b_red[r]);
+      s_h[r] = __fdividef(v, 1.f + __expf(-v));
+    }
+  }
+  __syncthreads();
+  for (int m = tid; m < mid; m += blockDim.x) {
+    float acc = __bfloat162float(b_se[m]);
+#pragma unroll 8
+    for (int r = 0; r < R; ++r) acc = fmaf(__bfloat162float(__ldg(w_se_t + (int64_t)r * mid + m)), s_h[r], acc);
+    gate[(int64_t)b * mid + m] = __fdividef(1.f, 1.f + __expf(-acc));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+se_scale_kernel(const float* __restrict__ gate, const __nv_bfloat16* __restrict__ w_proj, __nv_bfloat16* __restrict__ wg,
+                int mid, int cout, int rep, int64_t total_vec) {
+  const int row_vec = rep * mid >> 3;                       // 8-element vectors per output row
+  const int64_t per_img = (int64_t)rep * cout * row_vec;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / per_img);
+    const int rem = (int)(i - (int64_t)b * per_img);
+    const int row = rem / row_vec, k0 = (rem - row * row_vec) << 3;
+    const int r = row / cout, c = row - r * cout;
+    const int r2 = k0 / mid, m0 = k0 - r2 * mid;            // mid % 8 == 0: a vector never straddles two pixels
+    uint4 q = make_uint4(0u, 0u, 0u, 0u);
+    if (r == r2) {
+      q = __ldg(reinterpret_cast<const uint4*>(w_proj + (int64_t)c * mid + m0));
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gate + (int64_t)b * mid + m0));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gate + (int64_t)b * mid + m0 + 4));
+      const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      __nv_bfloat162* hq = reinterpret_cast<__nv_bfloat162*>(&q);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(hq[j]);
+        hq[j] = __floats2bfloat162_rn(f.x * gv[2 * j], f.y * gv[2 * j + 1]);
+      }
+    }
+    reinterpret_cast<uint4*>(wg)[i] = q;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // Circular width padding of a padded channels-last image [B, Hp, Wp, C] whose interior (rows lo .. lo+H-1, columns
 // lo .. lo+W-1) has been written: columns [0, lo) <- interior columns [W - lo, W), columns [lo + W, Wp) <- interior
@@ -754,12 +828,29 @@ extern "C" int ccvpe_wrap_columns_nhwc(void* buf, int B, int H, int W, int C, in
 
 extern "C" int ccvpe_se_gate_scale(const int64_t* chan_sum, float inv_hw, const void* w_red, const void* b_red,
                                    const void* w_se, const void* b_se, const void* w_proj, void* wg, int B, int mid,
-                                   int R, int cout, void* stream) {
+                                   int R, int cout, int rep, float* gate_ws, void* stream) {
   using namespace ccvpe;
   CCVPE_REQUIRE(chan_sum && w_red && b_red && w_se && b_se && w_proj && wg, "ccvpe_se_gate_scale: null pointer");
   CCVPE_REQUIRE(B > 0 && B <= 65535 * 32 && mid > 0 && mid % 8 == 0 && R > 0 && cout > 0,
                 "ccvpe_se_gate_scale: bad shape B=%d mid=%d R=%d cout=%d", B, mid, R, cout);
   CCVPE_REQUIRE(aligned16(w_red) && aligned16(w_proj) && aligned16(wg), "ccvpe_se_gate_scale: pointers must be 16-byte aligned");
+  CCVPE_REQUIRE(rep >= 1 && rep <= 8, "ccvpe_se_gate_scale: rep=%d out of range", rep);
+  CCVPE_REQUIRE(rep == 1 || gate_ws, "ccvpe_se_gate_scale: packed weights (rep > 1) need the gate workspace");
+  CCVPE_REQUIRE((size_t)(mid + R) * sizeof(float) <= 48 * 1024, "ccvpe_se_gate_scale: mid too large");
+  if (gate_ws && (rep > 1 || (int64_t)cout * mid >= 32768)) {
+    CCVPE_REQUIRE(aligned16(gate_ws), "ccvpe_se_gate_scale: gate workspace must be 16-byte aligned");
+    se_gate_kernel<<<B, 512, (size_t)(mid + R) * sizeof(float), (cudaStream_t)stream>>>(
+        reinterpret_cast<const long long*>(chan_sum), inv_hw, (const __nv_bfloat16*)w_red, (const __nv_bfloat16*)b_red,
+        (const __nv_bfloat16*)w_se, (const __nv_bfloat16*)b_se, gate_ws, mid, R);
+    CCVPE_LAUNCH_CHECK("se_gate_kernel");
+    const int64_t total_vec = (int64_t)B * rep * cout * (rep * mid / 8);
+    int64_t blocks = (total_vec + 255) / 256;
+    if (blocks > 8LL * sm_count()) blocks = 8LL * sm_count();
+    se_scale_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(gate_ws, (const __nv_bfloat16*)w_proj, (__nv_bfloat16*)wg, mid,
+                                                                         cout, rep, total_vec);
+    CCVPE_LAUNCH_CHECK("se_scale_kernel");
+    return CCVPE_OK;
+  }
   int rows = 98304 / mid;
   if (rows < 8) rows = 8;
   if (rows > cout) rows = cout;

@@ -568,8 +568,7 @@ int igemm_tcgen05(const ccvpe_igemm_desc& d, cudaStream_t st, const TcOutPad* ou
   int stages = (light ? light_budget - w_bytes : TC_SMEM_BUDGET) / stage_bytes;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   if (g.halo) {
-    // one CTA per SM: a ring of halo A tiles + a deep ring of weight tiles (weights stream: nine tiles per K block)
-    light = false;
+    // a ring of halo A tiles + a ring of weight tiles (weights stream: nine tiles per K block).
     p.w_resident = 0;
     w_bytes = 0;
     p.halo = 1;
@@ -577,11 +576,25 @@ int igemm_tcgen05(const ccvpe_igemm_desc& d, cudaStream_t st, const TcOutPad* ou
     p.halo_tx0 = (g.tw + 2) * (g.th + 2) * p.kw0 * 2;
     p.halo_tx1 = (g.tw + 2) * (g.th + 2) * p.kw1 * 2;
     p.a_slot_bytes = ((g.tw + 2) * (g.th + 2) * kw_max * 2 + 1023) / 1024 * 1024;
-    p.a_slots = 3;
-    p.b_off = p.a_slots * p.a_slot_bytes;
     stage_bytes = (block_n * kw_max * 2 + 1023) / 1024 * 1024;
     p.stage_bytes = stage_bytes;
-    stages = (TC_SMEM_BUDGET - p.b_off) / stage_bytes;
+    // Narrow N tiles (level 3: N = 64 / 80): the ncu source view shows BOTH single-thread roles saturated -- the producer
+    // (one B tile of block_n box rows per tap) and the MMA issuer (~70 instructions per tap for 1-4 short MMAs) -- while
+    // the tensor pipe idles.  Two CTAs per SM (the LIGHT instantiation: two producers, two issuers, staged epilogue)
+    // double both; the shallower rings are what fits 2 x 104 KB.
+    static const int halo_light_env = getenv("CCVPE_HALO_LIGHT") ? atoi(getenv("CCVPE_HALO_LIGHT")) : 1;   // development switch
+    const int hl_budget = light_budget - 2 * p.a_slot_bytes;
+    if (halo_light_env && p.tmem_cols <= 256 && block_n <= 96 && hl_budget / stage_bytes >= 3) {
+      light = true;
+      p.a_slots = 2;
+      p.b_off = p.a_slots * p.a_slot_bytes;
+      stages = hl_budget / stage_bytes;
+    } else {
+      light = false;   // one CTA per SM with all of its shared memory
+      p.a_slots = 3;
+      p.b_off = p.a_slots * p.a_slot_bytes;
+      stages = (TC_SMEM_BUDGET - p.b_off) / stage_bytes;
+    }
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
     if (stages < 3) return fail(CCVPE_ERR_UNSUPPORTED, "ccvpe_igemm(tcgen05): halo mode does not fit shared memory");
   }

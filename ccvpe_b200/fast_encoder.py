@@ -113,6 +113,14 @@ class FastEncoder:
             self._buffers[key] = buf
         return buf                                                                   # NHWC physical
 
+    def _packed_bias(self, o, rep) -> torch.Tensor:
+        key = ("bproj", id(o), rep)
+        buf = self._buffers.get(key)
+        if buf is None:
+            buf = o.b_proj.repeat(rep).contiguous()
+            self._buffers[key] = buf
+        return buf
+
     def _wrap_columns(self, buf, H, W, lo, hi):
         """Circular width padding: copy the wrap-around columns inside the padded buffer (vertical borders stay zero)."""
         if buf.is_cuda and buf.dtype == torch.bfloat16 and buf.is_contiguous():
@@ -250,8 +258,12 @@ class FastEncoder:
             Bo, Ho, Wo, _ = d.shape
             # squeeze-excite gate folded into the projection weights
             if fused_dw:
-                wg = torch.empty((Bo, o.cout, o.mid), dtype=dt, device=d.device)
-                cabi.se_gate_scale(sums, 1.0 / float(Ho * Wo), o.w_red, o.b_red, o.w_se_t, o.b_se, o.w_proj, wg)
+                # shallow first block (mid = 32: 64-byte pixels): two pixels per GEMM row with block-diagonal weights, so
+                # the projection's TMA boxes carry full 128-byte rows (its load rate is per box row, not per byte)
+                rep = 2 if (o.mid <= 32 and (Ho * Wo) % 2 == 0 and not o.residual) else 1
+                wg = torch.empty((Bo, rep * o.cout, rep * o.mid), dtype=dt, device=d.device)
+                gate_ws = torch.empty((Bo, o.mid), dtype=torch.float32, device=d.device)
+                cabi.se_gate_scale(sums, 1.0 / float(Ho * Wo), o.w_red, o.b_red, o.w_se_t, o.b_se, o.w_proj, wg, gate_ws, rep)
             else:
                 sq = (sums / float(Ho * Wo)).to(dt)                                  # [B, mid]
                 g = torch.sigmoid(F.linear(F.silu(F.linear(sq, o.w_red, o.b_red)), o.w_se, o.b_se))   # [B, mid]
@@ -262,7 +274,13 @@ class FastEncoder:
                 cur = torch.empty((Bo, Ho, Wo, o.cout), dtype=dt, device=d.device)
                 want = keep_blocks and len(outs) in self.keep
                 kept = torch.empty_like(cur) if want else None
-                cabi.mbconv_project_nhwc(d, wg, block_in if o.residual else None, cur, o.b_proj if want else None, kept)
+                if rep > 1:
+                    cabi.mbconv_project_nhwc(d.view(Bo, Ho * Wo // rep, rep * o.mid), wg, None,
+                                             cur.view(Bo, Ho * Wo // rep, rep * o.cout),
+                                             self._packed_bias(o, rep) if want else None,
+                                             kept.view(Bo, Ho * Wo // rep, rep * o.cout) if want else None)
+                else:
+                    cabi.mbconv_project_nhwc(d, wg, block_in if o.residual else None, cur, o.b_proj if want else None, kept)
                 if keep_blocks:
                     outs.append(kept.permute(0, 3, 1, 2) if want else None)
                 continue

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define CCVPE_ABI_VERSION 2
+#define CCVPE_ABI_VERSION 3
 
 enum { CCVPE_F32 = 0, CCVPE_BF16 = 1 };
 
@@ -213,9 +213,13 @@ int ccvpe_wrap_columns_nhwc(void* buf, int B, int H, int W, int C, int pad_lo, i
  *   mean = chan_sum / CCVPE_SE_SUM_SCALE * inv_hw;  h = SiLU(w_red mean + b_red);  g = sigmoid(w_se h + b_se);  wg[b] = w_proj * diag(g[b])
  * chan_sum int64 fixed point [B, mid] (from ccvpe_dwconv_bias_silu_nhwc); w_red bf16 [R, mid]; b_red bf16 [R]; w_se bf16 [R, mid]
  * (the excite weights TRANSPOSED, so the gate mat-vec reads them coalesced); b_se bf16 [mid]; w_proj bf16 [cout, mid]; wg bf16 [B, cout, mid] = the per-image B operand of the projection GEMM
- * (W (g . x) == (W diag(g)) x, so the broadcast multiply over the expanded activation never happens).  mid % 8 == 0. */
+ * (W (g . x) == (W diag(g)) x, so the broadcast multiply over the expanded activation never happens).  mid % 8 == 0.
+ * rep > 1: wg is bf16 [B, rep*cout, rep*mid], block diagonal with rep copies of wg[b] -- the weights of `rep` consecutive
+ * pixels packed into one GEMM row (ccvpe_mbconv_project_nhwc on [B, HW/rep, rep*mid]).  gate_ws: fp32 [B, mid] workspace or
+ * NULL; required for rep > 1, and when given the deep blocks run as two launches (gate, then a flat scaling pass). */
 int ccvpe_se_gate_scale(const int64_t* chan_sum, float inv_hw, const void* w_red, const void* b_red, const void* w_se,
-                        const void* b_se, const void* w_proj, void* wg, int B, int mid, int R, int cout, void* stream);
+                        const void* b_se, const void* w_proj, void* wg, int B, int mid, int R, int cout, int rep,
+                        float* gate_ws, void* stream);
 
 /* Pointwise (1x1) convolution + bias + SiLU over channels-last bf16 pixels on the tcgen05 pipeline -- the MBConv expand
  * step and the encoder head (reference efficientnet_pytorch/model.py:100-106, 312-314 in eval mode, BN folded):

@@ -24,7 +24,7 @@ __device__ __forceinline__ void bulk1d(uint32_t dst, const void* src, uint32_t b
 }
 
 constexpr int STAGES = 8;
-constexpr int SLOT = 24 * 1024;
+constexpr int SLOT = 26 * 1024;   // (two 64-wide boxes of 130 rows: 2 x 17408 B would need 34 KB -- those configs are skipped)
 // mode 0: tensor boxes (nblk boxes of kw channels per segment); mode 1: one 1-D bulk copy per segment
 __global__ void probe(const __grid_constant__ CUtensorMap tm, const uint8_t* x, int mode, int C, int ld, int kw, int nblk, int iters, int W,
                       int rows, long long* out) {
@@ -46,9 +46,10 @@ __global__ void probe(const __grid_constant__ CUtensorMap tm, const uint8_t* x, 
       if (i < iters) {
         mbar_expect(smem_u32(&bar[s]), tx);
         // consecutive CTAs take consecutive segments of the image (like the ring kernel's strips), iteration i moves down
-        long long seg = (long long)i * gridDim.x + blockIdx.x;
-        int xs = (int)(seg % strips);
-        long long row = (seg / strips) % rows;
+        // (32-bit index math only: the first version's 64-bit div / mod cost ~600 cycles per iteration and hid everything)
+        const unsigned seg = (unsigned)i * gridDim.x + blockIdx.x;
+        const int xs = (int)(seg & (unsigned)(strips - 1));           // strips is a power of two (W = 512)
+        const unsigned row = (seg >> 2) & (unsigned)(rows - 1);        // rows is a power of two
         if (mode == 0) {
           for (int b = 0; b < nblk; ++b) tma3(base + s * SLOT + b * ((130 * kw * 2 + 1023) / 1024 * 1024), &tm, smem_u32(&bar[s]), b * kw, xs * 128 - 1, (int)row);
         } else {
@@ -71,11 +72,12 @@ int main() {
   long long* out; cudaMalloc(&out, sms * sizeof(long long));
   cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGES * SLOT + 2048);
   // {C, ld, kw}
-  int cfg[][3] = {{16, 16, 16}, {32, 32, 32}, {40, 40, 32}, {40, 40, 64}, {40, 64, 64}, {64, 64, 64}, {80, 80, 64}, {80, 128, 64}, {16, 64, 16}};
+  int cfg[][3] = {{16, 16, 16}, {32, 32, 32}, {40, 40, 32}, {40, 40, 64}, {40, 64, 64}, {64, 64, 64}, {16, 64, 16}};
   const int W = 512;
   for (auto& c : cfg) {
     const int C = c[0], ld = c[1], kw = c[2];
-    const int rows = (int)((size_t)400 * 1024 * 1024 / ((size_t)W * ld * 2));   // 400 MB image stack: every segment is cold
+    int rows = (int)((size_t)400 * 1024 * 1024 / ((size_t)W * ld * 2));   // 400 MB image stack: every segment is cold
+    { int p2 = 1; while (p2 * 2 <= rows) p2 *= 2; rows = p2; }             // (>= 200 MB: still larger than L2)
     void* x; size_t n = (size_t)rows * W * ld * 2; cudaMalloc(&x, n); cudaMemset(x, 0, n);
     CUtensorMap tm;
     CUtensorMapSwizzle sw = kw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : kw == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;

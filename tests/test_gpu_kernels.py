@@ -607,8 +607,13 @@ def test_stem_conv_silu_nhwc(cuda_device, B, H, W, circ, olo, ohi):
         assert bool((got[:, :, :olo] == 0).all()) and bool((got[:, :, olo + Wo:] == 0).all())
 
 
-@pytest.mark.parametrize("B,mid,R,cout", [(3, 96, 4, 24), (2, 1152, 48, 320), (5, 240, 10, 80), (1, 32, 8, 16)])
-def test_se_gate_scale(cuda_device, B, mid, R, cout):
+@pytest.mark.parametrize("B,mid,R,cout,ws,rep", [(3, 96, 4, 24, False, 1), (2, 1152, 48, 320, False, 1), (5, 240, 10, 80, False, 1),
+                                                 (1, 32, 8, 16, False, 1),
+                                                 # two-launch form (gate workspace given): deep block, small block (stays
+                                                 # fused), and the block-diagonal weights of two / four packed pixels
+                                                 (2, 1152, 48, 320, True, 1), (3, 96, 4, 24, True, 1), (3, 32, 8, 16, True, 2),
+                                                 (2, 48, 4, 8, True, 4)])
+def test_se_gate_scale(cuda_device, B, mid, R, cout, ws, rep):
     """fused squeeze-excite gate + projection-weight scaling vs torch (fp32 math on bf16 parameters)."""
     g = _gen(18)
     dev = cuda_device
@@ -623,12 +628,18 @@ def test_se_gate_scale(cuda_device, B, mid, R, cout):
     mean = sums / hw
     h = F.silu(mean @ w_red.float().t() + b_red.float())
     gate = torch.sigmoid(h @ w_se.float().t() + b_se.float())
-    ref = w_proj.float().unsqueeze(0) * gate.unsqueeze(1)
-    wg = torch.empty(B, cout, mid, device=dev, dtype=torch.bfloat16)
+    ref1 = w_proj.float().unsqueeze(0) * gate.unsqueeze(1)
+    ref = torch.zeros(B, rep * cout, rep * mid)
+    for r in range(rep):
+        ref[:, r * cout:(r + 1) * cout, r * mid:(r + 1) * mid] = ref1
+    wg = torch.full((B, rep * cout, rep * mid), 7.0, device=dev, dtype=torch.bfloat16)
+    gate_ws = torch.empty(B, mid, device=dev, dtype=torch.float32) if ws else None
     cabi.se_gate_scale(sums_fixed.to(dev), 1.0 / hw, w_red.to(dev), b_red.to(dev), w_se.t().contiguous().to(dev), b_se.to(dev),
-                       w_proj.to(dev), wg)
+                       w_proj.to(dev), wg, gate_ws, rep)
     torch.cuda.synchronize()
-    assert rel_err(wg.float(), ref) < 1e-2
+    assert rel_err(wg.float().cpu(), ref) < 1e-2
+    if rep > 1:                                     # off-diagonal blocks are exact zeros
+        assert bool((wg.float().cpu()[ref == 0] == 0).all())
 
 
 @pytest.mark.parametrize("B,HW,mid,cout,res,biased", [
