@@ -49,6 +49,21 @@ struct TcOutPad {
   int Hp, Wp, lo;
 };
 
+// Arguments of the tensor-core encoder stem (stem_tcgen05.cu); x (planar fp32) or x8 (planar uint8 + the normalisation
+// u8 * sc + sh, per-image roll and source row pitch Wsrc) is the image batch.
+struct StemTcParams {
+  const float* x;
+  const uint8_t* x8;
+  const int32_t* shift;
+  int Wsrc;
+  float sc[3], sh[3];
+  const float* w;          // fp32 [27][32], k = (ci * 3 + ky) * 3 + kx
+  const float* bias;       // fp32 [32]
+  __nv_bfloat16* out;      // padded channels-last image [B, Hp, Wp, 32]
+  int B, H, W, Ho, Wo, in_lo, out_lo, Hp, Wp, strips, total_tiles;
+};
+int stem_tcgen05(StemTcParams p, bool circular, bool u8, cudaStream_t st);
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 int sm_count();  // cached cudaDevAttrMultiProcessorCount of the current device (148 on B200)

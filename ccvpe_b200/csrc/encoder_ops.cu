@@ -718,7 +718,7 @@ se_gate_scale_kernel(const long long* __restrict__ chan_sum, float inv_hw, const
 // writes the block-diagonal weights of `rep` pixels packed into one GEMM row,
 //   wg[b][r * cout + c][r' * mid + m] = (r == r') ? w_proj[c][m] * g[b][m] : 0,
 // which lets the projection GEMM of the shallow first block (mid = 32: 64-byte pixels) read full 128-byte rows.
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(1024)
 se_gate_kernel(const long long* __restrict__ chan_sum, float inv_hw, const __nv_bfloat16* __restrict__ w_red,
                const __nv_bfloat16* __restrict__ b_red, const __nv_bfloat16* __restrict__ w_se_t,
                const __nv_bfloat16* __restrict__ b_se, float* __restrict__ gate, int mid, int R) {
@@ -839,7 +839,8 @@ extern "C" int ccvpe_se_gate_scale(const int64_t* chan_sum, float inv_hw, const 
   CCVPE_REQUIRE((size_t)(mid + R) * sizeof(float) <= 48 * 1024, "ccvpe_se_gate_scale: mid too large");
   if (gate_ws && (rep > 1 || (int64_t)cout * mid >= 32768)) {
     CCVPE_REQUIRE(aligned16(gate_ws), "ccvpe_se_gate_scale: gate workspace must be 16-byte aligned");
-    se_gate_kernel<<<B, 512, (size_t)(mid + R) * sizeof(float), (cudaStream_t)stream>>>(
+    // (one block per image: both mat-vecs are chains of dependent L2 loads, so more threads = fewer rounds)
+    se_gate_kernel<<<B, mid >= 512 ? 1024 : 512, (size_t)(mid + R) * sizeof(float), (cudaStream_t)stream>>>(
         reinterpret_cast<const long long*>(chan_sum), inv_hw, (const __nv_bfloat16*)w_red, (const __nv_bfloat16*)b_red,
         (const __nv_bfloat16*)w_se, (const __nv_bfloat16*)b_se, gate_ws, mid, R);
     CCVPE_LAUNCH_CHECK("se_gate_kernel");
@@ -881,6 +882,14 @@ extern "C" int ccvpe_stem_conv_silu_nhwc(const float* x, int B, int H, int W, co
   const int pairs = (Wo + 1) / 2;
   const dim3 grid((pairs + 127) / 128, Ho, B);
   cudaStream_t st = (cudaStream_t)stream;
+  static const int stem_tc = getenv("CCVPE_STEM_TC") ? atoi(getenv("CCVPE_STEM_TC")) : 1;   // development switch: 0 = CUDA-core kernel
+  if (stem_tc) {
+    StemTcParams tp;
+    memset(&tp, 0, sizeof(tp));
+    tp.x = x; tp.w = w; tp.bias = bias; tp.out = (__nv_bfloat16*)out;
+    tp.B = B; tp.H = H; tp.W = W; tp.Ho = Ho; tp.Wo = Wo; tp.in_lo = in_pad_lo; tp.out_lo = out_pad_lo; tp.Hp = Hp; tp.Wp = Wp;
+    return stem_tcgen05(tp, circular != 0, false, st);
+  }
   StemU8 none;
   memset(&none, 0, sizeof(none));
   if (circular)
@@ -919,6 +928,19 @@ extern "C" int ccvpe_stem_conv_silu_u8_nhwc(const uint8_t* x, int B, int H, int 
     u.sh[c] = -mean_host[c] / std_host[c];
   }
   cudaStream_t st = (cudaStream_t)stream;
+  static const int stem_tc = getenv("CCVPE_STEM_TC") ? atoi(getenv("CCVPE_STEM_TC")) : 1;   // development switch: 0 = CUDA-core kernel
+  if (stem_tc) {
+    StemTcParams tp;
+    memset(&tp, 0, sizeof(tp));
+    tp.x8 = x; tp.shift = shift; tp.Wsrc = Wsrc;
+    for (int c = 0; c < 3; ++c) {
+      tp.sc[c] = u.sc[c];
+      tp.sh[c] = u.sh[c];
+    }
+    tp.w = w; tp.bias = bias; tp.out = (__nv_bfloat16*)out;
+    tp.B = B; tp.H = H; tp.W = W; tp.Ho = Ho; tp.Wo = Wo; tp.in_lo = in_pad_lo; tp.out_lo = out_pad_lo; tp.Hp = Hp; tp.Wp = Wp;
+    return stem_tcgen05(tp, circular != 0, true, st);
+  }
   if (circular)
     stem_conv_silu_kernel<32, true, true><<<grid, 128, 0, st>>>(nullptr, w, bias, (__nv_bfloat16*)out, H, W, Ho, Wo, in_pad_lo, out_pad_lo, Hp, Wp, u);
   else

@@ -38,6 +38,7 @@ for w in $what; do
     ncu_pw) timeout 600 ncu --set full --clock-control none --import-source on -k regex:igemm_tcgen05 -s 2 -c 1 -o gpurun_out/${tag}_prof_pw python scripts/bench_pointwise.py 64 0 > gpurun_out/${tag}_ncu_pw.log 2>&1; tail -3 gpurun_out/${tag}_ncu_pw.log | cut -c1-200;;
     halo_light) for hl in 0 1; do echo "CCVPE_HALO_LIGHT=$hl"; for a in "conv 16 80 24 80 128" "conv 16 80 0 80 128" "conv 16 64 24 64 128" "conv 16 64 0 64 128" "conv 16 160 40 160 64"; do CCVPE_HALO_LIGHT=$hl timeout 120 python scripts/bench_igemm.py $a 2>&1 | tail -1; done; done | tee gpurun_out/${tag}_halo_light.txt;;
     test_enc) timeout 900 python -m pytest tests/test_gpu_kernels.py tests/test_fast_encoder.py tests/test_gpu_forward.py -m gpu -q -x -k "mbconv_project or se_gate or conv3x3 or deconv or encoder or bit_reproducible or bf16" 2>&1 | tail -6;;
+    test_stem) timeout 900 python -m pytest tests/test_gpu_kernels.py tests/test_fast_encoder.py tests/test_gpu_forward.py -m gpu -q -x -k "stem or encoder or bit_reproducible or bf16 or uint8" 2>&1 | tail -6;;
     wgrad_halo) CCVPE_WGRAD_HALO=1 timeout 300 python -m pytest tests/test_gpu_train.py -m gpu -q -k "wgrad_conv3x3_tcgen05" 2>&1 | tail -3; CCVPE_WGRAD_HALO=0 timeout 300 python -m pytest tests/test_gpu_train.py -m gpu -q -k "wgrad_conv3x3_tcgen05" 2>&1 | tail -3;;
     *) echo "unknown step $w";;
   esac
