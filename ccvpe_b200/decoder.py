@@ -295,7 +295,7 @@ class PostEncoderPipeline:
         g: List[torch.Tensor] = [torch.empty((Bg, Wg * h[0].shape[0]), dtype=f32, device=dev) for h in w["heads"]]
         heads = w["heads"]
         ctot = sum(h[0].shape[0] for h in heads)
-        self._op("grd_project_all_kernel:grd_descriptors|", 2.0 * Bg * Wg * Kg * (6 * Hg + ctot),
+        self._op("grd_project_tiled_kernel:grd_descriptors|", 2.0 * Bg * Wg * Kg * (6 * Hg + ctot),
                  grd_feat.numel() * grd_feat.element_size() + sum(t.numel() for t in g) * 4,
                  lambda: cabi.grd_descriptors(grd_feat, heads, g, scratch_g))
 
