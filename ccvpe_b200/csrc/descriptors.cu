@@ -103,56 +103,58 @@ __global__ void grd_height_reduce_all_kernel(const T* __restrict__ feat, int B, 
 
 // Shared-memory tiled projection (six small fp32 GEMMs [B*W x K] . [K x c_l]).  The first version, one warp per output
 // element, re-read an S row once per output channel (126 x 5 KB per row from L2: 0.8 GB for B = 64, measured 0.14 ms =
-// 3.6 % of the HBM roofline for 39 MB of operands); here a block owns 32 rows x (up to) 64 channels of one head and walks
-// K in steps of 32, so every operand element is fetched once per block.  grid = (row tiles, heads); 256 threads, a thread
-// accumulates 2 rows x 4 channels.
+// 3.6 % of the HBM roofline for 39 MB of operands).  Here a block owns 8 rows x (up to) 64 channels of one head and walks
+// K in steps of 128 (ten barrier rounds for K = 1280; a first tiled attempt with 32-row tiles and 32-wide K steps had too
+// few blocks and forty exposed load latencies each and was slower than the warp-per-output kernel).  grid = (row tiles,
+// heads); 256 threads; a thread accumulates 2 rows x 1 channel with float4 shared loads along K.
+constexpr int GP_ROWS = 8, GP_COLS = 64, GP_KT = 128, GP_PITCH = GP_KT + 4;
 __global__ void __launch_bounds__(256) grd_project_tiled_kernel(const float* __restrict__ S, HeadTable t, int B, int W, int K, int H) {
-  __shared__ float sS[32][33];
-  __shared__ float sW[64][33];
+  __shared__ __align__(16) float sS[GP_ROWS][GP_PITCH];
+  __shared__ __align__(16) float sW[GP_COLS][GP_PITCH];
   const int l = blockIdx.y;
   const int c = t.c[l];
   const int BW = B * W;
-  const int r0 = blockIdx.x * 32;
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int r0 = blockIdx.x * GP_ROWS;
+  const int tid = threadIdx.x, col = tid & 63, rg = tid >> 6;
   const float* Sl = S + (int64_t)l * BW * K;
   const float* Wl = t.w1[l];
-  for (int n0 = 0; n0 < c; n0 += 64) {
-    float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-    for (int k0 = 0; k0 < K; k0 += 32) {
-      for (int i = tid; i < 32 * 32; i += 256) {
-        const int r = i >> 5, kk = i & 31;
-        sS[r][kk] = (r0 + r < BW && k0 + kk < K) ? Sl[(int64_t)(r0 + r) * K + k0 + kk] : 0.f;
+  float vs = 0.f;
+  for (int h = 0; h < H; ++h) vs += t.w2[l][h];
+  for (int n0 = 0; n0 < c; n0 += GP_COLS) {
+    const int nc = min(GP_COLS, c - n0);
+    float acc0 = 0.f, acc1 = 0.f;
+    for (int k0 = 0; k0 < K; k0 += GP_KT) {
+      for (int i = tid; i < GP_ROWS * (GP_KT / 4); i += 256) {          // S tile: one float4 per thread
+        const int r = i / (GP_KT / 4), k4 = (i - r * (GP_KT / 4)) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r0 + r < BW && k0 + k4 < K) v = *reinterpret_cast<const float4*>(Sl + (int64_t)(r0 + r) * K + k0 + k4);
+        *reinterpret_cast<float4*>(&sS[r][k4]) = v;
       }
-      for (int i = tid; i < 64 * 32; i += 256) {
-        const int n = i >> 5, kk = i & 31;
-        sW[n][kk] = (n0 + n < c && k0 + kk < K) ? __ldg(Wl + (int64_t)(n0 + n) * K + k0 + kk) : 0.f;
+      for (int i = tid; i < nc * (GP_KT / 4); i += 256) {               // W tile: up to eight float4 per thread, all in flight
+        const int n = i / (GP_KT / 4), k4 = (i - n * (GP_KT / 4)) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k0 + k4 < K) v = __ldg(reinterpret_cast<const float4*>(Wl + (int64_t)(n0 + n) * K + k0 + k4));
+        *reinterpret_cast<float4*>(&sW[n][k4]) = v;
       }
       __syncthreads();
-      if (n0 + 4 * tx < c) {
+      if (col < nc) {
 #pragma unroll 8
-        for (int kk = 0; kk < 32; ++kk) {
-          const float a0 = sS[2 * ty][kk], a1 = sS[2 * ty + 1][kk];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float b = sW[4 * tx + j][kk];
-            acc[0][j] = fmaf(a0, b, acc[0][j]);
-            acc[1][j] = fmaf(a1, b, acc[1][j]);
-          }
+        for (int k4 = 0; k4 < GP_KT; k4 += 4) {
+          const float4 b = *reinterpret_cast<const float4*>(&sW[col][k4]);
+          const float4 a0 = *reinterpret_cast<const float4*>(&sS[2 * rg][k4]);
+          const float4 a1 = *reinterpret_cast<const float4*>(&sS[2 * rg + 1][k4]);
+          acc0 = fmaf(a0.x, b.x, acc0); acc0 = fmaf(a0.y, b.y, acc0); acc0 = fmaf(a0.z, b.z, acc0); acc0 = fmaf(a0.w, b.w, acc0);
+          acc1 = fmaf(a1.x, b.x, acc1); acc1 = fmaf(a1.y, b.y, acc1); acc1 = fmaf(a1.z, b.z, acc1); acc1 = fmaf(a1.w, b.w, acc1);
         }
       }
       __syncthreads();
     }
-    float vs = 0.f;
-    for (int h = 0; h < H; ++h) vs += t.w2[l][h];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int r = r0 + 2 * ty + i;
-      if (r >= BW) continue;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int ch = n0 + 4 * tx + j;
-        if (ch < c) t.out[l][(int64_t)r * c + ch] = acc[i][j] + t.b1[l][ch] * vs + t.b2[l][0];
-      }
+    if (col < nc) {
+      const int ch = n0 + col;
+      const float add = t.b1[l][ch] * vs + t.b2[l][0];
+      const int r = r0 + 2 * rg;
+      if (r < BW) t.out[l][(int64_t)r * c + ch] = acc0 + add;
+      if (r + 1 < BW) t.out[l][(int64_t)(r + 1) * c + ch] = acc1 + add;
     }
   }
 }
@@ -187,7 +189,7 @@ extern "C" int ccvpe_grd_descriptors(const void* feat, int dtype, int B, int K, 
   else
     grd_height_reduce_all_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)feat, B, K, H, W, sb, sk, sh, sw, t, scratch, k_fastest);
   CCVPE_LAUNCH_CHECK("grd_height_reduce_all_kernel");
-  const dim3 pgrid((unsigned)(((int64_t)B * W + 31) / 32), (unsigned)n_heads);
+  const dim3 pgrid((unsigned)(((int64_t)B * W + GP_ROWS - 1) / GP_ROWS), (unsigned)n_heads);
   grd_project_tiled_kernel<<<pgrid, 256, 0, st>>>(scratch, t, B, W, K, H);
   CCVPE_LAUNCH_CHECK("grd_project_tiled_kernel");
   return CCVPE_OK;

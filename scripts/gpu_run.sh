@@ -39,6 +39,10 @@ for w in $what; do
     halo_light) for hl in 0 1; do echo "CCVPE_HALO_LIGHT=$hl"; for a in "conv 16 80 24 80 128" "conv 16 80 0 80 128" "conv 16 64 24 64 128" "conv 16 64 0 64 128" "conv 16 160 40 160 64"; do CCVPE_HALO_LIGHT=$hl timeout 120 python scripts/bench_igemm.py $a 2>&1 | tail -1; done; done | tee gpurun_out/${tag}_halo_light.txt;;
     test_enc) timeout 900 python -m pytest tests/test_gpu_kernels.py tests/test_fast_encoder.py tests/test_gpu_forward.py -m gpu -q -x -k "mbconv_project or se_gate or conv3x3 or deconv or encoder or bit_reproducible or bf16" 2>&1 | tail -6;;
     test_stem) timeout 900 python -m pytest tests/test_gpu_kernels.py tests/test_fast_encoder.py tests/test_gpu_forward.py -m gpu -q -x -k "stem or encoder or bit_reproducible or bf16 or uint8" 2>&1 | tail -6;;
+    bench_enc_ops) for a in "project 64 12800 144 24 1" "project 64 51200 32 16 0" "project 64 200 1152 192 1" "project 64 800 480 80 1" "stem 64 512 512 0 0" "stem 64 320 640 1 0" "stem 64 512 512 0 1"; do timeout 120 python scripts/bench_encoder_ops.py $a 2>&1 | tail -1; done | tee gpurun_out/${tag}_bench_enc_ops.txt;;
+    ncu_stem) timeout 600 ncu --set full --clock-control none --import-source on -k regex:stem_tcgen05 -s 4 -c 1 -o gpurun_out/${tag}_prof_stem python scripts/bench_encoder_ops.py stem 64 512 512 0 0 > gpurun_out/${tag}_ncu_stem.log 2>&1; tail -2 gpurun_out/${tag}_ncu_stem.log | cut -c1-200;;
+    ncu_project) timeout 600 ncu --set full --clock-control none --import-source on -k regex:project_tcgen05 -s 4 -c 1 -o gpurun_out/${tag}_prof_project python scripts/bench_encoder_ops.py project 64 12800 144 24 1 > gpurun_out/${tag}_ncu_project.log 2>&1; tail -2 gpurun_out/${tag}_ncu_project.log | cut -c1-200;;
+    ncu_halo3) timeout 600 ncu --set full --clock-control none --import-source on -k regex:igemm_tcgen05 -s 6 -c 1 -o gpurun_out/${tag}_prof_igemm_halo3 python scripts/bench_igemm.py conv 16 80 24 80 128 > gpurun_out/${tag}_ncu_halo3.log 2>&1; tail -2 gpurun_out/${tag}_ncu_halo3.log | cut -c1-200;;
     wgrad_halo) CCVPE_WGRAD_HALO=1 timeout 300 python -m pytest tests/test_gpu_train.py -m gpu -q -k "wgrad_conv3x3_tcgen05" 2>&1 | tail -3; CCVPE_WGRAD_HALO=0 timeout 300 python -m pytest tests/test_gpu_train.py -m gpu -q -k "wgrad_conv3x3_tcgen05" 2>&1 | tail -3;;
     *) echo "unknown step $w";;
   esac

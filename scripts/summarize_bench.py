@@ -1,15 +1,19 @@
-"""Collects the bench.py JSON lines recorded under gpurun_out/ in round 2 into profiles/r02_bench_lines.md (profiles tool)."""
+"""Collects the bench.py JSON lines recorded under gpurun_out/ into profiles/<tag>_bench_lines.md (profiles tool).
+usage: python scripts/summarize_bench.py [tag] [single-GPU run prefix]   (defaults: r03 r03k)"""
 import json
 import os
+import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TAG = sys.argv[1] if len(sys.argv) > 1 else "r03"
+RUN = sys.argv[2] if len(sys.argv) > 2 else "r03k"
 RUNS = [
-    ("vigor_b64 (default workload), 1 GPU", "r02x_bench.json"),
-    ("kitti_b32, 1 GPU", "r02x_bench_kitti_b32.json"),
-    ("vigor_prior72_fov180, 1 GPU", "r02x_bench_vigor_prior72_fov180.json"),
-    ("vigor_prior72_fov108, 1 GPU", "r02x_bench_vigor_prior72_fov108.json"),
-    ("oxford_b1 (batch-1 sequential frames), 1 GPU", "r02x_bench_oxford_b1.json"),
-    ("train, B=8 bf16, one CUDA graph per step, 1 GPU", "r02x_bench_train.json"),
+    ("vigor_b64 (default workload), 1 GPU", RUN + "_bench.json"),
+    ("kitti_b32, 1 GPU", RUN + "_bench_kitti_b32.json"),
+    ("vigor_prior72_fov180, 1 GPU", RUN + "_bench_vigor_prior72_fov180.json"),
+    ("vigor_prior72_fov108, 1 GPU", RUN + "_bench_vigor_prior72_fov108.json"),
+    ("oxford_b1 (batch-1 sequential frames), 1 GPU", RUN + "_bench_oxford_b1.json"),
+    ("train, B=8 bf16, one CUDA graph per step, 1 GPU", RUN + "_bench_train.json"),
     ("train, B=8 fp32 parity path (eager), 1 GPU", "r02f_bench_train_fp32.json"),
     ("2 GPUs, weak (64 pairs per GPU)", "r02m_n2_weak.json"),
     ("2 GPUs, strong (one batch of 64)", "r02m_n2_strong.json"),
@@ -27,7 +31,9 @@ def load(name):
         return None
 
 
-out = ["# Bench lines recorded in round 2 (B200; the full JSON lines live under gpurun_out/, which is not tracked)", ""]
+out = ["# Bench lines recorded in round 2 (B200; the full JSON lines live under gpurun_out/, which is not tracked)",
+       "Single-GPU lines: run %s (final code of the round); multi-GPU lines: earlier runs of the round (r02m / r02s / r02t, before the"
+       % RUN, "halo convolution and this session's encoder / ring / stem kernels).", ""]
 for tag, f in RUNS:
     d = load(f)
     if not d:
@@ -54,5 +60,5 @@ for tag, f in RUNS:
     if d.get("latency_ms_per_frame"):
         out.append("latency: %s" % d["latency_ms_per_frame"])
     out.append("")
-open(os.path.join(ROOT, "profiles", "r02_bench_lines.md"), "w").write("\n".join(out))
+open(os.path.join(ROOT, "profiles", TAG + "_bench_lines.md"), "w").write("\n".join(out))
 print("\n".join(out))

@@ -1,9 +1,12 @@
-"""Summarises the parity numbers recorded by the GPU tests (gpurun_out/parity_*.json) into profiles/r02_parity.md."""
+"""Summarises the parity numbers recorded by the GPU tests (gpurun_out/parity_*.json) into profiles/<tag>_parity.md.
+usage: python scripts/summarize_parity.py [tag]   (default r03)"""
 import glob
 import json
 import os
+import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TAG = sys.argv[1] if len(sys.argv) > 1 else "r03"
 out = ["# Parity numbers measured on the B200 (round 2; tests/test_gpu_forward.py)", ""]
 out += ["## fp32 path: orientation field v/|v| against the CPU oracle, and the noise floor", "",
         "`ours` = libccvpe_b200 fp32 path; `floor` = the ORACLE ITSELF executed through cuDNN/cuBLAS fp32 (TF32 off) on the same GPU.",
@@ -36,5 +39,5 @@ for f in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "parity_bf16_*.json")
     out.append("argmax: %d / %d pairs equal to the oracle's; %d / %d of the pairs whose top-2 logit gap exceeds 10x the rms logit error (%.4f)"
                % (a["agree"], a["pairs"], a["agree_decided"], a["decided_pairs"], a["logit_rms_err"]))
     out.append("")
-open(os.path.join(ROOT, "profiles", "r02_parity.md"), "w").write("\n".join(out) + "\n")
+open(os.path.join(ROOT, "profiles", TAG + "_parity.md"), "w").write("\n".join(out) + "\n")
 print("\n".join(out))
