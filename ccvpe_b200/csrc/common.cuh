@@ -60,7 +60,7 @@ struct StemTcParams {
   const float* w;          // fp32 [27][32], k = (ci * 3 + ky) * 3 + kx
   const float* bias;       // fp32 [32]
   __nv_bfloat16* out;      // padded channels-last image [B, Hp, Wp, 32]
-  int B, H, W, Ho, Wo, in_lo, out_lo, Hp, Wp, strips, total_tiles, fast;
+  int B, H, W, Ho, Wo, in_lo, out_lo, Hp, Wp, strips, total_tiles;
 };
 int stem_tcgen05(StemTcParams p, bool circular, bool u8, cudaStream_t st);
 

@@ -90,58 +90,21 @@ __global__ void __launch_bounds__(128) stem_tcgen05_kernel(const __grid_constant
       }
       return __ldg(p.x + ((int64_t)(b * 3 + ci) * p.H + ih) * p.W + iw);
     };
-    if (p.fast) {
-      // in_lo == 0 and W even: the window columns are 2 wo, 2 wo + 1 (always inside the row; one 8-byte load for fp32)
-      // and 2 wo + 2 = the NEXT pixel's first column, taken from the neighbouring lane.  The ncu capture of the
-      // 27-scalar-load version showed the L1 pipe at 72 % (8 sectors per request, half of every sector unused).
-      const int lane = tid & 31;
-      const int iw0 = 2 * wo;
-      const bool edge = lane == 31 || iw0 + 2 >= p.W;        // no neighbour lane, or the column wraps / leaves the image
+    // (A variant with one 8-byte load for columns 2 wo, 2 wo + 1 and the third column taken from the neighbouring lane cut the
+    // L1 sector traffic three-fold but measured 3-45 % SLOWER on every shape -- profiles/r03_stem_ab.txt -- and was dropped.)
 #pragma unroll
-      for (int ci = 0; ci < 3; ++ci) {
+    for (int ci = 0; ci < 3; ++ci) {
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-          const int ih = 2 * ho + ky;
-          const bool ok = valid && ih < p.H;
-          float a0 = 0.f, a1 = 0.f;
-          if (ok) {
-            if (U8) {
-              a0 = load1(ci, ih, iw0);
-              a1 = load1(ci, ih, iw0 + 1);
-            } else {
-              const float2 t2 = __ldg(reinterpret_cast<const float2*>(p.x + ((int64_t)(b * 3 + ci) * p.H + ih) * p.W + iw0));
-              a0 = t2.x;
-              a1 = t2.y;
-            }
-          }
-          float a2 = __shfl_down_sync(0xffffffffu, a0, 1);
-          if (edge) {
-            a2 = 0.f;
-            if (ok) {
-              if (iw0 + 2 < p.W) a2 = load1(ci, ih, iw0 + 2);
-              else if (CIRC) a2 = load1(ci, ih, iw0 + 2 - p.W);
-            }
-          }
-          v[(ci * 3 + ky) * 3 + 0] = a0;
-          v[(ci * 3 + ky) * 3 + 1] = a1;
-          v[(ci * 3 + ky) * 3 + 2] = a2;
-        }
-      }
-    } else {
+      for (int ky = 0; ky < 3; ++ky) {
+        const int ih = 2 * ho + ky - p.in_lo;
+        const bool row_ok = valid && ih >= 0 && ih < p.H;
 #pragma unroll
-      for (int ci = 0; ci < 3; ++ci) {
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-          const int ih = 2 * ho + ky - p.in_lo;
-          const bool row_ok = valid && ih >= 0 && ih < p.H;
-#pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
-            int iw = 2 * wo + kx - p.in_lo;
-            bool ok = row_ok;
-            if (CIRC) iw = iw < 0 ? iw + p.W : (iw >= p.W ? iw - p.W : iw);
-            else ok = ok && iw >= 0 && iw < p.W;
-            v[(ci * 3 + ky) * 3 + kx] = ok ? load1(ci, ih, iw) : 0.f;
-          }
+        for (int kx = 0; kx < 3; ++kx) {
+          int iw = 2 * wo + kx - p.in_lo;
+          bool ok = row_ok;
+          if (CIRC) iw = iw < 0 ? iw + p.W : (iw >= p.W ? iw - p.W : iw);
+          else ok = ok && iw >= 0 && iw < p.W;
+          v[(ci * 3 + ky) * 3 + kx] = ok ? load1(ci, ih, iw) : 0.f;
         }
       }
     }
@@ -229,9 +192,6 @@ __global__ void __launch_bounds__(128) stem_tcgen05_kernel(const __grid_constant
 
 int stem_tcgen05(StemTcParams p, bool circular, bool u8, cudaStream_t st) {
   p.strips = (p.Wo + TC_BM - 1) / TC_BM;
-  // paired loads + neighbour-lane exchange need: no left padding, even row length (2 wo + 1 stays inside the row) and, for
-  // the fp32 image, 8-byte aligned rows
-  p.fast = (p.in_lo == 0 && p.W % 2 == 0 && p.Wo * 2 == p.W && (u8 || (reinterpret_cast<uintptr_t>(p.x) & 7u) == 0)) ? 1 : 0;
   const int64_t total = (int64_t)p.B * p.Ho * p.strips;
   if (total >= (1LL << 31)) return fail(CCVPE_ERR_BAD_ARGUMENT, "stem: too many tiles");
   p.total_tiles = (int)total;
