@@ -15,8 +15,10 @@ RUNS = [
     ("oxford_b1 (batch-1 sequential frames), 1 GPU", RUN + "_bench_oxford_b1.json"),
     ("train, B=8 bf16, one CUDA graph per step, 1 GPU", RUN + "_bench_train.json"),
     ("train, B=8 fp32 parity path (eager), 1 GPU", "r02f_bench_train_fp32.json"),
-    ("2 GPUs, weak (64 pairs per GPU)", "r02m_n2_weak.json"),
-    ("2 GPUs, strong (one batch of 64)", "r02m_n2_strong.json"),
+    ("2 GPUs, weak (64 pairs per GPU), final code", "r03q_n2_weak.json"),
+    ("2 GPUs, strong (one batch of 64), final code", "r03q_n2_strong.json"),
+    ("2 GPUs, weak (64 pairs per GPU), earlier in the round", "r02m_n2_weak.json"),
+    ("2 GPUs, strong (one batch of 64), earlier in the round", "r02m_n2_strong.json"),
     ("2 GPUs, train (graph)", "r02m_n2_train.json"),
     ("8 GPUs, weak (64 pairs per GPU)", "r02s_n8_weak.json"),
     ("8 GPUs, strong (one batch of 64: 8 pairs per GPU)", "r02s_n8_strong.json"),
