@@ -532,119 +532,10 @@ static bool dwt_plan(int K, int Ho, int Wo, int C, int B, DwTileParams* p) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Encoder stem: 3x3 stride-2 convolution over the fp32 NCHW image (3 channels, TensorFlow-"same" zero padding, optionally
-// circular along the width for panoramas) + folded-BN bias + SiLU, written as bf16 channels-last into the interior of the
-// first depthwise convolution's padded input image (wrap columns included for the circular encoder).  Replaces: dtype /
-// layout conversion of the image, two F.pad copies, cuDNN's conv + its own padding pass, and the bias/SiLU pass.
-// One thread = two horizontally adjacent output pixels x all CO output channels (weights broadcast from shared memory).
-// ---------------------------------------------------------------------------------------------------------------------
-// U8: the image arrives as uint8 NCHW [B, 3, H, Wsrc] and ToTensor + Normalize (v = u8 * sc[c] + sh[c]), the per-image
-// panorama roll (torch.roll along the width) and the FoV crop to the first W columns happen in the load (reference
-// train_VIGOR.py:55-70, 272-273; datasets.py:118) -- the f4 input pipeline fused into the first kernel of the encoder.
-struct StemU8 {
-  const uint8_t* x;
-  const int32_t* shift;      // [B] or NULL
-  int Wsrc;
-  float sc[3], sh[3];
-};
-
-template <int CO, bool CIRC, bool U8>
-__global__ void __launch_bounds__(128)
-stem_conv_silu_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                      __nv_bfloat16* __restrict__ out, int H, int W, int Ho, int Wo, int in_lo, int out_lo, int Hp, int Wp,
-                      const StemU8 u8) {
-  __shared__ __align__(16) float s_w[27 * CO];
-  __shared__ __align__(16) float s_b[CO];
-  for (int i = threadIdx.x; i < 27 * CO; i += blockDim.x) s_w[i] = w[i];
-  for (int i = threadIdx.x; i < CO; i += blockDim.x) s_b[i] = bias[i];
-  __syncthreads();
-  const int pw = blockIdx.x * blockDim.x + threadIdx.x;      // pair index along the output row
-  const int wo0 = 2 * pw;
-  if (wo0 >= Wo) return;
-  const int ho = blockIdx.y, b = blockIdx.z;
-  uint64_t acc[2][CO / 2];                                    // packed fp32 pairs over the output channels (FFMA2)
-#pragma unroll
-  for (int c = 0; c < CO / 2; ++c) acc[0][c] = acc[1][c] = pack_f32x2(s_b[2 * c], s_b[2 * c + 1]);
-  const float* xb = U8 ? nullptr : x + (int64_t)b * 3 * H * W;
-  const uint8_t* xb8 = U8 ? u8.x + (int64_t)b * 3 * H * u8.Wsrc : nullptr;
-  int roll = 0;
-  if (U8 && u8.shift) {
-    roll = u8.shift[b] % u8.Wsrc;
-    if (roll < 0) roll += u8.Wsrc;
-  }
-#pragma unroll 1
-  for (int ci = 0; ci < 3; ++ci) {
-#pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-      const int ih = 2 * ho + ky - in_lo;
-      uint64_t in[5];                                         // each input value broadcast into both halves of a pair
-#pragma unroll
-      for (int ix = 0; ix < 5; ++ix) {
-        int iw = 2 * wo0 + ix - in_lo;
-        bool ok = ih >= 0 && ih < H;
-        if (CIRC) iw = iw < 0 ? iw + W : (iw >= W ? iw - W : iw);
-        else ok = ok && iw >= 0 && iw < W;
-        float v = 0.f;
-        if (ok) {
-          if (U8) {
-            int ws = iw - roll;                    // torch.roll: out[w] = in[(w - shift) mod Wsrc]
-            if (ws < 0) ws += u8.Wsrc;
-            v = fmaf((float)__ldg(xb8 + ((int64_t)ci * H + ih) * u8.Wsrc + ws), u8.sc[ci], u8.sh[ci]);
-          } else {
-            v = __ldg(xb + ((int64_t)ci * H + ih) * W + iw);
-          }
-        }
-        in[ix] = pack_f32x2(v, v);
-      }
-#pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const float* wt = s_w + ((ci * 3 + ky) * 3 + kx) * CO;
-#pragma unroll
-        for (int c = 0; c < CO; c += 4) {
-          const float4 wv = *reinterpret_cast<const float4*>(wt + c);
-          const uint64_t w01 = pack_f32x2(wv.x, wv.y), w23 = pack_f32x2(wv.z, wv.w);
-          acc[0][c / 2] = ffma2(in[kx], w01, acc[0][c / 2]);
-          acc[0][c / 2 + 1] = ffma2(in[kx], w23, acc[0][c / 2 + 1]);
-          acc[1][c / 2] = ffma2(in[kx + 2], w01, acc[1][c / 2]);
-          acc[1][c / 2 + 1] = ffma2(in[kx + 2], w23, acc[1][c / 2 + 1]);
-        }
-      }
-    }
-  }
-  __nv_bfloat16* orow = out + ((int64_t)b * Hp + ho + out_lo) * Wp * CO;
-#pragma unroll
-  for (int t = 0; t < 2; ++t) {
-    const int wo = wo0 + t;
-    if (wo >= Wo) break;
-    uint4 q[CO / 8];
-    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(q);
-#pragma unroll
-    for (int c = 0; c < CO; c += 2) {
-      float a0, a1;
-      unpack_f32x2(acc[t][c >> 1], a0, a1);
-      a0 *= 0.5f;                                              // SiLU(a) = h + h * tanh(h), h = a / 2
-      a1 *= 0.5f;
-      h[c >> 1] = __floats2bfloat162_rn(fmaf(a0, dw_tanh(a0), a0), fmaf(a1, dw_tanh(a1), a1));
-    }
-    uint4* dst = reinterpret_cast<uint4*>(orow + (int64_t)(wo + out_lo) * CO);
-#pragma unroll
-    for (int i = 0; i < CO / 8; ++i) dst[i] = q[i];
-    if (CIRC) {   // wrap columns of the circularly padded image: [0, out_lo) <- last columns, [out_lo + Wo, Wp) <- first ones
-      const int hi = Wp - out_lo - Wo;
-      if (wo >= Wo - out_lo) {
-        uint4* d2 = reinterpret_cast<uint4*>(orow + (int64_t)(wo - (Wo - out_lo)) * CO);
-#pragma unroll
-        for (int i = 0; i < CO / 8; ++i) d2[i] = q[i];
-      }
-      if (wo < hi) {
-        uint4* d2 = reinterpret_cast<uint4*>(orow + (int64_t)(out_lo + Wo + wo) * CO);
-#pragma unroll
-        for (int i = 0; i < CO / 8; ++i) d2[i] = q[i];
-      }
-    }
-  }
-}
-
+// Encoder stem: see stem_tcgen05.cu (3x3 stride-2 convolution over the planar fp32 / uint8 image as an implicit GEMM on the
+// tensor cores + folded-BN bias + SiLU, written as bf16 channels-last into the interior of the first depthwise
+// convolution's padded input image, wrap columns included for the circular encoder).  The CUDA-core kernel that used to
+// live here (864 packed FMAs per pixel pair, 0.29 + 0.32 ms per step) was retired in round 2.
 // ---------------------------------------------------------------------------------------------------------------------
 // Squeeze-excite gate folded into the projection weights, one launch per MBConv block:
 //     mean[b, m]   = chan_sum[b, m] * inv_hw
@@ -876,28 +767,14 @@ extern "C" int ccvpe_stem_conv_silu_nhwc(const float* x, int B, int H, int W, co
                 "ccvpe_stem_conv_silu_nhwc: bad padding");
   CCVPE_REQUIRE(aligned16(out), "ccvpe_stem_conv_silu_nhwc: out must be 16-byte aligned");
   const int Ho = (H + in_pad_lo + in_pad_hi - 3) / 2 + 1, Wo = (W + in_pad_lo + in_pad_hi - 3) / 2 + 1;
-  CCVPE_REQUIRE(Ho <= 65535, "ccvpe_stem_conv_silu_nhwc: image too tall");
   CCVPE_REQUIRE(!circular || (out_pad_lo <= Wo && out_pad_hi <= Wo), "ccvpe_stem_conv_silu_nhwc: wrap wider than the image");
   const int Hp = Ho + out_pad_lo + out_pad_hi, Wp = Wo + out_pad_lo + out_pad_hi;
-  const int pairs = (Wo + 1) / 2;
-  const dim3 grid((pairs + 127) / 128, Ho, B);
   cudaStream_t st = (cudaStream_t)stream;
-  static const int stem_tc = getenv("CCVPE_STEM_TC") ? atoi(getenv("CCVPE_STEM_TC")) : 1;   // development switch: 0 = CUDA-core kernel
-  if (stem_tc) {
-    StemTcParams tp;
-    memset(&tp, 0, sizeof(tp));
-    tp.x = x; tp.w = w; tp.bias = bias; tp.out = (__nv_bfloat16*)out;
-    tp.B = B; tp.H = H; tp.W = W; tp.Ho = Ho; tp.Wo = Wo; tp.in_lo = in_pad_lo; tp.out_lo = out_pad_lo; tp.Hp = Hp; tp.Wp = Wp;
-    return stem_tcgen05(tp, circular != 0, false, st);
-  }
-  StemU8 none;
-  memset(&none, 0, sizeof(none));
-  if (circular)
-    stem_conv_silu_kernel<32, true, false><<<grid, 128, 0, st>>>(x, w, bias, (__nv_bfloat16*)out, H, W, Ho, Wo, in_pad_lo, out_pad_lo, Hp, Wp, none);
-  else
-    stem_conv_silu_kernel<32, false, false><<<grid, 128, 0, st>>>(x, w, bias, (__nv_bfloat16*)out, H, W, Ho, Wo, in_pad_lo, out_pad_lo, Hp, Wp, none);
-  CCVPE_LAUNCH_CHECK("stem_conv_silu_kernel");
-  return CCVPE_OK;
+  StemTcParams tp;
+  memset(&tp, 0, sizeof(tp));
+  tp.x = x; tp.w = w; tp.bias = bias; tp.out = (__nv_bfloat16*)out;
+  tp.B = B; tp.H = H; tp.W = W; tp.Ho = Ho; tp.Wo = Wo; tp.in_lo = in_pad_lo; tp.out_lo = out_pad_lo; tp.Hp = Hp; tp.Wp = Wp;
+  return stem_tcgen05(tp, circular != 0, false, st);
 }
 
 extern "C" int ccvpe_stem_conv_silu_u8_nhwc(const uint8_t* x, int B, int H, int Wsrc, int crop_w, const int32_t* shift,
@@ -914,39 +791,18 @@ extern "C" int ccvpe_stem_conv_silu_u8_nhwc(const uint8_t* x, int B, int H, int 
                 "ccvpe_stem_conv_silu_u8_nhwc: bad padding");
   CCVPE_REQUIRE(aligned16(out), "ccvpe_stem_conv_silu_u8_nhwc: out must be 16-byte aligned");
   const int Ho = (H + in_pad_lo + in_pad_hi - 3) / 2 + 1, Wo = (W + in_pad_lo + in_pad_hi - 3) / 2 + 1;
-  CCVPE_REQUIRE(Ho <= 65535, "ccvpe_stem_conv_silu_u8_nhwc: image too tall");
   CCVPE_REQUIRE(!circular || (out_pad_lo <= Wo && out_pad_hi <= Wo), "ccvpe_stem_conv_silu_u8_nhwc: wrap wider than the image");
   const int Hp = Ho + out_pad_lo + out_pad_hi, Wp = Wo + out_pad_lo + out_pad_hi;
-  const int pairs = (Wo + 1) / 2;
-  const dim3 grid((pairs + 127) / 128, Ho, B);
-  StemU8 u;
-  u.x = x;
-  u.shift = shift;
-  u.Wsrc = Wsrc;
+  StemTcParams tp;
+  memset(&tp, 0, sizeof(tp));
+  tp.x8 = x; tp.shift = shift; tp.Wsrc = Wsrc;
   for (int c = 0; c < 3; ++c) {           // (u8 / 255 - mean) / std  ==  u8 * sc + sh
-    u.sc[c] = 1.f / (255.f * std_host[c]);
-    u.sh[c] = -mean_host[c] / std_host[c];
+    tp.sc[c] = 1.f / (255.f * std_host[c]);
+    tp.sh[c] = -mean_host[c] / std_host[c];
   }
-  cudaStream_t st = (cudaStream_t)stream;
-  static const int stem_tc = getenv("CCVPE_STEM_TC") ? atoi(getenv("CCVPE_STEM_TC")) : 1;   // development switch: 0 = CUDA-core kernel
-  if (stem_tc) {
-    StemTcParams tp;
-    memset(&tp, 0, sizeof(tp));
-    tp.x8 = x; tp.shift = shift; tp.Wsrc = Wsrc;
-    for (int c = 0; c < 3; ++c) {
-      tp.sc[c] = u.sc[c];
-      tp.sh[c] = u.sh[c];
-    }
-    tp.w = w; tp.bias = bias; tp.out = (__nv_bfloat16*)out;
-    tp.B = B; tp.H = H; tp.W = W; tp.Ho = Ho; tp.Wo = Wo; tp.in_lo = in_pad_lo; tp.out_lo = out_pad_lo; tp.Hp = Hp; tp.Wp = Wp;
-    return stem_tcgen05(tp, circular != 0, true, st);
-  }
-  if (circular)
-    stem_conv_silu_kernel<32, true, true><<<grid, 128, 0, st>>>(nullptr, w, bias, (__nv_bfloat16*)out, H, W, Ho, Wo, in_pad_lo, out_pad_lo, Hp, Wp, u);
-  else
-    stem_conv_silu_kernel<32, false, true><<<grid, 128, 0, st>>>(nullptr, w, bias, (__nv_bfloat16*)out, H, W, Ho, Wo, in_pad_lo, out_pad_lo, Hp, Wp, u);
-  CCVPE_LAUNCH_CHECK("stem_conv_silu_kernel");
-  return CCVPE_OK;
+  tp.w = w; tp.bias = bias; tp.out = (__nv_bfloat16*)out;
+  tp.B = B; tp.H = H; tp.W = W; tp.Ho = Ho; tp.Wo = Wo; tp.in_lo = in_pad_lo; tp.out_lo = out_pad_lo; tp.Hp = Hp; tp.Wp = Wp;
+  return stem_tcgen05(tp, circular != 0, true, (cudaStream_t)stream);
 }
 
 extern "C" int ccvpe_pointwise_silu_nhwc(const void* x, int B, int H, int W, int K, int ldx, const void* w_nk,
