@@ -20,8 +20,10 @@ RUNS = [
     ("2 GPUs, weak (64 pairs per GPU), earlier in the round", "r02m_n2_weak.json"),
     ("2 GPUs, strong (one batch of 64), earlier in the round", "r02m_n2_strong.json"),
     ("2 GPUs, train (graph)", "r02m_n2_train.json"),
-    ("8 GPUs, weak (64 pairs per GPU)", "r02s_n8_weak.json"),
-    ("8 GPUs, strong (one batch of 64: 8 pairs per GPU)", "r02s_n8_strong.json"),
+    ("8 GPUs, weak (64 pairs per GPU), final code", "r03s_n8_weak.json"),
+    ("8 GPUs, strong (one batch of 64: 8 pairs per GPU), final code", "r03s_n8_strong.json"),
+    ("8 GPUs, weak (64 pairs per GPU), earlier in the round", "r02s_n8_weak.json"),
+    ("8 GPUs, strong (one batch of 64: 8 pairs per GPU), earlier in the round", "r02s_n8_strong.json"),
     ("8 GPUs, train (B=8 per GPU, graph)", "r02t_n8_train.json"),
 ]
 
@@ -34,8 +36,8 @@ def load(name):
 
 
 out = ["# Bench lines recorded in round 2 (B200; the full JSON lines live under gpurun_out/, which is not tracked)",
-       "Single-GPU lines: run %s (final code of the round); multi-GPU lines: earlier runs of the round (r02m / r02s / r02t, before the"
-       % RUN, "halo convolution and this session's encoder / ring / stem kernels).", ""]
+       "Single-GPU lines: run %s (final code of the round); 2- and 8-GPU inference lines: runs r03q / r03s (final code); the multi-GPU"
+       % RUN, "training lines are earlier runs of the round (r02m / r02t).", ""]
 for tag, f in RUNS:
     d = load(f)
     if not d:
