@@ -459,7 +459,15 @@ int match_tcgen05(const void* x, int B, int HW, int C, const float* g, int L, in
   // ~52 KB of pipeline per CTA so that four CTAs (16 norm/epilogue warps) share an SM: the epilogue is scalar-ALU and
   // store bound and needs the extra warps to hide its own latency (windowed: three CTAs per SM, each with up to 24 KB of
   // prefix-sum snapshots behind its ring)
-  int stages = (52 * 1024) / p.stage_bytes;
+  // The coarse levels have fewer tiles than the GPU has CTA slots (level 1 of a batch of 64: 64 tiles of 20 K blocks): there
+  // a CTA is alone on its SM and a two-stage ring exposes the full load latency on every K block (52 us for 42 MB) -- give
+  // it the ring depth the empty SM can afford instead.
+  const int per_sm_max = windowed ? 3 : 4;
+  int ctas_needed = (p.total_tiles + sm_count() - 1) / sm_count();
+  if (ctas_needed > per_sm_max) ctas_needed = per_sm_max;
+  const int snap_bytes = windowed ? (n_events > 0 ? n_events : 1) * TC_BM * 4 : 0;
+  const int budget = ctas_needed >= per_sm_max ? 52 * 1024 : (160 * 1024) / ctas_needed - snap_bytes;
+  int stages = budget / p.stage_bytes;
   if (stages < 2) stages = 2;
   p.stages = stages > MT_MAX_STAGES ? MT_MAX_STAGES : stages;
   p.n_rolls = n_rolls;
