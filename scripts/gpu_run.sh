@@ -44,6 +44,7 @@ for w in $what; do
     ncu_project) timeout 600 ncu --set full --clock-control none --import-source on -k regex:project_tcgen05 -s 4 -c 1 -o gpurun_out/${tag}_prof_project python scripts/bench_encoder_ops.py project 64 12800 144 24 1 > gpurun_out/${tag}_ncu_project.log 2>&1; tail -2 gpurun_out/${tag}_ncu_project.log | cut -c1-200;;
     ncu_halo3) timeout 600 ncu --set full --clock-control none --import-source on -k regex:igemm_tcgen05 -s 6 -c 1 -o gpurun_out/${tag}_prof_igemm_halo3 python scripts/bench_igemm.py conv 16 80 24 80 128 > gpurun_out/${tag}_ncu_halo3.log 2>&1; tail -2 gpurun_out/${tag}_ncu_halo3.log | cut -c1-200;;
     stem_ab) for f in 0 1; do echo "CCVPE_STEM_FAST=$f"; for a in "stem 64 512 512 0 0" "stem 64 320 640 1 0" "stem 64 512 512 0 1" "stem 64 320 640 1 1" "stem 64 320 640 0 0" "stem 64 256 1024 0 0"; do CCVPE_STEM_FAST=$f timeout 120 python scripts/bench_encoder_ops.py $a 2>&1 | tail -1; done; done | tee gpurun_out/${tag}_stem_ab.txt;;
+    ncu_match1) timeout 600 ncu --set full --clock-control none --import-source on -k regex:match_tcgen05 -s 4 -c 1 -o gpurun_out/${tag}_prof_match1 python scripts/bench_match.py 64 1280 8 20 64 tc > gpurun_out/${tag}_ncu_match1.log 2>&1; tail -2 gpurun_out/${tag}_ncu_match1.log | cut -c1-200; timeout 120 python scripts/bench_match.py 64 1280 8 20 64 tc | tail -1; timeout 120 python scripts/bench_match.py 1 1280 8 20 64 tc | tail -1;;
     wgrad_halo) CCVPE_WGRAD_HALO=1 timeout 300 python -m pytest tests/test_gpu_train.py -m gpu -q -k "wgrad_conv3x3_tcgen05" 2>&1 | tail -3; CCVPE_WGRAD_HALO=0 timeout 300 python -m pytest tests/test_gpu_train.py -m gpu -q -k "wgrad_conv3x3_tcgen05" 2>&1 | tail -3;;
     *) echo "unknown step $w";;
   esac
