@@ -254,8 +254,10 @@ extern "C" int ccvpe_mbconv_project_nhwc(const void* d, const void* wg, const vo
   p.stage_bytes = p.a_bytes + (p.block_n * p.kw * 2 + 1023) / 1024 * 1024;
   p.stages = PJ_SMEM_BUDGET / p.stage_bytes;
   if (p.stages > PJ_MAX_STAGES) p.stages = PJ_MAX_STAGES;
+  // two accumulator stages; the epilogue reads whole 32-column chunks, so the second stage's last chunk may reach up to
+  // block_n + 32 columns past the first stage's start: keep that inside the allocation (matters for block_n = 16)
   p.tmem_cols = 32;
-  while (p.tmem_cols < 2 * p.block_n) p.tmem_cols <<= 1;
+  while (p.tmem_cols < 2 * p.block_n || p.tmem_cols < p.block_n + ((p.block_n + 31) / 32) * 32) p.tmem_cols <<= 1;
   p.res = (const __nv_bfloat16*)residual;
   p.bias = (const __nv_bfloat16*)bias;
   p.out = (__nv_bfloat16*)out;
