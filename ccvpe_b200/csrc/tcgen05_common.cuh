@@ -468,8 +468,11 @@ inline int tc_block_width(int c) {
   static const bool old_rule = getenv("CCVPE_KW_OLD") != nullptr;   // development switch: A/B against the round-1 rule
   return c <= 16 ? 16 : (c < (old_rule ? 64 : 33) ? 32 : 64);
 }
-// the matching kernel's norm warps were tuned against the original rule
-inline int tc_block_width_match(int c) { return c <= 16 ? 16 : (c < 64 ? 32 : 64); }
+// the matching kernel (same rule; CCVPE_MATCH_KW_OLD restores two 32-wide blocks for 33..63 channels: development switch)
+inline int tc_block_width_match(int c) {
+  static const bool old_rule = getenv("CCVPE_MATCH_KW_OLD") != nullptr;
+  return c <= 16 ? 16 : (c < (old_rule ? 64 : 33) ? 32 : 64);
+}
 
 inline void fill_epi(EpiParams& e, const ccvpe_igemm_desc& d) {
   e.N = d.N;
